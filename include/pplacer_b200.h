@@ -1,0 +1,180 @@
+/* pplacer_b200 — C ABI of libpplacer_b200.so: the B200-native (sm_100a) implementation of
+ * pplacer's per-query placement hot path.
+ *
+ * This header is the drop-in boundary.  Plain C, plain pointers and sizes, caller-owned HOST
+ * buffers unless a function says "device".  It replaces, for this path, what the reference binds
+ * through OCaml `external`s to pplacer_src/linear_c.c (declared in pplacer_src/linear.ml:13-89)
+ * plus the OCaml loops that call them; INTEGRATION.md shows the OCaml stub a maintainer adds.
+ *
+ *   reference interface replaced                          entry point here
+ *   ---------------------------------------------------   ---------------------------------
+ *   Model.build / Diagd / Gamma          (gmix_model.ml:25-39, gcat_model.ml:52-69,
+ *                                         diagd.ml:169, gamma.ml:52)        pp_create
+ *   Like_stree.calc_distal_and_proximal + pull(-10) + Glv_arr.prep_supernodes
+ *                                        (pplacer_run.ml:322-340)           pp_precompute
+ *   darr / parr / snodes Bigarrays       (pplacer_run.ml:289-309)           pp_export_glvs
+ *   Core.pplacer_core (name, seq) -> result list   (core.ml:76,113-409)     pp_place
+ *   Glv.masked_logdot over all edges     (core.ml:187-194; linear_c.c:251,465)   pp_prefilter_scores
+ *   Three_tax.log_like                   (three_tax.ml:30-36; linear_c.c:170,367) pp_three_tax_log_like
+ *   Model.evolve_into                    (gmix_model.ml:308, gcat_model.ml:327;
+ *                                         linear_c.c:29,92)                 pp_evolve
+ *   Gamma.discrete_gamma                 (gamma.ml:52)                      pp_discrete_gamma
+ *   Diagd.normed_of_exchangeable_pair    (diagd.ml:169)                     pp_diagd
+ *
+ * Every function returns 0 on success or a PP_E* code; pp_last_error() gives the message for the
+ * calling thread.  There is NO CPU fallback: without a CUDA device every compute entry point
+ * fails with PP_ENODEVICE.
+ */
+#ifndef PPLACER_B200_H
+#define PPLACER_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_ABI_VERSION 1
+
+/* error codes */
+enum {
+  PP_OK = 0,
+  PP_EINVAL = 1,     /* bad argument */
+  PP_ENODEVICE = 2,  /* no CUDA device / driver */
+  PP_ECUDA = 3,      /* CUDA runtime error (message in pp_last_error) */
+  PP_ENOMEM = 4,
+  PP_ESTATE = 5      /* call order (e.g. pp_place before pp_precompute) */
+};
+
+/* per-query status written by pp_place (0 = placed).  The GSL-like codes are handled inside the
+ * path exactly as core.ml:272-297 does (retry from defaults, then skip the location); a query
+ * status is non-zero only where the reference would abort the run or produce no placement. */
+enum {
+  PP_Q_OK = 0,
+  PP_Q_NO_INFORMATIVE = 103,   /* core.ml:157: "has no informative sites" */
+  PP_Q_EMPTY_RESULTS = 104,    /* core.ml:323 */
+  PP_Q_BAD_CHAR = 105,         /* character outside nuc_models.ml:28-45 / prot_models.ml:5,40-44 */
+  PP_Q_FIND_START_FAILURE = 101, /* Minimization.FindStartFailure  (uncaught in the reference) */
+  PP_Q_INVALID_START = 102,      /* Minimization.InvalidStartValues (uncaught in the reference) */
+  PP_Q_PP_FAILED = 107           /* find_upper_limit raised ExceededMaxIter (three_tax.ml:154) */
+};
+
+/* Substitution model inputs (what Model.build consumes, glvm.ml:5-9). */
+typedef struct pp_model {
+  int32_t n_states;     /* 4 (nucleotide) or 20 (amino acid) */
+  int32_t model_class;  /* 0 = Gmix_model (Gamma mixture), 1 = Gcat_model (per-site CAT) */
+  int32_t n_rates;      /* Gamma categories, or number of CAT rate categories */
+  int32_t _pad;
+  const double *exch;   /* [S*S] symmetric exchangeabilities, diagonal ignored (GTR: nuc_models.ml:78; LG/WAG/JTT) */
+  const double *statd;  /* [S] stationary distribution, or NULL = empirical from statd_chars (alignment.ml:186) */
+  const uint8_t *statd_chars; /* UN-premasked reference alignment characters, used when statd == NULL */
+  int64_t n_statd_chars;
+  const double *rates;  /* [n_rates] explicit rates (CAT), or NULL = discrete_gamma(n_rates, gamma_alpha) */
+  double gamma_alpha;
+  const int32_t *site_cat; /* Gcat: [L] zero-based category per (pre-masked) site; NULL for Gmix */
+} pp_model;
+
+/* Reference tree: node ids exactly as numbered by the reference's Newick parser (post-order,
+ * newick_parser.mly:49-62) = jplace edge numbers.  Children in CSR form, in Newick order. */
+typedef struct pp_tree {
+  int32_t n_nodes;          /* E + 1 */
+  int32_t root_id;
+  const int32_t *child_ptr; /* [n_nodes + 1] */
+  const int32_t *child_idx; /* [child_ptr[n_nodes]] */
+  const double *bl;         /* [n_nodes]; root 0 (newick_gtree.ml:145-157) */
+  const int32_t *leaf_row;  /* [n_nodes] row of ref_chars for leaves, -1 otherwise */
+} pp_tree;
+
+/* Prefs fields on this path (prefs.ml:65-120; core.ml:10,14). */
+typedef struct pp_prefs {
+  double start_pend;        /* 0.1  */
+  double max_pend;          /* 2.0  */
+  double initial_tolerance; /* 0.01 */
+  double final_tolerance;   /* 1e-5 */
+  int32_t max_iter;         /* 200  */
+  int32_t max_strikes;      /* 6  (0 = evaluate every edge) */
+  double strike_box;        /* 3.0  */
+  int32_t max_pitches;      /* 40   */
+  int32_t keep_at_most;     /* 7    */
+  double keep_factor;       /* 0.01 */
+  int32_t calc_pp;          /* 0    (-p sets 1 and keep_at_most 20, keep_factor 0.001, max_strikes 20) */
+  int32_t prior_kind;       /* 0 uniform, 1 flat exponential, 2 informative exponential */
+  double pp_rel_err;        /* 0.01 */
+  double prior_mean;        /* flat prior mean = tree length / n_edges (pplacer_run.ml:387-390) */
+  const double *prior_means;/* [n_nodes] informative prior means (core.ml:34-52) or NULL */
+} pp_prefs;
+
+/* One placement (core.ml:370-404, placement.ml:50-65). */
+typedef struct pp_result {
+  int32_t edge;       /* location = jplace edge_num */
+  int32_t _pad;
+  double log_like;    /* "likelihood" */
+  double pendant;     /* pendant_length */
+  double distal;      /* distal_length */
+  double ml_ratio;    /* like_weight_ratio */
+  double marginal_like; /* NaN unless calc_pp */
+  double post_prob;     /* NaN unless calc_pp */
+} pp_result;
+
+/* Optional stage outputs of pp_place for parity tests / --timing (any pointer may be NULL). */
+typedef struct pp_debug {
+  double *scores;        /* [Q * n_nodes] prefilter score per edge, NaN at the root */
+  int32_t *n_pitches;    /* [Q] number of baseball results */
+  int32_t *pitch_edges;  /* [Q * (max_pitches+1)] in play order */
+  double *pitch_ll, *pitch_pend, *pitch_dist; /* [Q * (max_pitches+1)] */
+  int64_t *n_like_calls; /* [Q] objective evaluations (three_tax.ml:8) */
+  double *timing;        /* [4] seconds: ranking, ML calculation, PP calculation, query prep (core.ml timers) */
+} pp_debug;
+
+typedef struct pp_ctx pp_ctx;
+
+const char *pp_last_error(void);
+int pp_abi_version(void);
+void pp_default_prefs(pp_prefs *);
+
+/* Builds the model (a2, a3), uploads tree / alignment, allocates darr, parr, snodes on `device`. */
+int pp_create(const pp_model *, const pp_tree *, const uint8_t *ref_chars /* n_leaves x L, uppercase, pre-masked */,
+              int32_t n_leaves, int32_t L, int32_t device, pp_ctx **out);
+void pp_destroy(pp_ctx *);
+/* a4-a9 on device (level-order pruning, exponent pulls at -50 then -10, supernodes). */
+int pp_precompute(pp_ctx *);
+/* Copy GLVs [node_begin, node_end) of darr (which=0) / parr (1) / snodes (2) back in the REFERENCE
+ * layout: Gmix a[R][L][S], Gcat a[L][S] per node (linear_c.c:5-12); e[L] as int64 per node. */
+int pp_export_glvs(pp_ctx *, int32_t which, int32_t node_begin, int32_t node_end, double *a, int64_t *e);
+/* Model numerics as built (statd[S], x[S*S], lambda[S], xit[S*S], rates[R]); any may be NULL. */
+int pp_get_model(pp_ctx *, double *statd, double *x, double *lambda, double *xit, double *rates);
+
+/* The path: place Q pre-masked, upper-cased queries (Q x L chars).  out is Q x keep_at_most. */
+int pp_place(pp_ctx *, const pp_prefs *, int64_t Q, const uint8_t *query_chars, pp_result *out,
+             int32_t *n_out, int32_t *status, pp_debug *dbg_or_null);
+
+/* Same work with inputs/outputs already resident in HBM (device pointers): used to time the
+ * kernels without host<->device copies.  d_out: Q x keep_at_most pp_result, d_n_out/d_status: Q. */
+int pp_place_device(pp_ctx *, const pp_prefs *, int64_t Q, const uint8_t *d_query_chars, pp_result *d_out,
+                    int32_t *d_n_out, int32_t *d_status);
+
+/* Stage-level entry points (host buffers) for parity tests against the oracle / linear_c.c. */
+int pp_prefilter_scores(pp_ctx *, double start_pend, int64_t Q, const uint8_t *query_chars,
+                        double *scores /* Q x n_nodes, NaN at root */, int32_t kernel /* 0 default, 1 direct-FMA, 2 table */);
+int pp_three_tax_log_like(pp_ctx *, int64_t n, const uint8_t *query_chars /* n x L */, const int32_t *edge,
+                          const double *pendant, const double *distal, double *ll_out);
+/* dst = evolve(src, bl) on GLVs given in the reference layout (n_sites sites; Gcat uses site_cat of
+ * the first n_sites sites). */
+int pp_evolve(pp_ctx *, const double *src_a, const int64_t *src_e, int32_t n_sites, double bl, double *dst_a,
+              int64_t *dst_e);
+
+/* Host numerics exposed for tests. */
+int pp_discrete_gamma(int32_t n_cat, double alpha, double *rates_out);
+int pp_diagd(int32_t S, const double *exch, const double *pi, double *x, double *lambda, double *xit);
+int pp_emper_freq(int32_t S, const uint8_t *chars, int64_t n, double *out);
+
+/* Counters for bench.py: kernels launched by this library on this context since the last reset,
+ * and accumulated device time (ms, CUDA events) of the named phase kernels. */
+int64_t pp_kernel_launches(pp_ctx *, int32_t reset);
+int pp_phase_times_ms(pp_ctx *, double *out4 /* prefilter, rank, optimise, pp */, int32_t reset);
+/* FP64 FMA micro-benchmark on the context's device: returns measured DFMA throughput in TFLOP/s. */
+int pp_measure_fp64_peak(pp_ctx *, double *tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
