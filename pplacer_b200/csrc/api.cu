@@ -1,0 +1,787 @@
+// libpplacer_b200.so — context, host orchestration and the C ABI (include/pplacer_b200.h).
+// Host-side control flow mirrors Pplacer_run.run_placements (pplacer_src/pplacer_run.ml:289-340)
+// for the precompute and Core.pplacer_core (pplacer_src/core.ml:113-409) for the per-query path,
+// batched over queries.  All arithmetic runs in the CUDA kernels of this directory; there is no
+// CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_segmented_sort.cuh>
+
+#include "../../include/pplacer_b200.h"
+#include "baseball.cuh"
+#include "device_common.cuh"
+#include "model_host.hpp"
+#include "precompute.cuh"
+#include "query.cuh"
+#include "threetax.cuh"
+
+using namespace ppb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      return fail(e_ == cudaErrorMemoryAllocation ? PP_ENOMEM : PP_ECUDA,                          \
+                  std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" +         \
+                      std::to_string(__LINE__) + ")");                                             \
+    }                                                                                              \
+  } while (0)
+
+// (S, GCAT) dispatch for the templated kernels
+#define DISPATCH_MODEL(ctx, ...)                                          \
+  do {                                                                    \
+    if ((ctx)->S == 4 && !(ctx)->gcat) { constexpr int S_ = 4; constexpr bool G_ = false; __VA_ARGS__; }       \
+    else if ((ctx)->S == 4 && (ctx)->gcat) { constexpr int S_ = 4; constexpr bool G_ = true; __VA_ARGS__; }    \
+    else if ((ctx)->S == 20 && !(ctx)->gcat) { constexpr int S_ = 20; constexpr bool G_ = false; __VA_ARGS__; }\
+    else { constexpr int S_ = 20; constexpr bool G_ = true; __VA_ARGS__; }                                     \
+  } while (0)
+
+namespace {
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  int ensure(size_t want) {
+    if (want <= n) return PP_OK;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    size_t cap = want + want / 8 + 16;
+    cudaError_t e = cudaMalloc(&p, cap * sizeof(T));
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(PP_ENOMEM, std::string("cudaMalloc of ") + std::to_string(cap * sizeof(T)) + " bytes: " + cudaGetErrorString(e)); }
+    n = cap;
+    return PP_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+constexpr int kTTThreadsDNA = 128;
+constexpr int kTTThreadsAA = 256;
+
+}  // namespace
+
+struct pp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  Alphabet al;
+  DevModel hm;
+  DevModel *dm = nullptr;
+  int S = 0, R = 0, Rg = 0, K = 0, gcat = 0, L = 0, Lp = 0, n_nodes = 0, root_id = 0, n_leaves = 0;
+  std::vector<int32_t> child_ptr, child_idx, parent, leaf_row, depth;
+  std::vector<double> bl;
+  GlvArrays g{};
+  TreeDev t{};
+  double *d_bl = nullptr;
+  uint8_t *d_code_of_char = nullptr, *d_ref_codes = nullptr;
+  int32_t *d_site_cat = nullptr, *d_child_ptr = nullptr, *d_child_idx = nullptr, *d_parent = nullptr, *d_leaf_row = nullptr;
+  bool precomputed = false;
+  // workspace
+  DevBuf<uint8_t> chars, codes, sort_tmp;
+  DevBuf<int32_t> qsite, nq, prep_status, rank_in, rank_loc, seg_off, i32pool, n_out;
+  DevBuf<double> Tq, scores, keys_in, keys_out, wbuf, f64pool;
+  DevBuf<CandIn> cand;
+  DevBuf<CandOut> cand_out, pp_out;
+  DevBuf<PlaceOut> place_out;
+  DevBuf<int64_t> n_calls;
+  DevBuf<int> counters;  // [0] queue head, [1] wave count, [2] active queries, [3] keep count
+  int *h_counters = nullptr;  // pinned
+  int64_t launches = 0;
+  double phase_ms[4] = {0, 0, 0, 0};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  int tt_blocks = 0;
+  size_t tt_smem = 0;
+};
+
+static int tt_threads(const pp_ctx *c) { return c->S == 4 ? kTTThreadsDNA : kTTThreadsAA; }
+
+template <int S, bool G>
+static size_t tt_smem_bytes(const pp_ctx *c) {
+  if (S == 4) return ThreeTax<S, G, kTTThreadsDNA>::smem_doubles(c->R, c->al.n_codes) * sizeof(double);
+  return ThreeTax<S, G, kTTThreadsAA>::smem_doubles(c->R, c->al.n_codes) * sizeof(double);
+}
+
+extern "C" const char *pp_last_error(void) { return g_err.c_str(); }
+extern "C" int pp_abi_version(void) { return PP_ABI_VERSION; }
+
+extern "C" void pp_default_prefs(pp_prefs *p) {
+  std::memset(p, 0, sizeof *p);
+  p->start_pend = 0.1; p->max_pend = 2.0; p->initial_tolerance = 0.01; p->final_tolerance = 1e-5;
+  p->max_iter = 200; p->max_strikes = 6; p->strike_box = 3.0; p->max_pitches = 40; p->keep_at_most = 7;
+  p->keep_factor = 0.01; p->calc_pp = 0; p->prior_kind = 1; p->pp_rel_err = 0.01; p->prior_mean = 1.0;
+  p->prior_means = nullptr;
+}
+
+extern "C" int pp_discrete_gamma(int32_t n_cat, double alpha, double *out) {
+  if (n_cat < 1 || !(alpha > 0) || !out) return fail(PP_EINVAL, "pp_discrete_gamma: bad arguments");
+  discrete_gamma(n_cat, alpha, out);
+  return PP_OK;
+}
+extern "C" int pp_diagd(int32_t S, const double *exch, const double *pi, double *x, double *lambda, double *xit) {
+  if (S < 2 || S > kMaxStates) return fail(PP_EINVAL, "pp_diagd: bad S");
+  diagd_normed(S, exch, pi, x, lambda, xit);
+  return PP_OK;
+}
+extern "C" int pp_emper_freq(int32_t S, const uint8_t *chars, int64_t n, double *out) {
+  if (S != 4 && S != 20) return fail(PP_EINVAL, "pp_emper_freq: S must be 4 or 20");
+  if (!emper_freq(S, chars, n, out)) return fail(PP_EINVAL, "pp_emper_freq: unknown base in alignment");
+  return PP_OK;
+}
+
+template <class T>
+static int upload(T **dst, const T *src, size_t n) {
+  CK(cudaMalloc(dst, std::max<size_t>(n, 1) * sizeof(T)));
+  if (n) CK(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return PP_OK;
+}
+
+extern "C" void pp_destroy(pp_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int w = 0; w < 3; ++w) { if (c->g.a[w]) cudaFree(c->g.a[w]); if (c->g.e[w]) cudaFree(c->g.e[w]); }
+  void *ptrs[] = {c->dm, c->d_bl, c->d_code_of_char, c->d_ref_codes, c->d_site_cat, c->d_child_ptr, c->d_child_idx, c->d_parent, c->d_leaf_row};
+  for (void *p : ptrs) if (p) cudaFree(p);
+  c->chars.release(); c->codes.release(); c->sort_tmp.release(); c->qsite.release(); c->nq.release();
+  c->prep_status.release(); c->rank_in.release(); c->rank_loc.release(); c->seg_off.release(); c->i32pool.release();
+  c->n_out.release(); c->Tq.release(); c->scores.release(); c->keys_in.release(); c->keys_out.release();
+  c->wbuf.release(); c->f64pool.release(); c->cand.release(); c->cand_out.release(); c->pp_out.release();
+  c->place_out.release(); c->n_calls.release(); c->counters.release();
+  if (c->h_counters) cudaFreeHost(c->h_counters);
+  if (c->ev[0]) cudaEventDestroy(c->ev[0]);
+  if (c->ev[1]) cudaEventDestroy(c->ev[1]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref_chars, int32_t n_leaves, int32_t L,
+                         int32_t device, pp_ctx **out) {
+  if (!m || !t || !ref_chars || !out) return fail(PP_EINVAL, "pp_create: null argument");
+  *out = nullptr;
+  if (m->n_states != 4 && m->n_states != 20) return fail(PP_EINVAL, "pp_create: n_states must be 4 or 20");
+  if (m->n_rates < 1 || m->n_rates > kMaxRates) return fail(PP_EINVAL, "pp_create: n_rates out of range");
+  if (m->model_class == 1 && (!m->site_cat || !m->rates)) return fail(PP_EINVAL, "pp_create: Gcat needs rates and site_cat");
+  if (L < 1 || t->n_nodes < 2) return fail(PP_EINVAL, "pp_create: empty problem");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(PP_ENODEVICE, "pp_create: no CUDA device (libpplacer_b200 has no CPU fallback)"); }
+  if (device < 0 || device >= ndev) return fail(PP_EINVAL, "pp_create: bad device index");
+  CK(cudaSetDevice(device));
+  pp_ctx *c = new pp_ctx();
+  c->device = device;
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  c->S = m->n_states; c->gcat = m->model_class ? 1 : 0; c->R = m->n_rates; c->Rg = c->gcat ? 1 : c->R; c->K = c->Rg * c->S;
+  c->L = L; c->Lp = (L + 31) / 32 * 32; c->n_nodes = t->n_nodes; c->root_id = t->root_id; c->n_leaves = n_leaves;
+  c->al = make_alphabet(c->S);
+  // ---- model numerics (a2, a3) ----
+  DevModel &hm = c->hm;
+  std::memset(&hm, 0, sizeof hm);
+  hm.S = c->S; hm.R = c->R; hm.Rg = c->Rg; hm.K = c->K; hm.gcat = c->gcat; hm.n_codes = c->al.n_codes; hm.any_code = c->al.any_code;
+  if (m->statd) std::memcpy(hm.statd, m->statd, sizeof(double) * c->S);
+  else {
+    if (!m->statd_chars) { delete c; return fail(PP_EINVAL, "pp_create: neither statd nor statd_chars given"); }
+    if (!emper_freq(c->S, m->statd_chars, m->n_statd_chars, hm.statd)) { delete c; return fail(PP_EINVAL, "pp_create: unknown base in reference alignment"); }
+  }
+  diagd_normed(c->S, m->exch, hm.statd, hm.x, hm.lam, hm.xit);
+  if (m->rates) std::memcpy(hm.rates, m->rates, sizeof(double) * c->R);
+  else discrete_gamma(c->R, m->gamma_alpha, hm.rates);
+  std::memcpy(hm.mask_of_code, c->al.mask_of_code, sizeof(uint32_t) * kMaxCodesDev);
+  // ---- tree ----
+  c->child_ptr.assign(t->child_ptr, t->child_ptr + t->n_nodes + 1);
+  c->child_idx.assign(t->child_idx, t->child_idx + t->child_ptr[t->n_nodes]);
+  c->leaf_row.assign(t->leaf_row, t->leaf_row + t->n_nodes);
+  c->bl.assign(t->bl, t->bl + t->n_nodes);
+  c->parent.assign(t->n_nodes, -1);
+  for (int i = 0; i < t->n_nodes; ++i)
+    for (int k = c->child_ptr[i]; k < c->child_ptr[i + 1]; ++k) {
+      const int ch = c->child_idx[k];
+      if (ch < 0 || ch >= t->n_nodes || c->parent[ch] != -1 || ch == t->root_id) { delete c; return fail(PP_EINVAL, "pp_create: malformed tree"); }
+      c->parent[ch] = i;
+    }
+  c->depth.assign(t->n_nodes, -1);
+  {
+    std::vector<int> stack{t->root_id};
+    c->depth[t->root_id] = 0;
+    size_t seen = 0;
+    while (!stack.empty()) {
+      const int v = stack.back(); stack.pop_back(); ++seen;
+      for (int k = c->child_ptr[v]; k < c->child_ptr[v + 1]; ++k) { c->depth[c->child_idx[k]] = c->depth[v] + 1; stack.push_back(c->child_idx[k]); }
+    }
+    if ((int)seen != t->n_nodes) { delete c; return fail(PP_EINVAL, "pp_create: tree is not connected"); }
+  }
+  for (int i = 0; i < t->n_nodes; ++i) {
+    const bool leaf = c->child_ptr[i] == c->child_ptr[i + 1];
+    if (leaf && (c->leaf_row[i] < 0 || c->leaf_row[i] >= n_leaves)) { delete c; return fail(PP_EINVAL, "pp_create: leaf without alignment row"); }
+  }
+  // ---- reference alignment -> codes ----
+  std::vector<uint8_t> codes((size_t)n_leaves * c->Lp, (uint8_t)(c->al.any_code | kGapBit));
+  for (int r = 0; r < n_leaves; ++r)
+    for (int s = 0; s < L; ++s) {
+      const uint8_t code = c->al.code_of_char[ref_chars[(size_t)r * L + s]];
+      if (code == kBadCode) { delete c; return fail(PP_EINVAL, std::string("pp_create: '") + (char)ref_chars[(size_t)r * L + s] + "' is not a known base in the reference alignment"); }
+      codes[(size_t)r * c->Lp + s] = code;
+    }
+  std::vector<int32_t> cat(c->Lp, 0);
+  if (c->gcat)
+    for (int s = 0; s < L; ++s) {
+      if (m->site_cat[s] < 0 || m->site_cat[s] >= c->R) { delete c; return fail(PP_EINVAL, "pp_create: site category out of range"); }
+      cat[s] = m->site_cat[s];
+    }
+  int rc;
+#define UP(dst, src, n) if ((rc = upload(&(dst), (src), (n))) != PP_OK) { pp_destroy(c); return rc; }
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&c->ev[0]));
+  CK(cudaEventCreate(&c->ev[1]));
+  UP(c->dm, &hm, 1);
+  UP(c->d_bl, c->bl.data(), c->bl.size());
+  UP(c->d_code_of_char, c->al.code_of_char, 256);
+  UP(c->d_ref_codes, codes.data(), codes.size());
+  UP(c->d_site_cat, cat.data(), cat.size());
+  UP(c->d_child_ptr, c->child_ptr.data(), c->child_ptr.size());
+  UP(c->d_child_idx, c->child_idx.data(), c->child_idx.size());
+  UP(c->d_parent, c->parent.data(), c->parent.size());
+  UP(c->d_leaf_row, c->leaf_row.data(), c->leaf_row.size());
+#undef UP
+  c->g.L = c->L; c->g.Lp = c->Lp; c->g.K = c->K; c->g.n_nodes = c->n_nodes; c->g.a_stride = (int64_t)c->K * c->Lp;
+  for (int w = 0; w < 3; ++w) {
+    cudaError_t e1 = cudaMalloc(&c->g.a[w], sizeof(double) * (size_t)c->g.a_stride * c->n_nodes);
+    cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(&c->g.e[w], sizeof(int32_t) * (size_t)c->Lp * c->n_nodes) : e1;
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaGetLastError(); pp_destroy(c); return fail(PP_ENOMEM, "pp_create: not enough device memory for darr/parr/snodes"); }
+    cudaMemsetAsync(c->g.a[w], 0, sizeof(double) * (size_t)c->g.a_stride * c->n_nodes, c->stream);
+    cudaMemsetAsync(c->g.e[w], 0, sizeof(int32_t) * (size_t)c->Lp * c->n_nodes, c->stream);
+  }
+  c->t.child_ptr = c->d_child_ptr; c->t.child_idx = c->d_child_idx; c->t.parent = c->d_parent; c->t.leaf_row = c->d_leaf_row;
+  c->t.ref_codes = c->d_ref_codes; c->t.site_cat = c->d_site_cat;
+  CK(cudaMallocHost(&c->h_counters, 8 * sizeof(int)));
+  if ((rc = c->counters.ensure(8)) != PP_OK) { pp_destroy(c); return rc; }
+  // QNG tables -> constant memory
+  cudaMemcpyToSymbol(c_qng_x1, ppb_qng_x1, sizeof ppb_qng_x1); cudaMemcpyToSymbol(c_qng_w10, ppb_qng_w10, sizeof ppb_qng_w10);
+  cudaMemcpyToSymbol(c_qng_x2, ppb_qng_x2, sizeof ppb_qng_x2); cudaMemcpyToSymbol(c_qng_w21a, ppb_qng_w21a, sizeof ppb_qng_w21a);
+  cudaMemcpyToSymbol(c_qng_w21b, ppb_qng_w21b, sizeof ppb_qng_w21b); cudaMemcpyToSymbol(c_qng_x3, ppb_qng_x3, sizeof ppb_qng_x3);
+  cudaMemcpyToSymbol(c_qng_w43a, ppb_qng_w43a, sizeof ppb_qng_w43a); cudaMemcpyToSymbol(c_qng_w43b, ppb_qng_w43b, sizeof ppb_qng_w43b);
+  cudaMemcpyToSymbol(c_qng_x4, ppb_qng_x4, sizeof ppb_qng_x4); cudaMemcpyToSymbol(c_qng_w87a, ppb_qng_w87a, sizeof ppb_qng_w87a);
+  cudaMemcpyToSymbol(c_qng_w87b, ppb_qng_w87b, sizeof ppb_qng_w87b);
+  // three-taxon kernel configuration
+  DISPATCH_MODEL(c, {
+    c->tt_smem = tt_smem_bytes<S_, G_>(c);
+    constexpr int TH = (S_ == 4) ? kTTThreadsDNA : kTTThreadsAA;
+    auto kern = three_tax_kernel<S_, G_, TH>;
+    if (c->tt_smem > 227 * 1024) { pp_destroy(c); return fail(PP_EINVAL, "pp_create: model too large for shared memory (rates x states^2)"); }
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tt_smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TH, c->tt_smem));
+    if (per_sm < 1) per_sm = 1;
+    c->tt_blocks = per_sm * c->sm_count;
+  });
+  if ((rc = c->wbuf.ensure((size_t)c->tt_blocks * c->K * c->Lp)) != PP_OK) { pp_destroy(c); return rc; }
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaGetLastError());
+  *out = c;
+  return PP_OK;
+}
+
+extern "C" int pp_get_model(pp_ctx *c, double *statd, double *x, double *lambda, double *xit, double *rates) {
+  if (!c) return fail(PP_EINVAL, "null ctx");
+  if (statd) std::memcpy(statd, c->hm.statd, sizeof(double) * c->S);
+  if (x) std::memcpy(x, c->hm.x, sizeof(double) * c->S * c->S);
+  if (lambda) std::memcpy(lambda, c->hm.lam, sizeof(double) * c->S);
+  if (xit) std::memcpy(xit, c->hm.xit, sizeof(double) * c->S * c->S);
+  if (rates) std::memcpy(rates, c->hm.rates, sizeof(double) * c->R);
+  return PP_OK;
+}
+
+#define LAUNCH_CHECK(c) do { (c)->launches++; CK(cudaGetLastError()); } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// precompute (pplacer_run.ml:322-340)
+// ---------------------------------------------------------------------------------------------
+extern "C" int pp_precompute(pp_ctx *c) {
+  if (!c) return fail(PP_EINVAL, "null ctx");
+  CK(cudaSetDevice(c->device));
+  const int Rt = c->R;
+  const size_t pm = (size_t)c->n_nodes * Rt * c->S * c->S;
+  double *Pfull = nullptr, *Phalf = nullptr;
+  CK(cudaMalloc(&Pfull, pm * sizeof(double)));
+  CK(cudaMalloc(&Phalf, pm * sizeof(double)));
+  // level lists
+  int max_depth = 0;
+  for (int d : c->depth) max_depth = std::max(max_depth, d);
+  std::vector<std::vector<int32_t>> levels(max_depth + 1);
+  for (int i = 0; i < c->n_nodes; ++i) levels[c->depth[i]].push_back(i);
+  std::vector<int32_t> flat; std::vector<int> off(max_depth + 2, 0);
+  for (int d = 0; d <= max_depth; ++d) { off[d] = (int)flat.size(); flat.insert(flat.end(), levels[d].begin(), levels[d].end()); }
+  off[max_depth + 1] = (int)flat.size();
+  int32_t *d_levels = nullptr;
+  CK(cudaMalloc(&d_levels, flat.size() * sizeof(int32_t)));
+  CK(cudaMemcpyAsync(d_levels, flat.data(), flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  const int tiles = (c->L + kPreThreads - 1) / kPreThreads;
+  int rc = PP_OK;
+  DISPATCH_MODEL(c, {
+    const size_t sm_p = (size_t)(Rt * S_ + Rt * S_ * S_) * sizeof(double);
+    pmat_kernel<S_><<<c->n_nodes, 128, sm_p, c->stream>>>(c->dm, c->d_bl, c->n_nodes, 1.0, Rt, Pfull); LAUNCH_CHECK(c);
+    pmat_kernel<S_><<<c->n_nodes, 128, sm_p, c->stream>>>(c->dm, c->d_bl, c->n_nodes, 0.5, Rt, Phalf); LAUNCH_CHECK(c);
+    const size_t sm_l = (size_t)Rt * p_rstride<S_, G_>() * sizeof(double);
+    CK(cudaFuncSetAttribute(distal_level_kernel<S_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_l));
+    CK(cudaFuncSetAttribute(proximal_level_kernel<S_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_l));
+    CK(cudaFuncSetAttribute(supernode_kernel<S_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_l));
+    for (int d = max_depth; d >= 0; --d) {  // post-order by level: deepest first
+      const int n = off[d + 1] - off[d];
+      for (int s0 = 0; s0 < n; s0 += 65535) {
+        dim3 grid(tiles, std::min(65535, n - s0));
+        distal_level_kernel<S_, G_><<<grid, kPreThreads, sm_l, c->stream>>>(c->dm, c->g, c->t, d_levels + off[d] + s0, Pfull, Rt); LAUNCH_CHECK(c);
+      }
+    }
+    set_unit_kernel<<<64, 256, 0, c->stream>>>(c->g, 1, c->root_id); LAUNCH_CHECK(c);
+    for (int d = 1; d <= max_depth; ++d) {  // pre-order by level: children of level d-1
+      const int n = off[d + 1] - off[d];
+      for (int s0 = 0; s0 < n; s0 += 65535) {
+        dim3 grid(tiles, std::min(65535, n - s0));
+        proximal_level_kernel<S_, G_><<<grid, kPreThreads, sm_l, c->stream>>>(c->dm, c->g, c->t, d_levels + off[d] + s0, Pfull, Rt); LAUNCH_CHECK(c);
+      }
+    }
+    for (int s0 = 0; s0 < c->n_nodes; s0 += 65535) {
+      // supernode_kernel indexes nodes by blockIdx.y; shift arrays by chunk via a node offset
+      if (s0 != 0) { rc = fail(PP_EINVAL, "pp_precompute: more than 65535 nodes not supported yet"); break; }
+      dim3 grid(tiles, std::min(65535, c->n_nodes));
+      supernode_kernel<S_, G_><<<grid, kPreThreads, sm_l, c->stream>>>(c->dm, c->g, c->t, Phalf, Rt); LAUNCH_CHECK(c);
+    }
+  });
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(Pfull); cudaFree(Phalf); cudaFree(d_levels);
+  if (e != cudaSuccess) return fail(PP_ECUDA, std::string("pp_precompute: ") + cudaGetErrorString(e));
+  if (rc != PP_OK) return rc;
+  c->precomputed = true;
+  return PP_OK;
+}
+
+extern "C" int pp_export_glvs(pp_ctx *c, int32_t which, int32_t nb, int32_t ne, double *a, int64_t *e) {
+  if (!c || which < 0 || which > 2 || nb < 0 || ne > c->n_nodes || nb > ne) return fail(PP_EINVAL, "pp_export_glvs: bad arguments");
+  CK(cudaSetDevice(c->device));
+  const size_t per = (size_t)c->g.a_stride;
+  std::vector<double> tmp(per);
+  std::vector<int32_t> te(c->Lp);
+  for (int node = nb; node < ne; ++node) {
+    if (a) {
+      CK(cudaMemcpy(tmp.data(), c->g.a[which] + (size_t)node * per, per * sizeof(double), cudaMemcpyDeviceToHost));
+      double *dst = a + (size_t)(node - nb) * c->K * c->L;
+      // device [r*S+s][Lp] -> reference [r][L][S]
+      for (int r = 0; r < c->Rg; ++r)
+        for (int s = 0; s < c->S; ++s) {
+          const double *pl = tmp.data() + (size_t)(r * c->S + s) * c->Lp;
+          for (int site = 0; site < c->L; ++site) dst[((size_t)r * c->L + site) * c->S + s] = pl[site];
+        }
+    }
+    if (e) {
+      CK(cudaMemcpy(te.data(), c->g.e[which] + (size_t)node * c->Lp, c->Lp * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      for (int site = 0; site < c->L; ++site) e[(size_t)(node - nb) * c->L + site] = te[site];
+    }
+  }
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// query preparation and prefilter
+// ---------------------------------------------------------------------------------------------
+static int prep_queries(pp_ctx *c, int64_t Q, const uint8_t *d_chars) {
+  int rc;
+  if ((rc = c->codes.ensure((size_t)Q * c->Lp)) || (rc = c->qsite.ensure((size_t)Q * c->Lp)) || (rc = c->nq.ensure(Q)) ||
+      (rc = c->prep_status.ensure(Q)))
+    return rc;
+  query_prep_kernel<<<(unsigned)Q, kPrepThreads, 0, c->stream>>>(d_chars, c->d_code_of_char, c->L, c->Lp, c->codes.p, c->qsite.p,
+                                                                  c->nq.p, c->prep_status.p, PP_Q_BAD_CHAR, PP_Q_NO_INFORMATIVE);
+  LAUNCH_CHECK(c);
+  return PP_OK;
+}
+
+static int build_query_table(pp_ctx *c, double t) {
+  int rc;
+  const size_t n = (size_t)c->R * c->al.n_codes * c->S;
+  if ((rc = c->Tq.ensure(n))) return rc;
+  DISPATCH_MODEL(c, {
+    const size_t sm = (size_t)(c->R * S_ + c->R * S_ * S_) * sizeof(double);
+    CK(cudaFuncSetAttribute(query_table_kernel<S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    query_table_kernel<S_><<<1, 256, sm, c->stream>>>(c->dm, t, c->Tq.p);
+    (void)G_;
+    LAUNCH_CHECK(c);
+  });
+  return PP_OK;
+}
+
+template <int S, bool G, int TE, int QT, int TH>
+static int launch_prefilter_direct(pp_ctx *c, int64_t Q) {
+  const size_t sm = ((size_t)c->R * c->al.n_codes * S + (size_t)(TH / 32) * TE * QT) * sizeof(double);
+  auto kern = prefilter_direct_kernel<S, G, TE, QT, TH>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  dim3 grid((c->n_nodes + TE - 1) / TE, (unsigned)((Q + QT - 1) / QT));
+  kern<<<grid, TH, sm, c->stream>>>(c->dm, c->g, c->Tq.p, c->codes.p, c->nq.p, c->d_site_cat, (int)Q, c->root_id, c->scores.p);
+  LAUNCH_CHECK(c);
+  return PP_OK;
+}
+
+static int run_prefilter(pp_ctx *c, int64_t Q, int kernel_choice) {
+  int rc;
+  (void)kernel_choice;
+  if ((rc = c->scores.ensure((size_t)Q * c->n_nodes))) return rc;
+  if (c->S == 4 && !c->gcat) return launch_prefilter_direct<4, false, 2, 4, 128>(c, Q);
+  if (c->S == 4 && c->gcat) return launch_prefilter_direct<4, true, 2, 4, 128>(c, Q);
+  if (c->S == 20 && !c->gcat) return launch_prefilter_direct<20, false, 1, 4, 128>(c, Q);
+  return launch_prefilter_direct<20, true, 1, 4, 128>(c, Q);
+}
+
+extern "C" int pp_prefilter_scores(pp_ctx *c, double start_pend, int64_t Q, const uint8_t *query_chars, double *scores,
+                                   int32_t kernel) {
+  if (!c || !query_chars || !scores || Q < 1) return fail(PP_EINVAL, "pp_prefilter_scores: bad arguments");
+  if (!c->precomputed) return fail(PP_ESTATE, "pp_prefilter_scores: call pp_precompute first");
+  CK(cudaSetDevice(c->device));
+  int rc;
+  if ((rc = c->chars.ensure((size_t)Q * c->L))) return rc;
+  CK(cudaMemcpyAsync(c->chars.p, query_chars, (size_t)Q * c->L, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = prep_queries(c, Q, c->chars.p)) || (rc = build_query_table(c, start_pend)) || (rc = run_prefilter(c, Q, kernel))) return rc;
+  CK(cudaMemcpyAsync(scores, c->scores.p, sizeof(double) * (size_t)Q * c->n_nodes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// three-taxon launches
+// ---------------------------------------------------------------------------------------------
+static int launch_three_tax(pp_ctx *c, const CandIn *in, CandOut *out, int n, const TTParams &prm) {
+  if (n <= 0) return PP_OK;
+  CK(cudaMemsetAsync(c->counters.p, 0, sizeof(int), c->stream));
+  const int blocks = std::min(c->tt_blocks, n);
+  DISPATCH_MODEL(c, {
+    constexpr int TH = (S_ == 4) ? kTTThreadsDNA : kTTThreadsAA;
+    three_tax_kernel<S_, G_, TH><<<blocks, TH, c->tt_smem, c->stream>>>(c->dm, c->g, c->d_bl, c->d_site_cat, c->codes.p, c->qsite.p,
+                                                                        c->nq.p, in, out, n, prm, c->wbuf.p, c->counters.p);
+    LAUNCH_CHECK(c);
+  });
+  return PP_OK;
+}
+
+static TTParams make_params(const pp_prefs *pf, int mode, double tol, int use_defaults) {
+  TTParams p;
+  p.start_pend = pf->start_pend; p.max_pend = pf->max_pend; p.tol = tol; p.pp_rel_err = pf->pp_rel_err;
+  p.prior_mean = pf->prior_mean; p.prior_means = nullptr; p.max_iter = pf->max_iter; p.mode = mode;
+  p.prior_kind = pf->prior_kind; p.use_defaults = use_defaults;
+  return p;
+}
+
+extern "C" int pp_three_tax_log_like(pp_ctx *c, int64_t n, const uint8_t *query_chars, const int32_t *edge,
+                                     const double *pendant, const double *distal, double *ll_out) {
+  if (!c || n < 1 || !query_chars || !edge || !pendant || !distal || !ll_out) return fail(PP_EINVAL, "pp_three_tax_log_like: bad arguments");
+  if (!c->precomputed) return fail(PP_ESTATE, "pp_three_tax_log_like: call pp_precompute first");
+  CK(cudaSetDevice(c->device));
+  int rc;
+  if ((rc = c->chars.ensure((size_t)n * c->L)) || (rc = c->cand.ensure(n)) || (rc = c->cand_out.ensure(n))) return rc;
+  CK(cudaMemcpyAsync(c->chars.p, query_chars, (size_t)n * c->L, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = prep_queries(c, n, c->chars.p))) return rc;
+  std::vector<CandIn> in(n);
+  for (int64_t i = 0; i < n; ++i) {
+    if (edge[i] < 0 || edge[i] >= c->n_nodes) return fail(PP_EINVAL, "pp_three_tax_log_like: edge out of range");
+    in[i].q = (int32_t)i; in[i].loc = edge[i]; in[i].pend0 = pendant[i]; in[i].dist0 = distal[i];
+  }
+  CK(cudaMemcpyAsync(c->cand.p, in.data(), n * sizeof(CandIn), cudaMemcpyHostToDevice, c->stream));
+  pp_prefs pf; pp_default_prefs(&pf);
+  if ((rc = launch_three_tax(c, c->cand.p, c->cand_out.p, (int)n, make_params(&pf, TT_MODE_LOGLIKE, 0.0, 0)))) return rc;
+  std::vector<CandOut> o(n);
+  CK(cudaMemcpyAsync(o.data(), c->cand_out.p, n * sizeof(CandOut), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  std::vector<int32_t> st(n);
+  CK(cudaMemcpy(st.data(), c->prep_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n; ++i) ll_out[i] = st[i] ? NAN : o[i].ll;
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the path: pp_place
+// ---------------------------------------------------------------------------------------------
+struct PhaseTimer {
+  pp_ctx *c; int phase;
+  PhaseTimer(pp_ctx *c_, int ph) : c(c_), phase(ph) { cudaEventRecord(c->ev[0], c->stream); }
+  void stop() { cudaEventRecord(c->ev[1], c->stream); cudaEventSynchronize(c->ev[1]); float ms = 0; cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->phase_ms[phase] += ms; }
+};
+
+static int place_batch(pp_ctx *c, const pp_prefs *pf, int64_t Q, const uint8_t *d_chars, PlaceOut *d_out, int32_t *d_n_out,
+                       int32_t *d_status, pp_debug *dbg, int64_t q_off) {
+  int rc;
+  const int n_nodes = c->n_nodes;
+  const bool all_edges = pf->max_strikes == 0;
+  const int P = all_edges ? n_nodes - 1 : pf->max_pitches + 1;
+  BallPrefs bp;
+  bp.t_max_pitches = all_edges ? 0x7fffffff : pf->max_pitches;
+  bp.t_max_strikes = all_edges ? 0x7fffffff : pf->max_strikes;
+  bp.strike_box = pf->strike_box; bp.keep_at_most = pf->keep_at_most; bp.log_keep_factor = std::log(pf->keep_factor);
+  // ---- stage 0: query prep, evolved-query table (core.ml:121-158) ----
+  if ((rc = prep_queries(c, Q, d_chars)) || (rc = build_query_table(c, pf->start_pend))) return rc;
+  // ---- stage 1: prefilter + ranking (core.ml:187-197) ----
+  {
+    PhaseTimer t(c, 0);
+    if ((rc = run_prefilter(c, Q, 0))) return rc;
+    t.stop();
+  }
+  const int64_t total = Q * (int64_t)n_nodes;
+  {
+    PhaseTimer t(c, 1);
+    if ((rc = c->keys_in.ensure(total)) || (rc = c->keys_out.ensure(total)) || (rc = c->rank_in.ensure(total)) ||
+        (rc = c->rank_loc.ensure(total)) || (rc = c->seg_off.ensure(Q + 1)))
+      return rc;
+    rank_keys_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->scores.p, c->keys_in.p, n_nodes, c->root_id, total); LAUNCH_CHECK(c);
+    iota_segments_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->rank_in.p, n_nodes, total); LAUNCH_CHECK(c);
+    std::vector<int32_t> off(Q + 1);
+    if (total > 0x7fffffffLL) return fail(PP_EINVAL, "place_batch: batch too large for 32-bit segment offsets");
+    for (int64_t q = 0; q <= Q; ++q) off[q] = (int32_t)(q * n_nodes);
+    CK(cudaMemcpyAsync(c->seg_off.p, off.data(), (Q + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceSegmentedSort::StableSortPairsDescending(nullptr, tmp_bytes, c->keys_in.p, c->keys_out.p, c->rank_in.p, c->rank_loc.p,
+                                                           total, (int)Q, c->seg_off.p, c->seg_off.p + 1, c->stream));
+    if ((rc = c->sort_tmp.ensure(tmp_bytes))) return rc;
+    CK(cub::DeviceSegmentedSort::StableSortPairsDescending(c->sort_tmp.p, tmp_bytes, c->keys_in.p, c->keys_out.p, c->rank_in.p, c->rank_loc.p,
+                                                           total, (int)Q, c->seg_off.p, c->seg_off.p + 1, c->stream));
+    c->launches += 3;
+    CK(cudaStreamSynchronize(c->stream));  // `off` must outlive the async copy
+    t.stop();
+  }
+  // ---- stage 2: baseball in waves (core.ml:283-318) ----
+  const size_t per_q_i32 = 7, per_q_f64 = 1;
+  if ((rc = c->i32pool.ensure((size_t)Q * (per_q_i32 + 2) + (size_t)Q * P)) || (rc = c->f64pool.ensure((size_t)Q * per_q_f64 + 3 * (size_t)Q * P)) ||
+      (rc = c->n_calls.ensure(Q)))
+    return rc;
+  BallState b;
+  {
+    int32_t *ip = c->i32pool.p;
+    b.next_rank = ip; ip += Q; b.n_results = ip; ip += Q; b.n_strikes = ip; ip += Q; b.done = ip; ip += Q;
+    b.wave_begin = ip; ip += Q; b.wave_n = ip; ip += Q; b.qstatus = ip; ip += Q;
+    KeepState dummy; (void)dummy;
+    b.res_loc = ip + 2 * Q;  // keep_begin / n_keep live in the two Q-sized slots before
+    double *fp = c->f64pool.p;
+    b.like_record = fp; fp += Q; b.res_ll = fp; fp += (size_t)Q * P; b.res_pend = fp; fp += (size_t)Q * P; b.res_dist = fp;
+    b.n_calls = c->n_calls.p; b.P = P;
+  }
+  KeepState ks; ks.keep_begin = c->i32pool.p + 7 * Q; ks.n_keep = c->i32pool.p + 8 * Q;
+  const int qb = (int)((Q + 255) / 256);
+  ball_init_kernel<<<qb, 256, 0, c->stream>>>(b, c->prep_status.p, (int)Q); LAUNCH_CHECK(c);
+  const size_t max_wave = all_edges ? (size_t)Q * (n_nodes - 1) : (size_t)Q * std::max(std::min(pf->max_strikes, pf->max_pitches + 1), 1);
+  if ((rc = c->cand.ensure(std::max(max_wave, (size_t)Q * pf->keep_at_most))) || (rc = c->cand_out.ensure(std::max(max_wave, (size_t)Q * pf->keep_at_most))))
+    return rc;
+  {
+    PhaseTimer t(c, 2);
+    const TTParams prm = make_params(pf, TT_MODE_OPTIMIZE, pf->initial_tolerance, 1);
+    for (int wave = 0;; ++wave) {
+      CK(cudaMemsetAsync(c->counters.p + 1, 0, 2 * sizeof(int), c->stream));
+      ball_plan_kernel<<<qb, 256, 0, c->stream>>>(b, bp, c->rank_loc.p, n_nodes, c->root_id, (int)Q, c->cand.p, c->counters.p + 1); LAUNCH_CHECK(c);
+      CK(cudaMemcpyAsync(c->h_counters, c->counters.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      const int n_cand = c->h_counters[1];
+      if (n_cand == 0) break;
+      if ((rc = launch_three_tax(c, c->cand.p, c->cand_out.p, n_cand, prm))) return rc;
+      ball_update_kernel<<<qb, 256, 0, c->stream>>>(b, bp, c->cand.p, c->cand_out.p, n_nodes, (int)Q, c->counters.p + 2); LAUNCH_CHECK(c);
+      if (wave > n_nodes + 64) return fail(PP_ECUDA, "place_batch: baseball did not terminate");
+    }
+    // ---- keep + refinement (core.ml:336-369) ----
+    CK(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(int), c->stream));
+    keep_select_kernel<<<qb, 256, 0, c->stream>>>(b, bp, ks, (int)Q, c->cand.p, c->counters.p + 3, PP_Q_EMPTY_RESULTS); LAUNCH_CHECK(c);
+    CK(cudaMemcpyAsync(c->h_counters, c->counters.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const int n_keep = c->h_counters[3];
+    if ((rc = launch_three_tax(c, c->cand.p, c->cand_out.p, n_keep, make_params(pf, TT_MODE_OPTIMIZE, pf->final_tolerance, 0)))) return rc;
+    refine_finish_kernel<<<qb, 256, 0, c->stream>>>(b, ks, (int)Q, c->cand.p, c->cand_out.p, d_out, pf->keep_at_most, d_n_out); LAUNCH_CHECK(c);
+    t.stop();
+    // ---- --pp (core.ml:379-404) ----
+    PhaseTimer tp(c, 3);
+    if (pf->calc_pp) {
+      if ((rc = c->pp_out.ensure(std::max(n_keep, 1)))) return rc;
+      TTParams pp = make_params(pf, TT_MODE_MARGINAL, 0.0, 0);
+      DevBuf<double> prior_means;
+      if (pf->prior_kind == 2) {
+        if (!pf->prior_means) return fail(PP_EINVAL, "pp_place: informative prior needs prior_means");
+        if ((rc = prior_means.ensure(n_nodes))) return rc;
+        CK(cudaMemcpyAsync(prior_means.p, pf->prior_means, sizeof(double) * n_nodes, cudaMemcpyHostToDevice, c->stream));
+        pp.prior_means = prior_means.p;
+      }
+      rc = launch_three_tax(c, c->cand.p, c->pp_out.p, n_keep, pp);
+      if (rc == PP_OK) { final_sort_kernel<<<qb, 256, 0, c->stream>>>(b, ks, (int)Q, c->pp_out.p, 1, d_out, pf->keep_at_most, d_n_out, PP_Q_PP_FAILED); c->launches++; }
+      cudaStreamSynchronize(c->stream);
+      prior_means.release();
+      if (rc) return rc;
+      CK(cudaGetLastError());
+    } else {
+      final_sort_kernel<<<qb, 256, 0, c->stream>>>(b, ks, (int)Q, nullptr, 0, d_out, pf->keep_at_most, d_n_out, PP_Q_PP_FAILED); LAUNCH_CHECK(c);
+    }
+    tp.stop();
+  }
+  CK(cudaMemcpyAsync(d_status, b.qstatus, Q * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+  // ---- optional stage outputs ----
+  if (dbg) {
+    if (dbg->scores) CK(cudaMemcpyAsync(dbg->scores + q_off * n_nodes, c->scores.p, sizeof(double) * total, cudaMemcpyDeviceToHost, c->stream));
+    if (dbg->n_pitches) CK(cudaMemcpyAsync(dbg->n_pitches + q_off, b.n_results, sizeof(int32_t) * Q, cudaMemcpyDeviceToHost, c->stream));
+    if (dbg->n_like_calls) CK(cudaMemcpyAsync(dbg->n_like_calls + q_off, b.n_calls, sizeof(int64_t) * Q, cudaMemcpyDeviceToHost, c->stream));
+    // NOTE: pitch_* arrays come back sorted by likelihood (keep_select sorts in place), not in play order
+    const int PK = pf->max_pitches + 1;
+    if (!all_edges && PK == P) {
+      if (dbg->pitch_edges) CK(cudaMemcpyAsync(dbg->pitch_edges + q_off * PK, b.res_loc, sizeof(int32_t) * Q * P, cudaMemcpyDeviceToHost, c->stream));
+      if (dbg->pitch_ll) CK(cudaMemcpyAsync(dbg->pitch_ll + q_off * PK, b.res_ll, sizeof(double) * Q * P, cudaMemcpyDeviceToHost, c->stream));
+      if (dbg->pitch_pend) CK(cudaMemcpyAsync(dbg->pitch_pend + q_off * PK, b.res_pend, sizeof(double) * Q * P, cudaMemcpyDeviceToHost, c->stream));
+      if (dbg->pitch_dist) CK(cudaMemcpyAsync(dbg->pitch_dist + q_off * PK, b.res_dist, sizeof(double) * Q * P, cudaMemcpyDeviceToHost, c->stream));
+    }
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return PP_OK;
+}
+
+static int64_t batch_size(const pp_ctx *c, const pp_prefs *pf) {
+  // bound the Q x n_nodes score / ranking buffers (~40 B per entry) to ~6 GB and 2^31 entries
+  const int64_t by_mem = (int64_t)(6.0e9 / (40.0 * c->n_nodes));
+  const int64_t by_idx = 0x7fffffffLL / c->n_nodes;
+  int64_t b = std::min<int64_t>(std::min(by_mem, by_idx), 1 << 16);
+  if (pf->max_strikes == 0) b = std::min<int64_t>(b, 4096);
+  return std::max<int64_t>(b, 1);
+}
+
+static int check_prefs(const pp_prefs *pf) {
+  if (!pf) return fail(PP_EINVAL, "null prefs");
+  if (pf->keep_at_most < 1 || pf->max_pitches < 1 || pf->max_strikes < 0 || !(pf->keep_factor > 0) || pf->max_iter < 1)
+    return fail(PP_EINVAL, "pp_place: bad prefs");
+  return PP_OK;
+}
+
+extern "C" int pp_place_device(pp_ctx *c, const pp_prefs *pf, int64_t Q, const uint8_t *d_query_chars, pp_result *d_out,
+                               int32_t *d_n_out, int32_t *d_status) {
+  if (!c || !d_query_chars || !d_out || !d_n_out || !d_status || Q < 0) return fail(PP_EINVAL, "pp_place_device: bad arguments");
+  if (!c->precomputed) return fail(PP_ESTATE, "pp_place_device: call pp_precompute first");
+  int rc;
+  if ((rc = check_prefs(pf))) return rc;
+  CK(cudaSetDevice(c->device));
+  static_assert(sizeof(PlaceOut) == sizeof(pp_result), "PlaceOut must match pp_result");
+  const int64_t B = batch_size(c, pf);
+  for (int64_t q0 = 0; q0 < Q; q0 += B) {
+    const int64_t n = std::min(B, Q - q0);
+    if ((rc = place_batch(c, pf, n, d_query_chars + q0 * c->L, reinterpret_cast<PlaceOut *>(d_out) + q0 * pf->keep_at_most,
+                          d_n_out + q0, d_status + q0, nullptr, q0)))
+      return rc;
+  }
+  return PP_OK;
+}
+
+extern "C" int pp_place(pp_ctx *c, const pp_prefs *pf, int64_t Q, const uint8_t *query_chars, pp_result *out, int32_t *n_out,
+                        int32_t *status, pp_debug *dbg) {
+  if (!c || !query_chars || !out || !n_out || !status || Q < 0) return fail(PP_EINVAL, "pp_place: bad arguments");
+  if (!c->precomputed) return fail(PP_ESTATE, "pp_place: call pp_precompute first");
+  int rc;
+  if ((rc = check_prefs(pf))) return rc;
+  CK(cudaSetDevice(c->device));
+  const int64_t B = batch_size(c, pf);
+  const int64_t Bm = std::min(B, std::max<int64_t>(Q, 1));
+  if ((rc = c->chars.ensure((size_t)Bm * c->L)) || (rc = c->place_out.ensure((size_t)Bm * pf->keep_at_most)) || (rc = c->n_out.ensure(2 * Bm)))
+    return rc;
+  if (dbg && dbg->timing) for (int i = 0; i < 4; ++i) dbg->timing[i] = 0.0;
+  double ms0[4]; std::memcpy(ms0, c->phase_ms, sizeof ms0);
+  for (int64_t q0 = 0; q0 < Q; q0 += B) {
+    const int64_t n = std::min(B, Q - q0);
+    CK(cudaMemcpyAsync(c->chars.p, query_chars + q0 * c->L, (size_t)n * c->L, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = place_batch(c, pf, n, c->chars.p, c->place_out.p, c->n_out.p, c->n_out.p + Bm, dbg, q0))) return rc;
+    CK(cudaMemcpyAsync(out + q0 * pf->keep_at_most, c->place_out.p, sizeof(pp_result) * (size_t)n * pf->keep_at_most, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(n_out + q0, c->n_out.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(status + q0, c->n_out.p + Bm, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  if (dbg && dbg->timing) {
+    dbg->timing[0] = (c->phase_ms[0] - ms0[0] + c->phase_ms[1] - ms0[1]) * 1e-3;  // "ranking"
+    dbg->timing[1] = (c->phase_ms[2] - ms0[2]) * 1e-3;                             // "ML calculation"
+    dbg->timing[2] = (c->phase_ms[3] - ms0[3]) * 1e-3;                             // "PP calculation"
+    dbg->timing[3] = 0.0;
+  }
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// misc
+// ---------------------------------------------------------------------------------------------
+template <int S, bool G>
+__global__ void evolve_test_kernel(const DevModel *__restrict__ m, const double *__restrict__ src, double *__restrict__ dst, int n,
+                                   int np, const int32_t *__restrict__ site_cat, double bl, int Rt) {
+  extern __shared__ double sm[];
+  constexpr int RS = p_rstride<S, G>();
+  double *ex = sm, *P = sm + Rt * S;
+  block_build_P<S>(m, Rt, bl, P, RS, ex);
+  const int Rg = G ? 1 : Rt;
+  for (int site = threadIdx.x + blockIdx.x * blockDim.x; site < n; site += gridDim.x * blockDim.x)
+    for (int r = 0; r < Rg; ++r) {
+      const double *Pr = P + (G ? site_cat[site] : r) * RS;
+      double v[S];
+      for (int s = 0; s < S; ++s) v[s] = src[(size_t)(r * S + s) * np + site];
+      for (int i = 0; i < S; ++i) {
+        double acc = 0.0;
+        for (int j = 0; j < S; ++j) acc = fma(Pr[i * S + j], v[j], acc);
+        dst[(size_t)(r * S + i) * np + site] = acc;
+      }
+    }
+}
+
+extern "C" int pp_evolve(pp_ctx *c, const double *src_a, const int64_t *src_e, int32_t n, double bl, double *dst_a, int64_t *dst_e) {
+  if (!c || !src_a || !dst_a || n < 1 || n > c->L) return fail(PP_EINVAL, "pp_evolve: bad arguments");
+  CK(cudaSetDevice(c->device));
+  const int np = (n + 31) / 32 * 32;
+  std::vector<double> h((size_t)c->K * np, 0.0);
+  for (int r = 0; r < c->Rg; ++r)
+    for (int site = 0; site < n; ++site)
+      for (int s = 0; s < c->S; ++s) h[(size_t)(r * c->S + s) * np + site] = src_a[((size_t)r * n + site) * c->S + s];
+  double *d_src = nullptr, *d_dst = nullptr;
+  CK(cudaMalloc(&d_src, h.size() * sizeof(double)));
+  CK(cudaMalloc(&d_dst, h.size() * sizeof(double)));
+  CK(cudaMemcpy(d_src, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+  DISPATCH_MODEL(c, {
+    const size_t sm = (size_t)(c->R * S_ + c->R * p_rstride<S_, G_>()) * sizeof(double);
+    CK(cudaFuncSetAttribute(evolve_test_kernel<S_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    evolve_test_kernel<S_, G_><<<(n + 127) / 128, 128, sm, c->stream>>>(c->dm, d_src, d_dst, n, np, c->d_site_cat, bl, c->R);
+    LAUNCH_CHECK(c);
+  });
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(h.data(), d_dst, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(d_src); cudaFree(d_dst);
+  for (int r = 0; r < c->Rg; ++r)
+    for (int site = 0; site < n; ++site)
+      for (int s = 0; s < c->S; ++s) dst_a[((size_t)r * n + site) * c->S + s] = h[(size_t)(r * c->S + s) * np + site];
+  if (src_e && dst_e) std::memcpy(dst_e, src_e, sizeof(int64_t) * n);  // exponents are copied (gmix_model.ml:311)
+  return PP_OK;
+}
+
+extern "C" int64_t pp_kernel_launches(pp_ctx *c, int32_t reset) {
+  if (!c) return -1;
+  const int64_t v = c->launches;
+  if (reset) c->launches = 0;
+  return v;
+}
+extern "C" int pp_phase_times_ms(pp_ctx *c, double *out4, int32_t reset) {
+  if (!c || !out4) return fail(PP_EINVAL, "pp_phase_times_ms: bad arguments");
+  std::memcpy(out4, c->phase_ms, sizeof c->phase_ms);
+  if (reset) std::memset(c->phase_ms, 0, sizeof c->phase_ms);
+  return PP_OK;
+}
+extern "C" int pp_measure_fp64_peak(pp_ctx *c, double *tflops_out) {
+  if (!c || !tflops_out) return fail(PP_EINVAL, "pp_measure_fp64_peak: bad arguments");
+  CK(cudaSetDevice(c->device));
+  const int blocks = c->sm_count * 8, threads = 256, iters = 1 << 15;
+  double *d = nullptr;
+  CK(cudaMalloc(&d, sizeof(double) * blocks * threads));
+  dfma_probe_kernel<<<blocks, threads, 0, c->stream>>>(d, 1024, 0.999999, 1e-9);  // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(c->ev[0], c->stream);
+    dfma_probe_kernel<<<blocks, threads, 0, c->stream>>>(d, iters, 0.999999, 1e-9);
+    cudaEventRecord(c->ev[1], c->stream);
+    CK(cudaEventSynchronize(c->ev[1]));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    best = std::min(best, ms);
+  }
+  c->launches += 6;
+  cudaFree(d);
+  *tflops_out = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
+  return PP_OK;
+}

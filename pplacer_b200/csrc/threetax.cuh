@@ -1,0 +1,565 @@
+// Second stage on device: the three-taxon tree, its likelihood, alternating Brent optimisation
+// of pendant and distal branch lengths, and the --pp marginal likelihood.
+//   Three_tax          pplacer_src/three_tax.ml:30-83 (log_like, set_*_bl, optimize), :124-215 (pp)
+//   Glv_edge.set_bl    pplacer_src/glv_edge.ml:29-35   (re-evolve on every branch-length change)
+//   Model.log_like3    gmix_model.ml:298-304 -> ten_log_like3_c linear_c.c:367-424
+//                      gcat_model.ml:317-323 -> mat_log_like3_c linear_c.c:170-216
+//   Model.evolve_into  gmix_model.ml:308-315 / gcat_model.ml:327-345 ; Diagd.multi_exp diagd.ml:79-98
+//   Minimization.brent pplacer_src/minimization.ml:11-41,83-101 over GSL's gsl_min_fminimizer_brent
+//   Integration        pplacer_src/integration.ml:27-31 over GSL's gsl_integration_qng
+//   core.ml:225-279    set_tt_edges / tt_edges_default / (safe_)ml_optimize_location
+//
+// One thread block owns one (query, edge) candidate at a time (persistent blocks pull candidates
+// from an atomic queue).  Threads stride the query's informative sites; the scalar Brent / QNG
+// state machines are executed redundantly and identically by every thread (all inputs are
+// block-uniform and the block reductions are deterministic), so no broadcast is needed.
+//
+// Restructurings relative to the reference (same arithmetic per site):
+//   * the distal / proximal GLVs are never gathered into masked copies (Glv.mask_into,
+//     core.ml:229-233): the kernel reads darr/parr planes at the query's site list directly;
+//   * the evolved pendant GLV is a per-character table (sum of columns of P(pendant));
+//   * while only the pendant length moves, w = (statd*prox_ev)*dist_ev is cached per site.
+#pragma once
+#include "device_common.cuh"
+#include "qng_tables.h"
+
+namespace ppb {
+
+enum : int {
+  ST_OK = 0,
+  ST_GSL_EINVAL = 4,
+  ST_GSL_EBADFUNC = 9,
+  ST_GSL_EBADTOL = 13,
+  ST_GSL_ETOL = 14,
+  ST_EXCEEDED_MAX_ITER = 100,
+  ST_FIND_START_FAILURE = 101,
+  ST_INVALID_START = 102,
+  ST_ASSERT = 106
+};
+__host__ __device__ inline bool st_is_gsl(int st) {
+  return st == ST_GSL_EINVAL || st == ST_GSL_EBADFUNC || st == ST_GSL_ETOL || st == ST_GSL_EBADTOL;
+}
+
+struct CandIn {
+  int32_t q, loc;
+  double pend0, dist0;
+};
+struct CandOut {
+  double ll, pend, dist, marg;
+  int32_t status, calls;
+};
+
+enum : int { TT_MODE_OPTIMIZE = 0, TT_MODE_LOGLIKE = 1, TT_MODE_MARGINAL = 2 };
+
+struct TTParams {
+  double start_pend, max_pend, tol, pp_rel_err, prior_mean;
+  const double *prior_means;  // informative prior (per edge) or null
+  int max_iter, mode, prior_kind, use_defaults;
+};
+
+__constant__ double c_qng_x1[5], c_qng_w10[5], c_qng_x2[5], c_qng_w21a[5], c_qng_w21b[6], c_qng_x3[11],
+    c_qng_w43a[10], c_qng_w43b[12], c_qng_x4[22], c_qng_w87a[21], c_qng_w87b[23];
+
+constexpr double kSqrtDblEps = 1.4901161193847656e-08;
+constexpr double kDblEps = 2.2204460492503131e-16;
+
+template <int S, bool GCAT, int THREADS>
+struct ThreeTax {
+  static constexpr int RS = p_rstride<S, GCAT>();
+  // ---- shared memory views ----
+  double *statd, *lam, *x, *xit, *rates, *ex, *Pd, *Pp, *Pq, *Tp, *red;
+  uint32_t *mask_of_code;
+  // ---- block-uniform state ----
+  GlvArrays g;
+  int R, Rt, Rg, K, nc;
+  const int32_t *qsite;
+  const uint8_t *qcode;
+  const int32_t *site_cat;
+  double *w;
+  int64_t wstride;
+  int nq, loc;
+  double e_tot_ln2, rate_term;
+  double pend_bl, dist_bl, prox_bl;
+  int calls;
+
+  static __host__ __device__ size_t smem_doubles(int Rt, int nc) {
+    size_t n = 0;
+    n += S + S + 2 * S * S + Rt;              // statd lam x xit rates
+    n += (size_t)Rt * S;                      // ex
+    n += 2 * (size_t)Rt * RS;                 // Pd Pp
+    n += (size_t)Rt * RS;                     // Pq (Gcat pendant tensor / Gmix scratch)
+    n += GCAT ? 0 : (size_t)nc * Rt * S;      // Tp
+    n += 40;                                  // red
+    n += kMaxCodesDev / 2;                    // mask_of_code (uint32)
+    return n;
+  }
+
+  __device__ void carve(double *sm, const DevModel *m) {
+    R = m->R; Rt = m->R; Rg = GCAT ? 1 : m->R; K = Rg * S; nc = m->n_codes;
+    double *p = sm;
+    statd = p; p += S; lam = p; p += S; x = p; p += S * S; xit = p; p += S * S; rates = p; p += Rt;
+    ex = p; p += Rt * S;
+    Pd = p; p += Rt * RS; Pp = p; p += Rt * RS; Pq = p; p += Rt * RS;
+    Tp = p; p += GCAT ? 0 : nc * Rt * S;
+    red = p; p += 40;
+    mask_of_code = reinterpret_cast<uint32_t *>(p);
+    for (int i = threadIdx.x; i < S; i += THREADS) { statd[i] = m->statd[i]; lam[i] = m->lam[i]; }
+    for (int i = threadIdx.x; i < S * S; i += THREADS) { x[i] = m->x[i]; xit[i] = m->xit[i]; }
+    for (int i = threadIdx.x; i < Rt; i += THREADS) rates[i] = m->rates[i];
+    for (int i = threadIdx.x; i < kMaxCodesDev; i += THREADS) mask_of_code[i] = m->mask_of_code[i];
+    __syncthreads();
+  }
+
+  // Diagd.multi_exp for all Rt rates into dst (diagd.ml:79-98; linear_c.c:92-146)
+  __device__ __noinline__ void build_P(double *dst, double bl) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < Rt * S; t += THREADS) {
+      const int r = t / S, k = t - r * S;
+      ex[t] = exp(rates[r] * bl * lam[k]);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < Rt * S * S; t += THREADS) {
+      const int r = t / (S * S), ij = t - r * S * S, i = ij / S, j = ij - i * S;
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < S; ++k) acc = fma(ex[r * S + k] * x[i * S + k], xit[j * S + k], acc);
+      dst[r * RS + ij] = acc;
+    }
+    __syncthreads();
+  }
+
+  // evolved pendant GLV as a table (Gmix) or tensor (Gcat): Glv_edge.set_bl on pend (core.ml:234)
+  __device__ __noinline__ void set_pend(double bl) {
+    pend_bl = bl;
+    build_P(Pq, bl);
+    if (!GCAT) {
+      for (int idx = threadIdx.x; idx < nc * Rt * S; idx += THREADS) {
+        const int code = idx / (Rt * S), rs = idx - code * (Rt * S), r = rs / S, s = rs - r * S;
+        uint32_t mask = mask_of_code[code];
+        double acc = 0.0;
+        while (mask) { const int j = __ffs(mask) - 1; mask &= mask - 1; acc += Pq[r * RS + s * S + j]; }
+        Tp[idx] = acc;
+      }
+      __syncthreads();
+    }
+  }
+  __device__ void set_dist_prox(double d, double p) {
+    dist_bl = d; prox_bl = p;
+    build_P(Pd, d);
+    build_P(Pp, p);
+  }
+
+  __device__ __forceinline__ double pend_val(int cat, int code, int r, int s) const {
+    if (!GCAT) return Tp[code * (Rt * S) + r * S + s];
+    uint32_t mask = mask_of_code[code];
+    const double *row = Pq + cat * RS + s * S;
+    if ((mask & (mask - 1)) == 0) return row[__ffs(mask) - 1];
+    double acc = 0.0;
+    while (mask) { const int j = __ffs(mask) - 1; mask &= mask - 1; acc += row[j]; }
+    return acc;
+  }
+
+  // Three_tax.log_like over all of the query's sites with the current P matrices; optionally
+  // caches w[k][i] = (statd_s * prox_ev) * dist_ev for the pendant-only evaluations.
+  template <bool WRITE_W>
+  __device__ __forceinline__ double eval_full_impl() {
+    LogProd lp;
+    lp.init();
+    const int64_t Lp = g.Lp;
+    const double *dbase = g.a[0] + (int64_t)loc * g.a_stride;
+    const double *pbase = g.a[1] + (int64_t)loc * g.a_stride;
+    for (int i = threadIdx.x; i < nq; i += THREADS) {
+      const int site = qsite[i];
+      const int code = qcode[site] & 0x7f;
+      const int cat = GCAT ? site_cat[site] : 0;
+      double u = 0.0;
+      for (int r = 0; r < Rg; ++r) {
+        const double *Prd = Pd + (GCAT ? cat : r) * RS, *Prp = Pp + (GCAT ? cat : r) * RS;
+        double d[S], p[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          d[s] = dbase[(int64_t)(r * S + s) * Lp + site];
+          p[s] = pbase[(int64_t)(r * S + s) * Lp + site];
+        }
+#pragma unroll(S == 4 ? 4 : 1)
+        for (int s = 0; s < S; ++s) {
+          double de = 0.0, pe = 0.0;
+#pragma unroll
+          for (int j = 0; j < S; ++j) { de = fma(Prd[s * S + j], d[j], de); pe = fma(Prp[s * S + j], p[j], pe); }
+          const double ww = (statd[s] * pe) * de;  // ((statd*x)*y) with x = prox, y = dist (three_tax.ml:31-36)
+          if (WRITE_W) w[(int64_t)(r * S + s) * wstride + i] = ww;
+          u = fma(ww, pend_val(cat, code, r, s), u);
+        }
+      }
+      lp.mul(u);
+    }
+    return block_sum<THREADS>(lp.value(), red) - rate_term + e_tot_ln2;
+  }
+  __device__ __noinline__ double eval_full_cache() { return eval_full_impl<true>(); }
+  __device__ __noinline__ double eval_full_plain() { return eval_full_impl<false>(); }
+  template <bool WRITE_W>
+  __device__ __forceinline__ double eval_full() { return WRITE_W ? eval_full_cache() : eval_full_plain(); }
+
+  __device__ __noinline__ double eval_pend_cached() {
+    LogProd lp;
+    lp.init();
+    for (int i = threadIdx.x; i < nq; i += THREADS) {
+      const int site = qsite[i];
+      const int code = qcode[site] & 0x7f;
+      const int cat = GCAT ? site_cat[site] : 0;
+      double u = 0.0;
+      for (int r = 0; r < Rg; ++r)
+#pragma unroll(S == 4 ? 4 : 1)
+        for (int s = 0; s < S; ++s) u = fma(w[(int64_t)(r * S + s) * wstride + i], pend_val(cat, code, r, s), u);
+      lp.mul(u);
+    }
+    return block_sum<THREADS>(lp.value(), red) - rate_term + e_tot_ln2;
+  }
+
+  // core.ml:225-239 set_tt_edges (without the gather): fix the candidate and its branch lengths
+  __device__ void set_tt_edges(int loc_, double cut_bl, double pendant, double distal) {
+    loc = loc_;
+    long long es = 0;
+    for (int i = threadIdx.x; i < nq; i += THREADS) {
+      const int site = qsite[i];
+      es += (long long)g.e[0][(int64_t)loc * g.Lp + site] + (long long)g.e[1][(int64_t)loc * g.Lp + site];
+    }
+    es = block_sum_ll<THREADS>(es, reinterpret_cast<long long *>(red));
+    e_tot_ln2 = kLn2 * (double)es;  // ln2 * (total_twoexp prox + total_twoexp dist), gstar_support.ml:43-49
+    rate_term = GCAT ? 0.0 : (double)((float)nq) * log((double)((float)R));  // linear_c.c:421
+    set_pend(pendant);
+    set_dist_prox(distal, cut_bl - distal);
+  }
+
+  // ---- objective functions ----
+  struct Prior {
+    int kind;
+    double mean;
+    __device__ double operator()(double x) const {  // core.ml:87-92; gsl_ran_exponential_pdf
+      if (kind == 0) return 1.0;
+      if (x < 0.0) return 0.0;
+      return exp(-x / mean) / mean;
+    }
+  };
+  enum : int { OBJ_PEND = 0, OBJ_DIST = 1, OBJ_UPPER = 2 };
+  Prior prior;
+  double target_ll, base_ll, upper_limit, pp_rel_err;
+  int pp_status;
+
+  __device__ __noinline__ double objective(int kind, double v) {
+    if (kind == OBJ_PEND) {  // three_tax.ml:51-54 with set_pend_bl
+      calls++;
+      set_pend(v);
+      return -eval_pend_cached();
+    }
+    if (kind == OBJ_DIST) {  // three_tax.ml:41-45,51-54 with set_dist_bl
+      calls++;
+      const double prox = (dist_bl + prox_bl) - v;
+      if (!(prox >= 0.0)) return __longlong_as_double(0x7ff8000000000000LL);
+      set_dist_prox(v, prox);
+      return -eval_full_plain();
+    }
+    // OBJ_UPPER: three_tax.ml:144-150
+    set_pend(v);
+    const double like = eval_pend_cached() + log(prior(v));
+    const double x = fabs(target_ll - like);
+    return (x == __longlong_as_double(0x7ff0000000000000LL)) ? 100000.0 : x;
+  }
+
+  // Minimization.brent (minimization.ml:83-101) with bisection_start_finder (:24-41) and GSL's
+  // gsl_min_fminimizer_set + brent (GSL 2.7 min/fsolver.c, min/brent.c).
+  __device__ __noinline__ int brent(int kind, double raw_start, double left, double right, double tolerance,
+                                    int max_iters, double *xmin_out) {
+    auto f = [this, kind](double v) { return objective(kind, v); };
+    if (left >= raw_start || raw_start >= right) return ST_INVALID_START;
+    const double lefty = f(left), righty = f(right);
+    const double smaller = (lefty < righty) ? left : right;
+    double miny = fmin(lefty, righty);
+    if (lefty != lefty || righty != righty) miny = __longlong_as_double(0x7ff8000000000000LL);
+    double start, prev = raw_start;
+    for (int iter = 1;; ++iter) {
+      const double pv = f(prev);
+      if (pv < miny) { start = prev; break; }
+      if (fabs(prev - smaller) < tolerance) { *xmin_out = smaller; return ST_OK; }  // FoundMin
+      if (iter > max_iters) return ST_FIND_START_FAILURE;
+      prev = (prev + smaller) / 2.0;
+    }
+    double x_minimum = start, x_lower = left, x_upper = right;
+    double f_lower = f(x_lower);
+    if (!isfinite(f_lower)) return ST_GSL_EBADFUNC;
+    double f_upper = f(x_upper);
+    if (!isfinite(f_upper)) return ST_GSL_EBADFUNC;
+    double f_minimum = f(x_minimum);
+    if (!isfinite(f_minimum)) return ST_GSL_EBADFUNC;
+    if (x_lower > x_upper) return ST_GSL_EINVAL;
+    if (x_minimum >= x_upper || x_minimum <= x_lower) return ST_GSL_EINVAL;
+    if (f_minimum >= f_lower || f_minimum >= f_upper) return ST_GSL_EINVAL;
+    const double golden = 0.3819660;
+    double v = x_lower + golden * (x_upper - x_lower), wv = v, d = 0.0, e = 0.0;
+    const double f_vw = f(v);
+    if (!isfinite(f_vw)) return ST_GSL_EBADFUNC;
+    double f_v = f_vw, f_w = f_vw;
+    for (int step = 1;; ++step) {
+      if (step > max_iters) return ST_EXCEEDED_MAX_ITER;
+      const double x_left = x_lower, x_right = x_upper, z = x_minimum, f_z = f_minimum;
+      double dd = e, ee = d;  // GSL: d = state->e; e = state->d
+      double u;
+      const double w_lower = z - x_left, w_upper = x_right - z;
+      const double tol = kSqrtDblEps * fabs(z);
+      double p = 0.0, q = 0.0, r = 0.0;
+      const double midpoint = 0.5 * (x_left + x_right);
+      if (fabs(ee) > tol) {
+        r = (z - wv) * (f_z - f_v);
+        q = (z - v) * (f_z - f_w);
+        p = (z - v) * q - (z - wv) * r;
+        q = 2.0 * (q - r);
+        if (q > 0.0) p = -p; else q = -q;
+        r = ee;
+        ee = dd;
+      }
+      if (fabs(p) < fabs(0.5 * q * r) && p < q * w_lower && p < q * w_upper) {
+        const double t2 = 2.0 * tol;
+        dd = p / q;
+        u = z + dd;
+        if ((u - x_left) < t2 || (x_right - u) < t2) dd = (z < midpoint) ? tol : -tol;
+      } else {
+        ee = (z < midpoint) ? x_right - z : -(z - x_left);
+        dd = golden * ee;
+      }
+      if (fabs(dd) >= tol) u = z + dd; else u = z + ((dd > 0.0) ? tol : -tol);
+      e = ee;
+      d = dd;
+      const double f_u = f(u);
+      if (!isfinite(f_u)) return ST_GSL_EBADFUNC;
+      if (f_u <= f_z) {
+        if (u < z) { x_upper = z; f_upper = f_z; } else { x_lower = z; f_lower = f_z; }
+        v = wv; f_v = f_w; wv = z; f_w = f_z; x_minimum = u; f_minimum = f_u;
+      } else {
+        if (u < z) { x_lower = u; f_lower = f_u; } else { x_upper = u; f_upper = f_u; }
+        if (f_u <= f_w || wv == z) { v = wv; f_v = f_w; wv = u; f_w = f_u; }
+        else if (f_u <= f_v || v == z || v == wv) { v = u; f_v = f_u; }
+      }
+      if (x_upper - x_lower < tolerance) { *xmin_out = x_minimum; return ST_OK; }
+    }
+  }
+
+  // Three_tax.optimize (three_tax.ml:70-83)
+  __device__ __noinline__ int optimize(double tolerance, double max_pend, int max_iter) {
+    double prev_pend = pend_bl, prev_dist = dist_bl;
+    for (int step = 1;; ++step) {
+      if (step > max_iter) return ST_EXCEEDED_MAX_ITER;
+      double curr_pend = pend_bl, curr_dist = dist_bl;
+      if (1e-8 != max_pend) {
+        (void)eval_full_cache();  // cache w for the pendant-only evaluations
+        const int st = brent(OBJ_PEND, pend_bl, 1e-8, max_pend, tolerance, 100, &curr_pend);
+        if (st != ST_OK) return st;
+      }
+      const double cut = dist_bl + prox_bl;
+      if (0.0 != cut) {
+        const int st = brent(OBJ_DIST, dist_bl, 0.0, cut, tolerance, 100, &curr_dist);
+        if (st != ST_OK) return st;
+      }
+      if (fabs(prev_pend - curr_pend) > tolerance || fabs(prev_dist - curr_dist) > tolerance) {
+        prev_pend = curr_pend;
+        prev_dist = curr_dist;
+      } else
+        return ST_OK;
+    }
+  }
+
+  // ---- --pp : Three_tax.calc_marg_prob (three_tax.ml:169-215) ----
+  __device__ int find_upper_limit(double max_pend, double orig_ll, double *out) {  // :124-159
+    const double orig_pend = pend_bl;
+    if (prior(orig_pend) == 0.0) {
+      double curr = orig_pend;
+      for (;;) {
+        const double next = curr / 2.0;
+        if (prior(next) > exp(-10.0)) { *out = curr; return ST_OK; }
+        curr = next;
+      }
+    }
+    target_ll = -10.0 + orig_ll + log(prior(orig_pend));
+    const double start = orig_pend + ((max_pend - orig_pend) / 2.0);
+    const int st = brent(OBJ_UPPER, start, orig_pend, max_pend, 0.02, 10, out);
+    if (st == ST_GSL_EINVAL) { *out = max_pend; return ST_OK; }
+    return st;
+  }
+
+  static __device__ double rescale_error(double err, double result_abs, double result_asc) {
+    err = fabs(err);
+    if (result_asc != 0.0 && err != 0.0) {
+      const double scale = pow((200.0 * err / result_asc), 1.5);
+      err = (scale < 1.0) ? result_asc * scale : result_asc;
+    }
+    if (result_abs > 2.2250738585072014e-308 / (50.0 * kDblEps)) {
+      const double min_err = 50.0 * kDblEps * result_abs;
+      if (min_err > err) err = min_err;
+    }
+    return err;
+  }
+
+  // integrands: inner (three_tax.ml:187-189) and outer (:192-197)
+  __device__ __noinline__ double integrand_inner(double pend) {
+    set_pend(pend);
+    return exp(eval_pend_cached() - base_ll) * prior(pend);
+  }
+  __device__ __noinline__ double integrand_outer(double dist) {
+    if (pp_status) return 0.0;  // the reference's exception is already unwinding
+    const double prox = (dist_bl + prox_bl) - dist;
+    if (!(prox >= 0.0)) { pp_status = ST_ASSERT; return 0.0; }
+    set_dist_prox(dist, prox);
+    (void)eval_full_cache();
+    double res;
+    const int st = qng<false>(0.0, upper_limit, 0.0, pp_rel_err, &res);
+    if (st) pp_status = st;
+    return res;
+  }
+
+  // gsl_integration_qng (GSL 2.7 integration/qng.c)
+  template <bool OUTER>
+  __device__ __noinline__ int qng(double a, double b, double epsabs, double epsrel, double *result) {
+    auto f = [this](double v) { return OUTER ? integrand_outer(v) : integrand_inner(v); };
+    double fv1[5], fv2[5], fv3[5], fv4[5], savfun[21];
+    const double half_length = 0.5 * (b - a), abs_half_length = fabs(half_length), center = 0.5 * (b + a);
+    const double f_center = f(center);
+    if (epsabs <= 0.0 && (epsrel < 50.0 * kDblEps || epsrel < 0.5e-28)) { *result = 0.0; return ST_GSL_EBADTOL; }
+    double res10 = 0.0, res21 = c_qng_w21b[5] * f_center, resabs = c_qng_w21b[5] * fabs(f_center);
+    for (int k = 0; k < 5; ++k) {
+      const double ab = half_length * c_qng_x1[k];
+      const double f1 = f(center + ab), f2 = f(center - ab), fv = f1 + f2;
+      res10 += c_qng_w10[k] * fv;
+      res21 += c_qng_w21a[k] * fv;
+      resabs += c_qng_w21a[k] * (fabs(f1) + fabs(f2));
+      savfun[k] = fv; fv1[k] = f1; fv2[k] = f2;
+    }
+    for (int k = 0; k < 5; ++k) {
+      const double ab = half_length * c_qng_x2[k];
+      const double f1 = f(center + ab), f2 = f(center - ab), fv = f1 + f2;
+      res21 += c_qng_w21b[k] * fv;
+      resabs += c_qng_w21b[k] * (fabs(f1) + fabs(f2));
+      savfun[k + 5] = fv; fv3[k] = f1; fv4[k] = f2;
+    }
+    resabs *= abs_half_length;
+    const double mean = 0.5 * res21;
+    double resasc = c_qng_w21b[5] * fabs(f_center - mean);
+    for (int k = 0; k < 5; ++k)
+      resasc += (c_qng_w21a[k] * (fabs(fv1[k] - mean) + fabs(fv2[k] - mean)) +
+                 c_qng_w21b[k] * (fabs(fv3[k] - mean) + fabs(fv4[k] - mean)));
+    resasc *= abs_half_length;
+    double result_kronrod = res21 * half_length;
+    double err = rescale_error((res21 - res10) * half_length, resabs, resasc);
+    if (err < epsabs || err < epsrel * fabs(result_kronrod)) { *result = result_kronrod; return ST_OK; }
+    double res43 = c_qng_w43b[11] * f_center;
+    for (int k = 0; k < 10; ++k) res43 += savfun[k] * c_qng_w43a[k];
+    for (int k = 0; k < 11; ++k) {
+      const double ab = half_length * c_qng_x3[k];
+      const double fv = f(center + ab) + f(center - ab);
+      res43 += fv * c_qng_w43b[k];
+      savfun[k + 10] = fv;
+    }
+    result_kronrod = res43 * half_length;
+    err = rescale_error((res43 - res21) * half_length, resabs, resasc);
+    if (err < epsabs || err < epsrel * fabs(result_kronrod)) { *result = result_kronrod; return ST_OK; }
+    double res87 = c_qng_w87b[22] * f_center;
+    for (int k = 0; k < 21; ++k) res87 += savfun[k] * c_qng_w87a[k];
+    for (int k = 0; k < 22; ++k) {
+      const double ab = half_length * c_qng_x4[k];
+      res87 += c_qng_w87b[k] * (f(center + ab) + f(center - ab));
+    }
+    result_kronrod = res87 * half_length;
+    err = rescale_error((res87 - res43) * half_length, resabs, resasc);
+    *result = result_kronrod;
+    if (err < epsabs || err < epsrel * fabs(result_kronrod)) return ST_OK;
+    return ST_GSL_ETOL;
+  }
+
+  __device__ int calc_marg_prob(double rel_err, double max_pend, double *out) {
+    pp_rel_err = rel_err;
+    base_ll = eval_full_cache();
+    const double cut_bl = dist_bl + prox_bl;
+    int st = find_upper_limit(max_pend, base_ll, &upper_limit);
+    if (st) return st;
+    for (int n_exceptions = 0;; ++n_exceptions) {
+      if (n_exceptions >= 10) { *out = base_ll; return ST_OK; }
+      pp_status = 0;
+      double val;
+      if (fabs(cut_bl - 0.0) < 1e-5) {  // cut_bl =~ 0.  (ppatteries.ml:96)
+        set_dist_prox(cut_bl / 2.0, (dist_bl + prox_bl) - cut_bl / 2.0);
+        (void)eval_full_cache();
+        pp_status = qng<false>(0.0, upper_limit, 0.0, rel_err, &val);
+      } else {
+        double res;
+        const int so = qng<true>(0.0, cut_bl, 0.0, rel_err, &res);
+        if (!pp_status && so) pp_status = so;
+        val = res / cut_bl;
+      }
+      if (pp_status == ST_GSL_ETOL) { upper_limit = upper_limit / 2.0; continue; }
+      if (pp_status) return pp_status;
+      *out = base_ll + log(val);
+      return ST_OK;
+    }
+  }
+};
+
+// Persistent kernel: blocks pull candidates from `counter` until n are done.
+template <int S, bool GCAT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+three_tax_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__restrict__ bl,
+                 const int32_t *__restrict__ site_cat, const uint8_t *__restrict__ codes,
+                 const int32_t *__restrict__ qsite, const int32_t *__restrict__ nq, const CandIn *__restrict__ in,
+                 CandOut *__restrict__ out, int n, TTParams prm, double *__restrict__ wbuf, int *counter) {
+  extern __shared__ double sm[];
+  __shared__ int s_idx;
+  ThreeTax<S, GCAT, THREADS> tt;
+  tt.g = g;
+  tt.carve(sm, m);
+  tt.site_cat = site_cat;
+  tt.wstride = g.Lp;
+  tt.w = wbuf + (int64_t)blockIdx.x * tt.K * g.Lp;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_idx = atomicAdd(counter, 1);
+    __syncthreads();
+    const int idx = s_idx;
+    if (idx >= n) break;
+    const CandIn c = in[idx];
+    tt.qsite = qsite + (int64_t)c.q * g.Lp;
+    tt.qcode = codes + (int64_t)c.q * g.Lp;
+    tt.nq = nq[c.q];
+    tt.calls = 0;
+    const double cut_bl = bl[c.loc];
+    CandOut o;
+    o.marg = __longlong_as_double(0x7ff8000000000000LL);
+    const double p0 = prm.use_defaults ? prm.start_pend : c.pend0;
+    const double d0 = prm.use_defaults ? cut_bl / 2.0 : c.dist0;
+    tt.set_tt_edges(c.loc, cut_bl, p0, d0);
+    int st = ST_OK;
+    if (prm.mode == TT_MODE_OPTIMIZE) {
+      // core.ml:254-279: ExceededMaxIter keeps the current state; a GSL error retries once from the
+      // default branch lengths (tt_edges_default, core.ml:240-245).
+      st = tt.optimize(prm.tol, prm.max_pend, prm.max_iter);
+      if (st_is_gsl(st)) {
+        tt.set_tt_edges(c.loc, cut_bl, prm.start_pend, cut_bl / 2.0);
+        st = tt.optimize(prm.tol, prm.max_pend, prm.max_iter);
+      }
+      if (st == ST_EXCEEDED_MAX_ITER) st = ST_OK;
+      o.ll = tt.template eval_full<false>();  // Three_tax.get_results (three_tax.ml:85)
+    } else if (prm.mode == TT_MODE_LOGLIKE) {
+      o.ll = tt.template eval_full<false>();
+    } else {
+      tt.prior.kind = prm.prior_kind;
+      tt.prior.mean = prm.prior_kind == 2 ? prm.prior_means[c.loc] : prm.prior_mean;
+      double mp = __longlong_as_double(0x7ff8000000000000LL);
+      st = tt.calc_marg_prob(prm.pp_rel_err, prm.max_pend, &mp);
+      o.marg = mp;
+      o.ll = mp;
+    }
+    o.pend = tt.pend_bl;
+    o.dist = tt.dist_bl;
+    o.status = st;
+    o.calls = tt.calls;
+    if (threadIdx.x == 0) out[idx] = o;
+  }
+}
+
+}  // namespace ppb
