@@ -135,13 +135,16 @@ def flat_exp_prior_mean(tree: Tree) -> float:
     return tree.tree_length() / float(tree.n_edges())
 
 
-def informative_prior_means(tree: Tree, prior_lower: float = 0.0) -> np.ndarray:
-    """Core.prior_mean_map ((+.) prior_lower) (core.ml:34-52): for edge i, the average over leaves
-    below i of (distance from the leaf up to the bottom of edge i) + (prior_lower + bl_i)."""
+def informative_prior_means(tree: Tree, prior_lower: float = 0.0, top_segment_f=None) -> np.ndarray:
+    """Core.prior_mean_map top_segment_f (core.ml:34-52): for edge i, the average over leaves below
+    i of (distance from the leaf up to the bottom of edge i) + top_segment_f(bl_i).  pplacer passes
+    top_segment_f = (+.) prior_lower (pplacer_run.ml:380-386), the default here."""
+    if top_segment_f is None:
+        top_segment_f = lambda b: prior_lower + b
     out = np.full(tree.n_nodes, np.nan)
     dists: Dict[int, List[float]] = {}
     for node in tree.postorder():
-        top = prior_lower + tree.bl[node]
+        top = top_segment_f(float(tree.bl[node]))
         if not tree.children[node]:
             out[node] = top
             dists[node] = [float(tree.bl[node])]

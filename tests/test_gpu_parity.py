@@ -1,0 +1,327 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libpplacer_b200.so), against the
+CPU oracle on the same seeded inputs, against the reference's own known answers, and through
+size-independent properties.  Tolerances are the north_star's: identical best edge and kept-edge
+sets except at documented near-ties, log-likelihood 1e-6 relative, branch lengths 1e-4,
+like_weight_ratio / post_prob 1e-5 absolute."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from pplacer_b200 import _lib, configs, reference, seqio
+from pplacer_b200.placer import Placer
+from tests.util import assert_placements_match
+
+pytestmark = pytest.mark.gpu
+
+PROBLEMS = {
+    "c1_gtr": lambda: configs.c1(),
+    "wag": lambda: configs.like_problem("wag", seed=11),
+    "gcat_dna": lambda: configs.gcat_variant("gtr"),
+    "gcat_aa": lambda: configs.gcat_variant("wag"),
+    "synth": lambda: configs.synthetic(60, 300, 64, seed=7, min_len=40),
+}
+_cache = {}
+
+
+def setup(name, oracle_binding):
+    if name not in _cache:
+        prob = PROBLEMS[name]()
+        o = oracle_binding.Oracle(prob)
+        o.precompute()
+        p = Placer(prob)
+        p.precompute()
+        _cache[name] = (prob, o, p)
+    return _cache[name]
+
+
+def oracle_prefs(ob, prob, **kw):
+    return ob.default_prefs(prior_mean=reference.flat_exp_prior_mean(prob.tree), **kw)
+
+
+# ---------------------------------------------------------------------------------------------
+# known answers of the reference, through the GPU
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["gtr", "wag", "jtt"])
+def test_phyml_tree_likelihood_at_every_edge(name):
+    """tests/pplacer/test_like.ml:57-66 on device: with an all-ones query (N / X everywhere)
+    masked_logdot(snode_i) and log_like3(evolve(d_i,bl/2), evolve(p_i,bl/2), 1) are the tree
+    log-likelihood PhyML reports, at EVERY edge, to 1e-7 relative."""
+    tree, aln, model = configs.like_inputs(name)
+    any_char = "N" if model.n_states == 4 else "X"
+    L = len(aln[0][1])
+    prob = reference.build_problem(tree, model, aln, [("ones", any_char * L)], pre_mask=False)
+    want = configs.PHYML_LL[name]
+    with Placer(prob) as p:
+        p.precompute()
+        scores = p.prefilter_scores(prob.query_chars)[0]
+        for e in range(tree.n_nodes):
+            if e == tree.root:
+                assert np.isnan(scores[e])
+            else:
+                assert abs(scores[e] - want) <= 1e-7 * abs(want), (e, scores[e], want)
+        edges = np.array(tree.nonroot_ids(), dtype=np.int32)
+        q = np.repeat(prob.query_chars, len(edges), axis=0)
+        ll = p.three_tax_log_like(q, edges, np.full(len(edges), 0.37), tree.bl[edges] / 2.0)
+        assert np.all(np.abs(ll - want) <= 1e-7 * abs(want)), (ll, want)
+
+
+# ---------------------------------------------------------------------------------------------
+# stage by stage against the oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1_gtr", "wag", "gcat_dna", "gcat_aa"])
+def test_precompute_glvs_match_oracle(oracle_binding, name):
+    prob, o, p = setup(name, oracle_binding)
+    exp_equal = exp_total = 0
+    for which in (0, 1, 2):
+        for node in range(prob.tree.n_nodes):
+            if which == 0 and False:
+                continue
+            a, e = p.glv(which, node)
+            oa, oe = o.glv(which, node)
+            sh = (1, -1, 1) if a.ndim == 3 else (-1, 1)
+            va = a * np.exp2(e.reshape(sh).astype(float))
+            vo = oa * np.exp2(oe.reshape(sh).astype(float))
+            assert np.allclose(va, vo, rtol=1e-11, atol=0.0), (which, node)
+            exp_equal += int((e == oe).sum())
+            exp_total += e.size
+    # exponent pulls happen at the same sites (a boundary flip needs max|a| within an ulp of 2^-k)
+    assert exp_equal == exp_total
+
+
+@pytest.mark.parametrize("name", ["c1_gtr", "wag", "gcat_dna", "gcat_aa", "synth"])
+def test_prefilter_scores_and_ranking_match_oracle(oracle_binding, name):
+    prob, o, p = setup(name, oracle_binding)
+    _, _, st, info = o.place(prob.query_chars, oracle_prefs(oracle_binding, prob), n_threads=4, debug=True)
+    want = info["scores"]
+    got = p.prefilter_scores(prob.query_chars)
+    root = prob.tree.root
+    assert np.isnan(got[:, root]).all()
+    keep = [i for i in range(prob.tree.n_nodes) if i != root]
+    g, w = got[:, keep], want[:, keep]
+    assert np.all(np.abs(g - w) <= 1e-10 * np.abs(w)), np.abs((g - w) / w).max()
+    # ranking (fig.ml:143-147): identical order wherever the oracle's scores are not tied to 1e-9
+    for q in range(g.shape[0]):
+        og, ow = np.argsort(-g[q], kind="stable"), np.argsort(-w[q], kind="stable")
+        for a, b in zip(og[:41], ow[:41]):
+            assert a == b or abs(w[q][a] - w[q][b]) <= 1e-9 * abs(w[q][a]), (q, a, b)
+
+
+@pytest.mark.parametrize("name", ["c1_gtr", "wag", "gcat_dna", "gcat_aa"])
+def test_three_tax_log_like_matches_oracle(oracle_binding, name):
+    prob, o, p = setup(name, oracle_binding)
+    rng = np.random.default_rng(3)
+    Q = prob.query_chars.shape[0]
+    n = 96
+    qi = rng.integers(0, Q, size=n)
+    edges = rng.choice(np.array(prob.tree.nonroot_ids()), size=n).astype(np.int32)
+    pend = rng.uniform(1e-8, 2.0, size=n)
+    dist = rng.uniform(0.0, 1.0, size=n) * prob.tree.bl[edges]
+    got = p.three_tax_log_like(prob.query_chars[qi], edges, pend, dist)
+    want = np.array([o.three_tax_ll(prob.query_chars[qi[i]], int(edges[i]), float(pend[i]), float(dist[i])) for i in range(n)])
+    assert np.all(np.abs(got - want) <= 1e-11 * np.abs(want)), np.abs((got - want) / want).max()
+
+
+@pytest.mark.parametrize("name", ["c1_gtr", "gcat_aa"])
+def test_evolve_matches_oracle(oracle_binding, name):
+    """pp_evolve (Model.evolve_into) against the oracle's multi_exp + the reference's own gemmish_c."""
+    prob, o, p = setup(name, oracle_binding)
+    a, e = o.glv(0, prob.tree.children[prob.tree.root][0])
+    bl = 0.2371
+    got_a, got_e = p.evolve(a, e, bl)
+    assert np.array_equal(got_e, e)
+    P = oracle_binding.multi_exp(o.x, o.lam, o.xit, o.rates, bl)
+    if prob.model.model_class == 0:
+        want = np.einsum("rij,rlj->rli", P, a)
+    else:
+        want = np.einsum("lij,lj->li", P[prob.site_cat], a)
+    assert np.allclose(got_a, want, rtol=1e-12, atol=1e-300)
+
+
+# ---------------------------------------------------------------------------------------------
+# the path end to end
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1_gtr", "wag", "gcat_dna", "gcat_aa", "synth"])
+def test_place_matches_oracle(oracle_binding, name):
+    prob, o, p = setup(name, oracle_binding)
+    exp, n_exp, st_exp, oinfo = o.place(prob.query_chars, oracle_prefs(oracle_binding, prob), n_threads=4, debug=True)
+    got, n_got, st_got, info = p.place(prob.query_chars, p.prefs(), debug=True)
+    near = assert_placements_match(got, n_got, st_got, exp, n_exp, st_exp, near_tie_ll=1e-3)
+    assert len(near) <= max(1, len(n_exp) // 50), near
+    # baseball visits the same number of locations (same stop rules on the same ranking)
+    same = (info["n_pitches"] == oinfo["n_pitches"]).mean()
+    assert same >= 0.98, (info["n_pitches"], oinfo["n_pitches"])
+    # objective-evaluation counts agree closely (identical Brent state machines; FMA-level
+    # differences in f can change a trajectory only at exact ties)
+    rel = np.abs(info["n_like_calls"] - oinfo["n_like_calls"]) / np.maximum(oinfo["n_like_calls"], 1)
+    assert np.median(rel) <= 0.02, (info["n_like_calls"][:8], oinfo["n_like_calls"][:8])
+
+
+@pytest.mark.parametrize("name", ["c1_gtr", "gcat_aa"])
+def test_place_posterior_probability_matches_oracle(oracle_binding, name):
+    """-p: marginal likelihood by nested QNG (three_tax.ml:169-215), keep_at_most 20,
+    keep_factor 0.001, max_strikes 20 (prefs.ml:198-203).  Parity UNPINNED in the reference - the
+    oracle restatement of GSL's qng is the arbiter."""
+    prob, o, p = setup(name, oracle_binding)
+    op = oracle_prefs(oracle_binding, prob, calc_pp=1, keep_at_most=20, keep_factor=0.001, max_strikes=20)
+    sub = prob.query_chars[:12]
+    exp, n_exp, st_exp, _ = o.place(sub, op, n_threads=4)
+    got, n_got, st_got, _ = p.place(sub, p.prefs(pp=True))
+    near = assert_placements_match(got, n_got, st_got, exp, n_exp, st_exp, pp=True, near_tie_ll=1e-3)
+    assert len(near) <= 1
+    for q in range(len(n_got)):
+        r = got[q][:n_got[q]]
+        assert abs(r["post_prob"].sum() - 1.0) < 1e-9
+
+
+def test_place_informative_and_uniform_priors(oracle_binding):
+    prob, o, p = setup("c1_gtr", oracle_binding)
+    sub = prob.query_chars[:6]
+    means = np.ascontiguousarray(np.nan_to_num(reference.informative_prior_means(prob.tree), nan=1.0))
+    for kind in (0, 2):
+        op = oracle_prefs(oracle_binding, prob, calc_pp=1, keep_at_most=20, keep_factor=0.001, max_strikes=20, prior_kind=kind)
+        if kind == 2:
+            op.prior_means = oracle_binding.dp(means)
+        exp, n_exp, st_exp, _ = o.place(sub, op, n_threads=2)
+        got, n_got, st_got, _ = p.place(sub, p.prefs(pp=True, uniform_prior=(kind == 0), informative_prior=(kind == 2)))
+        assert_placements_match(got, n_got, st_got, exp, n_exp, st_exp, pp=True, near_tie_ll=1e-3)
+
+
+def test_edge_cases(oracle_binding):
+    """Ragged and degenerate inputs: one informative site, all-N query, no
+    informative site (core.ml:157 -> status 103), unknown character (-> 105), keep_at_most 1,
+    max_strikes 0 (= optimise every edge, core.ml:100-102), Q = 1."""
+    prob, o, p = setup("c1_gtr", oracle_binding)
+    L = prob.L
+    base = prob.query_chars[0].copy()
+    one = np.full(L, ord("-"), np.uint8); one[L // 2] = base[L // 2] if base[L // 2] != ord("-") else ord("A")
+    alln = np.full(L, ord("N"), np.uint8)
+    gaps = np.full(L, ord("-"), np.uint8)
+    bad = base.copy(); bad[3] = ord("J")
+    amb = base.copy(); amb[::5] = ord("R"); amb[1::7] = ord("?")
+    qs = np.stack([one, alln, gaps, bad, amb, base])
+    op = oracle_prefs(oracle_binding, prob)
+    exp, n_exp, st_exp, _ = o.place(qs, op)
+    got, n_got, st_got, _ = p.place(qs, p.prefs())
+    assert list(st_exp) == [0, 0, 103, 105, 0, 0]
+    assert_placements_match(got, n_got, st_got, exp, n_exp, st_exp, near_tie_ll=1e-3)
+    # keep_at_most 1 and a single query
+    exp, n_exp, st_exp, _ = o.place(qs[5:6], oracle_prefs(oracle_binding, prob, keep_at_most=1))
+    got, n_got, st_got, _ = p.place(qs[5:6], p.prefs(keep_at_most=1))
+    assert n_got[0] == 1 and got[0][0]["ml_ratio"] == 1.0
+    assert_placements_match(got, n_got, st_got, exp, n_exp, st_exp)
+    # max_strikes 0: every edge is optimised
+    sub = prob.query_chars[:4]
+    exp, n_exp, st_exp, oi = o.place(sub, oracle_prefs(oracle_binding, prob, max_strikes=0), debug=True)
+    got, n_got, st_got, gi = p.place(sub, p.prefs(max_strikes=0), debug=True)
+    assert np.all(gi["n_pitches"] == prob.tree.n_nodes - 1) and np.array_equal(gi["n_pitches"], oi["n_pitches"])
+    assert_placements_match(got, n_got, st_got, exp, n_exp, st_exp, near_tie_ll=1e-3)
+    # Q = 0 is a no-op
+    got, n_got, st_got, _ = p.place(np.zeros((0, L), np.uint8), p.prefs())
+    assert got.shape[0] == 0
+
+
+def test_api_errors():
+    prob = configs.c1()
+    with Placer(prob) as p:
+        with pytest.raises(_lib.PplacerB200Error) as ei:
+            p.prefilter_scores(prob.query_chars[:1])      # before precompute
+        assert ei.value.code == _lib.PP_ESTATE
+        with pytest.raises(ValueError, match="not the same length"):
+            p.place(prob.query_chars[:, :-1])
+        p.precompute()
+        with pytest.raises(_lib.PplacerB200Error) as ei:
+            p.place(prob.query_chars[:1], p.prefs(keep_at_most=0))
+        assert ei.value.code == _lib.PP_EINVAL
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at the bench shape (C2: 800 taxa x 1500 columns)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c2_small():
+    prob = configs.c2(Q=1536)
+    p = Placer(prob)
+    p.precompute()
+    yield prob, p
+    p.close()
+
+
+def test_c2_properties(c2_small, oracle_binding):
+    prob, p = c2_small
+    Q = prob.query_chars.shape[0]
+    out, n_out, st, info = p.place(prob.query_chars, p.prefs(), debug=True)
+    assert (st == 0).all() and (n_out >= 1).all() and (n_out <= 7).all()
+    for q in range(Q):
+        r = out[q][:n_out[q]]
+        assert abs(r["ml_ratio"].sum() - 1.0) < 1e-9                     # weights normalised
+        assert np.all(np.diff(r["ml_ratio"]) <= 0)                        # sorted descending
+        assert np.all(r["log_like"] >= r["log_like"].max() + np.log(0.01) - 1e-9)   # keep_factor
+        assert len(set(r["edge"].tolist())) == n_out[q]
+        assert np.all((r["pendant"] >= 1e-8) & (r["pendant"] <= 2.0))
+        assert np.all((r["distal"] >= 0) & (r["distal"] <= prob.tree.bl[r["edge"]] + 1e-12))
+        # the best placement's likelihood is at least the best prefilter-ranked start
+        assert np.isfinite(r["log_like"]).all()
+    # idempotent / deterministic: a second pass gives the same bytes
+    out2, n2, st2, _ = p.place(prob.query_chars, p.prefs())
+    assert out.tobytes() == out2.tobytes() and np.array_equal(n_out, n2)
+    # order- and batch-independent: a permuted subset gives the same per-query records
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(Q)[:300]
+    out3, n3, st3, _ = p.place(prob.query_chars[perm], p.prefs())
+    assert out3.tobytes() == out[perm].tobytes() and np.array_equal(n3, n_out[perm])
+    # oracle spot check on a sample
+    o = oracle_binding.Oracle(prob)
+    o.precompute()
+    idx = perm[:48]
+    exp, n_exp, st_exp, _ = o.place(prob.query_chars[idx], oracle_prefs(oracle_binding, prob), n_threads=8)
+    near = assert_placements_match(out[idx], n_out[idx], st[idx], exp, n_exp, st_exp, near_tie_ll=1e-3)
+    assert len(near) <= 2
+    o.close()
+
+
+def test_device_resident_entry_point_matches_host_entry_point(c2_small):
+    import torch
+    prob, p = c2_small
+    q = prob.query_chars[:256]
+    out, n_out, st, _ = p.place(q, p.prefs())
+    d_chars = torch.from_numpy(q).cuda()
+    d_out = torch.zeros(q.shape[0] * 7 * 56, dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(q.shape[0], dtype=torch.int32, device="cuda")
+    d_st = torch.zeros(q.shape[0], dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    p.place_device(d_chars.data_ptr(), q.shape[0], d_out.data_ptr(), d_n.data_ptr(), d_st.data_ptr(), p.prefs())
+    torch.cuda.synchronize()
+    assert d_out.cpu().numpy().tobytes() == out.tobytes()
+    assert np.array_equal(d_n.cpu().numpy(), n_out) and np.array_equal(d_st.cpu().numpy(), st)
+
+
+# ---------------------------------------------------------------------------------------------
+# C3: the reference's only end-to-end golden (donovan-test ar53, WAG + Price-CAT 20)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.slow
+def test_ar53_golden_placements():
+    import torch
+    if not configs.ar53_available():
+        pytest.skip("tests/golden/_ar53 fixture not present (tests/golden/make_fixtures.py --ar53)")
+    if torch.cuda.get_device_properties(0).total_memory < 80e9:
+        pytest.skip("needs ~58 GB of HBM")
+    prob = configs.ar53()
+    assert prob.L == 8035 and prob.tree.n_nodes == 13934
+    gold = configs.ar53_golden()["GOLDEN"]
+    fields = gold["fields"]
+    want = {pq["nm"][0][0]: dict(zip(fields, pq["p"][0])) for pq in gold["placements"]}
+    with Placer(prob) as p:
+        p.precompute()
+        out, n_out, st, info = p.place(prob.query_chars, p.prefs(), debug=True)
+    assert (st == 0).all()
+    for q, names in enumerate(prob.query_names):
+        g = want[names[0]]
+        assert n_out[q] == 1
+        r = out[q][0]
+        assert int(r["edge"]) == g["edge_num"], (names, r, g)
+        assert abs(r["log_like"] - g["likelihood"]) <= 1e-6 * abs(g["likelihood"])
+        assert abs(r["pendant"] - g["pendant_length"]) <= 1e-4
+        assert abs(r["distal"] - g["distal_length"]) <= 1e-4
+        assert abs(r["ml_ratio"] - g["like_weight_ratio"]) <= 1e-5

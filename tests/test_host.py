@@ -1,0 +1,71 @@
+"""Host-side logic either side of the kernels: Newick numbering, pre-masking, de-duplication,
+alphabet checks, config builders, query sharding.  CPU only."""
+import numpy as np
+import pytest
+
+from pplacer_b200 import configs, models, newick, reference, seqio, shard, synth
+
+
+def test_newick_postorder_numbering():
+    # newick_parser.mly:49-62: ids assigned in post-order = jplace edge numbers
+    t = newick.parse("((A:2,B:9):7,C:5,D:1):0;")
+    assert t.n_nodes == 6 and t.root == 5
+    assert t.children[5] == [2, 3, 4] and t.children[2] == [0, 1]
+    assert [t.node_label[i] for i in (0, 1, 3, 4)] == ["A", "B", "C", "D"]
+    assert np.allclose(t.bl, [2, 9, 7, 5, 1, 0])
+    assert t.to_newick() == "((A:2{0},B:9{1}):7{2},C:5{3},D:1{4}){5};"
+    # quoted labels may hold ':' ';' ',' (ar53 has 1416 of them); {n} overrides numbering
+    t2 = newick.parse("('x:1;y',(b,'c d')'100.0:p__X;c__Y':0.5);")
+    assert t2.node_label[0] == "x:1;y" and t2.node_label[3] == "100.0:p__X;c__Y"
+    t3 = newick.parse("((A:1{1},B:2{0}):1{2},C:3{3}){4};")
+    assert t3.node_label[1] == "A" and t3.node_label[0] == "B"
+    rt = newick.parse(t3.to_newick())
+    assert rt.children == t3.children
+    with pytest.raises(newick.NewickError):
+        newick.parse("((A,B);")
+
+
+def test_premask_and_dedup():
+    tree = newick.parse("((A:0.1,B:0.2):0.1,C:0.3,D:0.1):0;")
+    m = models.ModelSpec(4, 0, "GTR", models.gtr_exch(1, 2, 1, 1, 2, 1), None, True, 4, 0.5, None, None)
+    ref = [("A", "AC-GT-A"), ("B", "AC-GA-A"), ("C", "AT-GT-C"), ("D", "AC-GT-A")]
+    qs = [("q1", "ac-g---"), ("q2", "AC-G---"), ("q3", "-CAG---")]
+    p = reference.build_problem(tree, m, ref, qs)
+    # columns 2 and 5 are all-gap in the reference, 4 and 6 all-gap in the queries
+    assert list(np.nonzero(p.mask)[0]) == [0, 1, 3]
+    assert p.L == 3 and p.L_raw == 7
+    assert p.query_names == [["q1", "q2"], ["q3"]]            # upper-cased then de-duplicated
+    assert p.query_chars.tobytes() == b"ACG-CG"
+    assert list(p.leaf_row[:2]) == [0, 1]
+    with pytest.raises(ValueError, match="not a known base"):
+        reference.build_problem(tree, m, ref, [("bad", "ACJGT-A")])
+    with pytest.raises(ValueError, match="not the same length"):
+        reference.build_problem(tree, m, ref, [("short", "ACG")])
+    with pytest.raises(ValueError, match="doesn't overlap"):
+        reference.build_problem(tree, m, ref, [("nov", "--A----")])
+
+
+def test_gcat_site_categories_follow_premask():
+    prob = configs.gcat_variant("gtr")
+    assert prob.model.model_class == 1
+    assert len(prob.site_cat) == prob.L
+    assert np.array_equal(prob.site_cat, prob.model.site_cat[prob.mask])
+
+
+def test_synthetic_problem_shapes():
+    prob = configs.synthetic(24, 120, 16, seed=3, min_len=30)
+    assert prob.tree.n_nodes == 2 * 24 - 2 and len(prob.tree.children[prob.tree.root]) == 3
+    assert prob.ref_chars.shape[0] == 24 and prob.query_chars.shape[1] == prob.L
+    inf = seqio.informative(prob.query_chars).sum(axis=1)
+    assert inf.min() >= 1
+    again = configs.synthetic(24, 120, 16, seed=3, min_len=30)
+    assert np.array_equal(prob.query_chars, again.query_chars)  # seeded
+
+
+def test_shard_ranges_cover_and_balance():
+    for Q, W in ((10, 1), (10, 3), (7, 8), (1_000_003, 8), (0, 4)):
+        spans = [shard.shard_range(Q, r, W) for r in range(W)]
+        assert spans[0][0] == 0 and spans[-1][1] == Q
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
