@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py - placements/sec of the per-query placement hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--queries Q]
+
+A step = one pass of the hot path (pp_place: query prep -> prefilter over every edge -> ranking ->
+baseball/Brent -> keep/refine -> weights) over one batch of Q synthetic queries on config C2 of
+BASELINE.json (16S shape: 800-taxon tree, 1500 columns, 10k reads, GTR+G4).  With N
+ranks every rank places its own Q-query shard against the replicated reference GLVs (weak scaling,
+no collective on the data path); value = all queries placed by all ranks / max-over-ranks time.
+
+  value     device-resident: query characters already in HBM, results left in HBM (pp_place_device)
+  e2e       the public C-ABI call with HOST buffers (pp_place): pinned host chars -> device, results
+            device -> host, inside the timed region
+  roofline  the dominant kernel's achieved FP64 rate against the DFMA peak measured in the same run
+            (MEASURED_PEAKS.json has no FP64 figure), plus its compulsory-HBM-traffic rate against
+            MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the CPU oracle port (oracle/) on all host cores over a bounded sample (rank 0, N=1)
+
+--impl reference times the CPU oracle port alone (the reference binary cannot be built here: no
+OCaml toolchain) on the same config, each step a bounded sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "placements/sec"
+WORKLOAD = "C2: 16S shape, 800-taxon tree (E=1597), 1500 columns, GTR+G4, synthetic reads 250-1500 columns"
+
+
+def env_int(k, d):
+    try:
+        return int(os.environ.get(k, d))
+    except ValueError:
+        return d
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh), "MEASURED_PEAKS.json"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def build_c2(Q: int, rank: int):
+    from pplacer_b200 import synth
+    from pplacer_b200.reference import build_problem
+    s = synth.simulate_reference(800, 1500, seed=2, alpha=0.5)
+    queries = synth.simulate_queries(s, Q, seed=2 + 1000 * rank)
+    return build_problem(s.tree, s.model, s.ref_align, queries)
+
+
+def oracle_rate(prob, n_threads: int, target_s: float):
+    """Times the CPU oracle port on a bounded sample; returns (placements/s, n_sample, seconds)."""
+    from oracle import binding as ob
+    from pplacer_b200 import reference
+    o = ob.Oracle(prob)
+    o.precompute()
+    pf = ob.default_prefs(prior_mean=reference.flat_exp_prior_mean(prob.tree))
+    Q = prob.query_chars.shape[0]
+    n0 = min(Q, 2 * n_threads)
+    t = time.perf_counter()
+    o.place(prob.query_chars[:n0], pf, n_threads=n_threads)
+    dt0 = max(time.perf_counter() - t, 1e-6)
+    n = int(min(Q, max(n0, (n0 / dt0) * target_s)))
+    t = time.perf_counter()
+    _, n_out, st, _ = o.place(prob.query_chars[:n], pf, n_threads=n_threads)
+    dt = time.perf_counter() - t
+    o.close()
+    return n / dt, n, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm for this path (oracle port; all host threads)."""
+    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    if rank != 0:
+        return
+    from oracle import binding as ob
+    from pplacer_b200 import reference
+    cores = os.cpu_count() or 1
+    prob = build_c2(min(args.queries, 4096), 0)
+    o = ob.Oracle(prob)
+    o.precompute()
+    pf = ob.default_prefs(prior_mean=reference.flat_exp_prior_mean(prob.tree))
+    Q = prob.query_chars.shape[0]
+    # calibrate the per-step sample to ~args.ref_step_seconds of CPU work
+    n0 = min(Q, 2 * cores)
+    t = time.perf_counter(); o.place(prob.query_chars[:n0], pf, n_threads=cores); dt0 = max(time.perf_counter() - t, 1e-6)
+    n = int(min(Q, max(n0, n0 / dt0 * args.ref_step_seconds)))
+    for _ in range(max(args.warmup - 1, 0)):
+        o.place(prob.query_chars[:n], pf, n_threads=cores)
+    t = time.perf_counter()
+    for k in range(args.steps):
+        lo = (k * n) % max(Q - n + 1, 1)
+        o.place(prob.query_chars[lo:lo + n], pf, n_threads=cores)
+    dt = time.perf_counter() - t
+    value = n * args.steps / dt
+    sample = "%d of the workload's queries per step (oracle port of the reference algorithm, %d threads over a shared query counter = pplacer -j %d)" % (n, cores, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "placements/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "queries_per_step": n, "flags": "pplacer defaults"},
+        "cpu_baseline": {"value": value, "unit": "placements/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "placements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pplacer_b200 import _lib, seqio
+    from pplacer_b200.placer import Placer
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    Q = args.queries
+    prob = build_c2(Q, rank)
+    Q = prob.query_chars.shape[0]
+    p = Placer(prob, device=local)
+    t0 = time.perf_counter(); p.precompute(); torch.cuda.synchronize(); precompute_ms = (time.perf_counter() - t0) * 1e3
+    prefs = p.prefs()
+    K = prefs.keep_at_most
+    stream = torch.cuda.Stream(device=dev)
+    p.set_stream(stream.cuda_stream)
+    fp64_peak = p.measure_fp64_peak()
+
+    # ---- device-resident arm -------------------------------------------------------------------
+    d_chars = torch.from_numpy(prob.query_chars).to(dev)
+    d_out = torch.zeros(Q * K * 56, dtype=torch.uint8, device=dev)
+    d_n = torch.zeros(Q, dtype=torch.int32, device=dev)
+    d_st = torch.zeros(Q, dtype=torch.int32, device=dev)
+
+    def step_device():
+        p.place_device(d_chars.data_ptr(), Q, d_out.data_ptr(), d_n.data_ptr(), d_st.data_ptr(), prefs)
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    barrier()
+    p.kernel_launches(reset=True); p.phase_times_ms(reset=True)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        ev1.record(stream)
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = p.kernel_launches()
+    phases = p.phase_times_ms() / args.steps       # prefilter, rank, optimise(+refine), pp
+    total_q = sum_over_ranks(float(Q)) * args.steps
+    value = total_q / (ms * 1e-3)
+    st_host = d_st.cpu().numpy()
+    n_host = d_n.cpu().numpy()
+
+    # ---- end-to-end arm: the public call with pinned HOST buffers -------------------------------
+    h_chars = torch.from_numpy(prob.query_chars).pin_memory()
+    chars_np = h_chars.numpy()
+    for _ in range(min(args.warmup, 2)):
+        p.place(chars_np, prefs)
+    barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            out, n_out, st, _ = p.place(chars_np, prefs)
+        ev1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), 0.0))
+    e2e_value = total_q / (e2e_ms * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+    assert np.array_equal(n_out, n_host) and np.array_equal(st, st_host), "device and host entry points disagree"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------
+    peaks, peaks_src = measured_peaks()
+    inf = seqio.informative(prob.query_chars)
+    sum_nq = float(inf.sum())
+    R, S, E = p.R, p.S, p.n_nodes - 1
+    share = {k: float(v) for k, v in zip(("prefilter", "rank", "optimise", "pp"), phases)}
+    pre_flops = 2.0 * R * S * E * sum_nq                 # 2RS flops per (query, edge, informative site)
+    pre_ms = share["prefilter"]
+    pre_tflops = pre_flops / (pre_ms * 1e-3) / 1e12 if pre_ms > 0 else 0.0
+    QT = 4                                               # queries sharing one pass over the supernodes (kernel tile)
+    pre_bytes = (8.0 * R * S + 4.0) * p.L * (E + 1) * ((Q + QT - 1) // QT) + Q * p.L + 8.0 * Q * (E + 1)
+    roofline = {
+        "kernel": "prefilter_direct_kernel", "bound": "fp64", "achieved": pre_tflops, "peak": fp64_peak,
+        "unit": "TFLOP/s", "frac": pre_tflops / fp64_peak if fp64_peak else None,
+        "peak_source": "DFMA micro-benchmark in this run (pp_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
+        "algorithmic_flops_per_launch": pre_flops, "ms_per_launch": pre_ms,
+        "hbm": {"achieved": pre_bytes / (pre_ms * 1e-3) / 1e9 if pre_ms > 0 else 0.0, "peak": peaks.get("hbm_gbs"),
+                "unit": "GB/s", "peak_source": peaks_src, "bytes_per_launch": pre_bytes,
+                "note": "bytes the kernel's tiling requests (supernodes re-read per 4-query tile; L2 absorbs most)"},
+        "traffic": None,
+        "share_of_step_ms": share, "step_ms": ms / args.steps,
+    }
+
+    # ---- CPU baseline on a bounded sample ------------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        rate, n_s, dt = oracle_rate(prob, cores, args.cpu_seconds)
+        cpu = {"value": rate, "unit": "placements/s", "cores": cores, "kind": "port",
+               "sample": "first %d queries of the workload, %.1f s, oracle port with %d threads" % (n_s, dt, cores)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "placements/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "queries_per_gpu_per_step": Q, "flags": "pplacer defaults (keep_at_most 7, max_strikes 6, max_pitches 40)",
+                   "sharding": "queries sharded over ranks, reference GLVs replicated, no data-path collective",
+                   "l2": "inputs larger than L2: supernodes %.0f MB + darr/parr %.0f MB per pass" % (
+                       8.0 * R * S * p.L * (E + 1) / 1e6, 16.0 * R * S * p.L * (E + 1) / 1e6),
+                   "placed_ok_frac": float((st_host == 0).mean()), "mean_kept": float(n_host.mean())},
+        "e2e": {"value": e2e_value, "unit": "placements/s", "h2d_bytes_per_step": int(Q * p.L),
+                "d2h_bytes_per_step": int(Q * K * 56 + 8 * Q), "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "precompute_ms": precompute_ms, "fp64_peak_tflops_measured": fp64_peak,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--queries", type=int, default=10_000, help="queries per GPU per step (C2: 10k)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline sample budget")
+    ap.add_argument("--ref-step-seconds", type=float, default=6.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

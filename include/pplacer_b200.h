@@ -167,6 +167,10 @@ int pp_discrete_gamma(int32_t n_cat, double alpha, double *rates_out);
 int pp_diagd(int32_t S, const double *exch, const double *pi, double *x, double *lambda, double *xit);
 int pp_emper_freq(int32_t S, const uint8_t *chars, int64_t n, double *out);
 
+/* Run this context's work on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL restores
+ * the context's own stream).  Lets the host time the path with CUDA events on the launching stream. */
+int pp_set_stream(pp_ctx *, void *cuda_stream);
+
 /* Counters for bench.py: kernels launched by this library on this context since the last reset,
  * and accumulated device time (ms, CUDA events) of the named phase kernels. */
 int64_t pp_kernel_launches(pp_ctx *, int32_t reset);

@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "pp_last_error", "pp_abi_version", "pp_default_prefs", "pp_create", "pp_destroy", "pp_precompute",
     "pp_export_glvs", "pp_get_model", "pp_place", "pp_place_device", "pp_prefilter_scores",
     "pp_three_tax_log_like", "pp_evolve", "pp_discrete_gamma", "pp_diagd", "pp_emper_freq",
-    "pp_kernel_launches", "pp_phase_times_ms", "pp_measure_fp64_peak",
+    "pp_kernel_launches", "pp_phase_times_ms", "pp_measure_fp64_peak", "pp_set_stream",
 ]
 
 
@@ -102,6 +102,7 @@ def load():
     L.pp_kernel_launches.restype = C.c_int64
     L.pp_phase_times_ms.argtypes = [C.c_void_p, c_double_p, C.c_int32]
     L.pp_measure_fp64_peak.argtypes = [C.c_void_p, c_double_p]
+    L.pp_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     _lib = L
     return L
 

@@ -70,7 +70,7 @@ constexpr int kTTThreadsAA = 256;
 
 struct pp_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
   int sm_count = 148;
   Alphabet al;
   DevModel hm;
@@ -158,7 +158,7 @@ extern "C" void pp_destroy(pp_ctx *c) {
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->ev[0]) cudaEventDestroy(c->ev[0]);
   if (c->ev[1]) cudaEventDestroy(c->ev[1]);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
 
@@ -236,7 +236,8 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
     }
   int rc;
 #define UP(dst, src, n) if ((rc = upload(&(dst), (src), (n))) != PP_OK) { pp_destroy(c); return rc; }
-  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
   CK(cudaEventCreate(&c->ev[0]));
   CK(cudaEventCreate(&c->ev[1]));
   UP(c->dm, &hm, 1);
@@ -325,6 +326,7 @@ extern "C" int pp_precompute(pp_ctx *c) {
   int rc = PP_OK;
   DISPATCH_MODEL(c, {
     const size_t sm_p = (size_t)(Rt * S_ + Rt * S_ * S_) * sizeof(double);
+    CK(cudaFuncSetAttribute(pmat_kernel<S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_p));
     pmat_kernel<S_><<<c->n_nodes, 128, sm_p, c->stream>>>(c->dm, c->d_bl, c->n_nodes, 1.0, Rt, Pfull); LAUNCH_CHECK(c);
     pmat_kernel<S_><<<c->n_nodes, 128, sm_p, c->stream>>>(c->dm, c->d_bl, c->n_nodes, 0.5, Rt, Phalf); LAUNCH_CHECK(c);
     const size_t sm_l = (size_t)Rt * p_rstride<S_, G_>() * sizeof(double);
@@ -749,6 +751,14 @@ extern "C" int pp_evolve(pp_ctx *c, const double *src_a, const int64_t *src_e, i
     for (int site = 0; site < n; ++site)
       for (int s = 0; s < c->S; ++s) dst_a[((size_t)r * n + site) * c->S + s] = h[(size_t)(r * c->S + s) * np + site];
   if (src_e && dst_e) std::memcpy(dst_e, src_e, sizeof(int64_t) * n);  // exponents are copied (gmix_model.ml:311)
+  return PP_OK;
+}
+
+extern "C" int pp_set_stream(pp_ctx *c, void *cuda_stream) {
+  if (!c) return fail(PP_EINVAL, "null ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
   return PP_OK;
 }
 

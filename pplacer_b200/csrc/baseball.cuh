@@ -195,15 +195,23 @@ __global__ void final_sort_kernel(BallState b, KeepState ks, int Q, const CandOu
                                   PlaceOut *__restrict__ res, int keep_at_most, int32_t *__restrict__ n_out,
                                   int pp_failed_status) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= Q || b.qstatus[q] != 0) { if (q < Q) n_out[q] = 0; return; }
-  const int nk = n_out[q], base = ks.keep_begin[q];
+  if (q >= Q) return;
   PlaceOut *r = res + (int64_t)q * keep_at_most;
+  PlaceOut zero;
+  zero.edge = 0; zero._pad = 0; zero.log_like = zero.pendant = zero.distal = zero.ml_ratio = zero.marginal_like = zero.post_prob = 0.0;
+  int nk = b.qstatus[q] != 0 ? 0 : n_out[q];
+  const int base = ks.keep_begin[q];
   if (calc_pp) {
     for (int i = 0; i < nk; ++i) {
       const CandOut o = pp_out[base + i];
-      if (o.status != ST_OK) { b.qstatus[q] = (o.status == ST_EXCEEDED_MAX_ITER) ? pp_failed_status : o.status; n_out[q] = 0; return; }
+      if (o.status != ST_OK) { b.qstatus[q] = (o.status == ST_EXCEEDED_MAX_ITER) ? pp_failed_status : o.status; nk = 0; break; }
       r[i].marginal_like = o.marg;
     }
+  }
+  // unused record slots are zero-filled so the output bytes are a pure function of the inputs
+  for (int i = nk; i < keep_at_most; ++i) r[i] = zero;
+  n_out[q] = nk;
+  if (calc_pp) {
     for (int i = 0; i < nk; ++i) {
       double tot = 0.0;
       for (int j = 0; j < nk; ++j) tot += exp(r[j].marginal_like - r[i].marginal_like);

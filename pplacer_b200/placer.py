@@ -174,6 +174,10 @@ class Placer:
                                                C.c_void_p(d_out_ptr), C.c_void_p(d_n_out_ptr),
                                                C.c_void_p(d_status_ptr)))
 
+    def set_stream(self, cuda_stream: Optional[int]):
+        """Run on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        _lib.check(_lib.load().pp_set_stream(self.ctx, C.c_void_p(cuda_stream) if cuda_stream else None))
+
     # ---- instrumentation ------------------------------------------------------------------
     def kernel_launches(self, reset: bool = False) -> int:
         return int(_lib.load().pp_kernel_launches(self.ctx, 1 if reset else 0))
