@@ -171,6 +171,13 @@ int pp_emper_freq(int32_t S, const uint8_t *chars, int64_t n, double *out);
  * the context's own stream).  Lets the host time the path with CUDA events on the launching stream. */
 int pp_set_stream(pp_ctx *, void *cuda_stream);
 
+/* Which prefilter kernel pp_place uses: 0 = default (the four-base table form for the DNA Gamma-4
+ * model, the direct FMA form otherwise), 1 = direct FMA form (K = rates*states DFMAs per query x edge
+ * x site: ten_masked_logdot_c / mat_masked_logdot_c as written, linear_c.c:465,251), 2 = table form.
+ * pp_prefilter_kernel_used reports what the last prefilter launch ran (1 or 2). */
+int pp_set_prefilter_kernel(pp_ctx *, int32_t kernel);
+int pp_prefilter_kernel_used(pp_ctx *);
+
 /* Counters for bench.py: kernels launched by this library on this context since the last reset,
  * and accumulated device time (ms, CUDA events) of the named phase kernels. */
 int64_t pp_kernel_launches(pp_ctx *, int32_t reset);

@@ -17,6 +17,7 @@
 #include "device_common.cuh"
 #include "model_host.hpp"
 #include "precompute.cuh"
+#include "prefilter.cuh"
 #include "query.cuh"
 #include "threetax.cuh"
 
@@ -84,6 +85,18 @@ struct pp_ctx {
   uint8_t *d_code_of_char = nullptr, *d_ref_codes = nullptr;
   int32_t *d_site_cat = nullptr, *d_child_ptr = nullptr, *d_child_idx = nullptr, *d_parent = nullptr, *d_leaf_row = nullptr;
   bool precomputed = false;
+  // supernodes in prefilter layout (edge fastest), see prefilter.cuh
+  double *snT_a = nullptr;
+  int32_t *snT_e = nullptr;
+  int64_t Np = 0;
+  double tq_pend = -1.0;   // pendant length the evolved-query table Tq was built for
+  double mt_pend = -1.0;   // ... and the four-base table MT
+  TqPrimary tqp;
+  DevBuf<uint8_t> qc;
+  DevBuf<double> partial, MT;
+  DevBuf<int32_t> bad_edge;
+  int prefilter_choice = 0;       // pp_set_prefilter_kernel: 0 default, 1 direct, 2 table
+  int prefilter_kernel_used = 0;  // 1 direct, 2 table (last run_prefilter)
   // workspace
   DevBuf<uint8_t> chars, codes, sort_tmp;
   DevBuf<int32_t> qsite, nq, prep_status, rank_in, rank_loc, seg_off, i32pool, n_out;
@@ -148,7 +161,8 @@ extern "C" void pp_destroy(pp_ctx *c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (int w = 0; w < 3; ++w) { if (c->g.a[w]) cudaFree(c->g.a[w]); if (c->g.e[w]) cudaFree(c->g.e[w]); }
-  void *ptrs[] = {c->dm, c->d_bl, c->d_code_of_char, c->d_ref_codes, c->d_site_cat, c->d_child_ptr, c->d_child_idx, c->d_parent, c->d_leaf_row};
+  c->qc.release(); c->partial.release(); c->MT.release(); c->bad_edge.release();
+  void *ptrs[] = {c->snT_a, c->snT_e, c->dm, c->d_bl, c->d_code_of_char, c->d_ref_codes, c->d_site_cat, c->d_child_ptr, c->d_child_idx, c->d_parent, c->d_leaf_row};
   for (void *p : ptrs) if (p) cudaFree(p);
   c->chars.release(); c->codes.release(); c->sort_tmp.release(); c->qsite.release(); c->nq.release();
   c->prep_status.release(); c->rank_in.release(); c->rank_loc.release(); c->seg_off.release(); c->i32pool.release();
@@ -258,6 +272,12 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
     cudaMemsetAsync(c->g.a[w], 0, sizeof(double) * (size_t)c->g.a_stride * c->n_nodes, c->stream);
     cudaMemsetAsync(c->g.e[w], 0, sizeof(int32_t) * (size_t)c->Lp * c->n_nodes, c->stream);
   }
+  c->Np = (c->n_nodes + 63) / 64 * 64;
+  {
+    cudaError_t e1 = cudaMalloc(&c->snT_a, sizeof(double) * (size_t)c->L * c->K * c->Np);
+    cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(&c->snT_e, sizeof(int32_t) * (size_t)c->L * c->Np) : e1;
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaGetLastError(); pp_destroy(c); return fail(PP_ENOMEM, "pp_create: not enough device memory for the prefilter copy of the supernodes"); }
+  }
   c->t.child_ptr = c->d_child_ptr; c->t.child_idx = c->d_child_idx; c->t.parent = c->d_parent; c->t.leaf_row = c->d_leaf_row;
   c->t.ref_codes = c->d_ref_codes; c->t.site_cat = c->d_site_cat;
   CK(cudaMallocHost(&c->h_counters, 8 * sizeof(int)));
@@ -355,6 +375,14 @@ extern "C" int pp_precompute(pp_ctx *c) {
       supernode_kernel<S_, G_><<<grid, kPreThreads, sm_l, c->stream>>>(c->dm, c->g, c->t, Phalf, Rt); LAUNCH_CHECK(c);
     }
   });
+  if (rc == PP_OK) {
+    // supernodes -> prefilter layout snT[site][k][edge] (prefilter.cuh)
+    dim3 grid((c->L + 31) / 32, (unsigned)(c->Np / 32), c->K);
+    transpose_to_edge_major_kernel<double><<<grid, 256, 0, c->stream>>>(c->g.a[2], c->snT_a, c->n_nodes, c->K, c->L, c->Lp, c->Np, 1.0); LAUNCH_CHECK(c);
+    dim3 grid_e((c->L + 31) / 32, (unsigned)(c->Np / 32), 1);
+    transpose_to_edge_major_kernel<int32_t><<<grid_e, 256, 0, c->stream>>>(c->g.e[2], c->snT_e, c->n_nodes, 1, c->L, c->Lp, c->Np, 0); LAUNCH_CHECK(c);
+    c->tq_pend = c->mt_pend = -1.0;
+  }
   cudaError_t e = cudaStreamSynchronize(c->stream);
   cudaFree(Pfull); cudaFree(Phalf); cudaFree(d_levels);
   if (e != cudaSuccess) return fail(PP_ECUDA, std::string("pp_precompute: ") + cudaGetErrorString(e));
@@ -404,6 +432,7 @@ static int prep_queries(pp_ctx *c, int64_t Q, const uint8_t *d_chars) {
 
 static int build_query_table(pp_ctx *c, double t) {
   int rc;
+  if (c->tq_pend == t) return PP_OK;  // the table only depends on the model and the pendant length
   const size_t n = (size_t)c->R * c->al.n_codes * c->S;
   if ((rc = c->Tq.ensure(n))) return rc;
   DISPATCH_MODEL(c, {
@@ -413,28 +442,124 @@ static int build_query_table(pp_ctx *c, double t) {
     (void)G_;
     LAUNCH_CHECK(c);
   });
+  std::memset(&c->tqp, 0, sizeof c->tqp);
+  if (c->S == 4 && !c->gcat && c->K <= 16) {
+    // the four base columns go to the kernels by value (parameter constant bank)
+    std::vector<double> h(n);
+    CK(cudaMemcpyAsync(h.data(), c->Tq.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int j = 0; j < 4; ++j)
+      for (int k = 0; k < c->K; ++k) c->tqp.v[j][k] = h[(size_t)(1 << j) * c->K + k];
+  }
+  c->tq_pend = t;
   return PP_OK;
 }
 
-template <int S, bool G, int TE, int QT, int TH>
-static int launch_prefilter_direct(pp_ctx *c, int64_t Q) {
-  const size_t sm = ((size_t)c->R * c->al.n_codes * S + (size_t)(TH / 32) * TE * QT) * sizeof(double);
-  auto kern = prefilter_direct_kernel<S, G, TE, QT, TH>;
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  dim3 grid((c->n_nodes + TE - 1) / TE, (unsigned)((Q + QT - 1) / QT));
-  kern<<<grid, TH, sm, c->stream>>>(c->dm, c->g, c->Tq.p, c->codes.p, c->nq.p, c->d_site_cat, (int)Q, c->root_id, c->scores.p);
-  LAUNCH_CHECK(c);
-  return PP_OK;
+// ---- prefilter launch plumbing (prefilter.cuh) ----
+struct PreGeom { int nqt, gx, gy, zs, sites_per_z; };
+
+static PreGeom prefilter_geometry(const pp_ctx *c, int64_t Q, int QT, int TE, int W, int blocks_per_sm) {
+  PreGeom g;
+  g.nqt = (int)((Q + QT - 1) / QT);
+  g.gx = (g.nqt + W - 1) / W;
+  g.gy = (int)(c->Np / (32 * TE));
+  // few queries on a long alignment: split the site range so every SM holds its share of blocks
+  const int64_t want = (int64_t)c->sm_count * blocks_per_sm * 2;
+  int zs = (int)std::min<int64_t>((want + (int64_t)g.gx * g.gy - 1) / ((int64_t)g.gx * g.gy), std::max(1, c->L / 256));
+  zs = std::max(1, std::min(zs, 64));
+  g.sites_per_z = (c->L + zs - 1) / zs;
+  g.zs = (c->L + g.sites_per_z - 1) / g.sites_per_z;
+  return g;
 }
 
-static int run_prefilter(pp_ctx *c, int64_t Q, int kernel_choice) {
+template <int QT>
+static int pack_codes(pp_ctx *c, int64_t Q, int nqt) {
   int rc;
-  (void)kernel_choice;
+  if ((rc = c->qc.ensure((size_t)nqt * c->L * QT + 16))) return rc;
+  dim3 grid((c->L + 255) / 256, nqt);
+  pack_codes_kernel<QT><<<grid, 256, 0, c->stream>>>(c->codes.p, c->qc.p, (int)Q, c->L, c->Lp); LAUNCH_CHECK(c);
+  return PP_OK;
+}
+
+static int prefilter_args(pp_ctx *c, int64_t Q, const PreGeom &g, PreArgs *A) {
+  int rc;
+  A->sn.a = c->snT_a; A->sn.e = c->snT_e; A->sn.Np = c->Np; A->sn.L = c->L; A->sn.K = c->K; A->sn.n_nodes = c->n_nodes;
+  A->qc = c->qc.p; A->Tq = c->Tq.p; A->site_cat = c->d_site_cat; A->nq = c->nq.p; A->bad_edge = nullptr;
+  A->Q = (int)Q; A->nqt = g.nqt; A->root_id = c->root_id; A->R = c->R; A->nc = c->al.n_codes; A->zs = g.zs; A->sites_per_z = g.sites_per_z;
+  if (g.zs > 1) {
+    if ((rc = c->partial.ensure((size_t)g.zs * Q * c->n_nodes))) return rc;
+    A->out = c->partial.p;
+  } else
+    A->out = c->scores.p;
+  return PP_OK;
+}
+
+static int prefilter_finish(pp_ctx *c, int64_t Q, const PreGeom &g) {
+  if (g.zs > 1) {
+    const int64_t total = Q * (int64_t)c->n_nodes;
+    combine_partials_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(c->partial.p, c->scores.p, g.zs, c->n_nodes, c->root_id, total); LAUNCH_CHECK(c);
+  }
+  return PP_OK;
+}
+
+template <int S, bool G, int NRC, int TE, int QT, int W, int TQSRC>
+static int launch_prefilter_direct(pp_ctx *c, int64_t Q, int blocks_per_sm) {
+  int rc;
+  const PreGeom g = prefilter_geometry(c, Q, QT, TE, W, blocks_per_sm);
+  PreArgs A;
+  if ((rc = pack_codes<QT>(c, Q, g.nqt)) || (rc = prefilter_args(c, Q, g, &A))) return rc;
+  const size_t tq_bytes = (size_t)c->al.n_codes * c->K * sizeof(double);
+  const size_t sm = TQSRC == TQ_SMEM ? tq_bytes : 0;
+  auto kern = prefilter_direct_kernel<S, G, NRC, TE, QT, W, TQSRC>;
+  if (TQSRC == TQ_CONST)  // stream-ordered refresh of the constant-bank copy of the evolved-query table
+    CK(cudaMemcpyToSymbolAsync(c_tq, c->Tq.p, tq_bytes, 0, cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  kern<<<dim3(g.gx, g.gy, g.zs), W * 32, sm, c->stream>>>(A); LAUNCH_CHECK(c);
+  c->prefilter_kernel_used = 1;
+  return prefilter_finish(c, Q, g);
+}
+
+template <int TE, int QT, int W>
+static int launch_prefilter_table(pp_ctx *c, int64_t Q, double pend, int blocks_per_sm) {
+  int rc;
+  if (c->mt_pend != pend) {  // four-base table: once per (reference, pendant length)
+    if ((rc = c->MT.ensure((size_t)c->L * 4 * c->Np)) || (rc = c->bad_edge.ensure(c->Np))) return rc;
+    CK(cudaMemsetAsync(c->bad_edge.p, 0, sizeof(int32_t) * c->Np, c->stream));
+    SnT sn; sn.a = c->snT_a; sn.e = c->snT_e; sn.Np = c->Np; sn.L = c->L; sn.K = c->K; sn.n_nodes = c->n_nodes;
+    mtable_kernel<16><<<dim3((unsigned)((c->Np + 127) / 128), c->L), 128, 0, c->stream>>>(sn, c->tqp, c->MT.p, c->bad_edge.p); LAUNCH_CHECK(c);
+    c->mt_pend = pend;
+  }
+  const PreGeom g = prefilter_geometry(c, Q, QT, TE, W, blocks_per_sm);
+  PreArgs A;
+  if ((rc = pack_codes<QT>(c, Q, g.nqt)) || (rc = prefilter_args(c, Q, g, &A))) return rc;
+  A.bad_edge = c->bad_edge.p;
+  prefilter_table_kernel<TE, QT, W><<<dim3(g.gx, g.gy, g.zs), W * 32, 0, c->stream>>>(A, c->MT.p); LAUNCH_CHECK(c);
+  c->prefilter_kernel_used = 2;
+  return prefilter_finish(c, Q, g);
+}
+
+// kernel_choice: 0 default (table form for DNA Gamma-4, direct otherwise), 1 direct FMA form, 2 table form
+static int run_prefilter(pp_ctx *c, int64_t Q, int kernel_choice, double pend) {
+  int rc;
   if ((rc = c->scores.ensure((size_t)Q * c->n_nodes))) return rc;
-  if (c->S == 4 && !c->gcat) return launch_prefilter_direct<4, false, 2, 4, 128>(c, Q);
-  if (c->S == 4 && c->gcat) return launch_prefilter_direct<4, true, 2, 4, 128>(c, Q);
-  if (c->S == 20 && !c->gcat) return launch_prefilter_direct<20, false, 1, 4, 128>(c, Q);
-  return launch_prefilter_direct<20, true, 1, 4, 128>(c, Q);
+  const bool few = Q <= 64;  // one warp per block when there are too few query tiles to fill a block
+  const bool const_ok = (size_t)c->al.n_codes * c->K <= (size_t)kConstTqDoubles;
+  if (c->S == 4 && !c->gcat && c->K == 16) {
+    if (kernel_choice == 1) return few ? launch_prefilter_direct<4, false, 4, 2, 8, 1, TQ_CONST>(c, Q, 8) : launch_prefilter_direct<4, false, 4, 2, 16, 8, TQ_CONST>(c, Q, 1);
+    if (kernel_choice == 3) return launch_prefilter_direct<4, false, 4, 2, 16, 8, TQ_SMEM>(c, Q, 1);
+    return few ? launch_prefilter_table<2, 8, 1>(c, Q, pend, 12) : launch_prefilter_table<2, 16, 4>(c, Q, pend, 3);
+  }
+  if (kernel_choice == 2) return fail(PP_EINVAL, "prefilter: the table form exists for the DNA Gamma-4 model only");
+  if (c->gcat) {
+    if (c->S == 4) return few ? launch_prefilter_direct<4, true, 1, 2, 8, 1, TQ_GLOBAL>(c, Q, 12) : launch_prefilter_direct<4, true, 1, 2, 16, 8, TQ_GLOBAL>(c, Q, 2);
+    return few ? launch_prefilter_direct<20, true, 1, 2, 4, 1, TQ_GLOBAL>(c, Q, 12) : launch_prefilter_direct<20, true, 1, 2, 8, 4, TQ_GLOBAL>(c, Q, 3);
+  }
+  if (c->S == 4) {
+    if (!const_ok) return launch_prefilter_direct<4, false, 0, 2, 8, 1, TQ_SMEM>(c, Q, 8);
+    return few ? launch_prefilter_direct<4, false, 0, 2, 8, 1, TQ_CONST>(c, Q, 8) : launch_prefilter_direct<4, false, 0, 2, 8, 8, TQ_CONST>(c, Q, 1);
+  }
+  if (!const_ok) return launch_prefilter_direct<20, false, 0, 2, 4, 1, TQ_SMEM>(c, Q, 8);
+  return few ? launch_prefilter_direct<20, false, 0, 2, 4, 1, TQ_CONST>(c, Q, 8) : launch_prefilter_direct<20, false, 0, 2, 8, 4, TQ_CONST>(c, Q, 2);
 }
 
 extern "C" int pp_prefilter_scores(pp_ctx *c, double start_pend, int64_t Q, const uint8_t *query_chars, double *scores,
@@ -445,7 +570,7 @@ extern "C" int pp_prefilter_scores(pp_ctx *c, double start_pend, int64_t Q, cons
   int rc;
   if ((rc = c->chars.ensure((size_t)Q * c->L))) return rc;
   CK(cudaMemcpyAsync(c->chars.p, query_chars, (size_t)Q * c->L, cudaMemcpyHostToDevice, c->stream));
-  if ((rc = prep_queries(c, Q, c->chars.p)) || (rc = build_query_table(c, start_pend)) || (rc = run_prefilter(c, Q, kernel))) return rc;
+  if ((rc = prep_queries(c, Q, c->chars.p)) || (rc = build_query_table(c, start_pend)) || (rc = run_prefilter(c, Q, kernel, start_pend))) return rc;
   CK(cudaMemcpyAsync(scores, c->scores.p, sizeof(double) * (size_t)Q * c->n_nodes, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return PP_OK;
@@ -525,7 +650,7 @@ static int place_batch(pp_ctx *c, const pp_prefs *pf, int64_t Q, const uint8_t *
   // ---- stage 1: prefilter + ranking (core.ml:187-197) ----
   {
     PhaseTimer t(c, 0);
-    if ((rc = run_prefilter(c, Q, 0))) return rc;
+    if ((rc = run_prefilter(c, Q, c->prefilter_choice, pf->start_pend))) return rc;
     t.stop();
   }
   const int64_t total = Q * (int64_t)n_nodes;
@@ -761,6 +886,14 @@ extern "C" int pp_set_stream(pp_ctx *c, void *cuda_stream) {
   c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
   return PP_OK;
 }
+
+extern "C" int pp_set_prefilter_kernel(pp_ctx *c, int32_t kernel) {
+  if (!c || kernel < 0 || kernel > 3) return fail(PP_EINVAL, "pp_set_prefilter_kernel: kernel must be 0, 1, 2 or 3");
+  if (kernel == 2 && !(c->S == 4 && !c->gcat && c->K == 16)) return fail(PP_EINVAL, "pp_set_prefilter_kernel: the table form exists for the DNA Gamma-4 model only");
+  c->prefilter_choice = kernel;
+  return PP_OK;
+}
+extern "C" int pp_prefilter_kernel_used(pp_ctx *c) { return c ? c->prefilter_kernel_used : -1; }
 
 extern "C" int64_t pp_kernel_launches(pp_ctx *c, int32_t reset) {
   if (!c) return -1;

@@ -178,6 +178,13 @@ class Placer:
         """Run on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
         _lib.check(_lib.load().pp_set_stream(self.ctx, C.c_void_p(cuda_stream) if cuda_stream else None))
 
+    def set_prefilter_kernel(self, kernel: int):
+        """0 default, 1 direct FMA form, 2 four-base table form (DNA Gamma-4 only)."""
+        _lib.check(_lib.load().pp_set_prefilter_kernel(self.ctx, int(kernel)))
+
+    def prefilter_kernel_used(self) -> int:
+        return int(_lib.load().pp_prefilter_kernel_used(self.ctx))
+
     # ---- instrumentation ------------------------------------------------------------------
     def kernel_launches(self, reset: bool = False) -> int:
         return int(_lib.load().pp_kernel_launches(self.ctx, 1 if reset else 0))

@@ -110,6 +110,39 @@ def test_prefilter_scores_and_ranking_match_oracle(oracle_binding, name):
             assert a == b or abs(w[q][a] - w[q][b]) <= 1e-9 * abs(w[q][a]), (q, a, b)
 
 
+@pytest.mark.parametrize("name,kernel", [("c1_gtr", 1), ("c1_gtr", 2), ("c1_gtr", 3), ("synth", 1), ("synth", 2), ("synth", 3)])
+def test_prefilter_kernel_variants_match_oracle(oracle_binding, name, kernel):
+    """The direct FMA form (1: evolved-query table in the constant bank, 3: in shared memory) and the
+    four-base table form (2) of the DNA Gamma-4 prefilter all reproduce ten_masked_logdot_c."""
+    prob, o, p = setup(name, oracle_binding)
+    _, _, st, info = o.place(prob.query_chars, oracle_prefs(oracle_binding, prob), n_threads=4, debug=True)
+    want = info["scores"]
+    got = p.prefilter_scores(prob.query_chars, kernel=kernel)
+    assert p.prefilter_kernel_used() == (2 if kernel == 2 else 1)
+    root = prob.tree.root
+    keep = [i for i in range(prob.tree.n_nodes) if i != root]
+    g, w = got[:, keep], want[:, keep]
+    assert np.isnan(got[:, root]).all()
+    assert np.all(np.abs(g - w) <= 1e-10 * np.abs(w)), np.abs((g - w) / w).max()
+
+
+def test_prefilter_many_queries_matches_few_query_kernels(oracle_binding):
+    """Q > 64 takes the multi-warp tiles (W = 4/8, QT = 16), Q <= 64 the one-warp blocks with the site
+    range split over blockIdx.z: same scores for the same queries either way, for every kernel form."""
+    prob, o, p = setup("synth", oracle_binding)
+    q = prob.query_chars
+    big = np.concatenate([q, q, q[:17]], axis=0)
+    assert big.shape[0] > 64
+    for kernel in (0, 1, 2, 3):
+        a = p.prefilter_scores(q, kernel=kernel)
+        b = p.prefilter_scores(big, kernel=kernel)
+        for lo in (0, q.shape[0]):
+            d = np.abs(b[lo:lo + q.shape[0]] - a)
+            assert np.all((d <= 1e-12 * np.abs(a)) | np.isnan(a)), (kernel, np.nanmax(d))
+        d = np.abs(b[2 * q.shape[0]:] - a[:17])
+        assert np.all((d <= 1e-12 * np.abs(a[:17])) | np.isnan(a[:17]))
+
+
 @pytest.mark.parametrize("name", ["c1_gtr", "wag", "gcat_dna", "gcat_aa"])
 def test_three_tax_log_like_matches_oracle(oracle_binding, name):
     prob, o, p = setup(name, oracle_binding)
