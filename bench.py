@@ -212,6 +212,7 @@ def run_ours(args):
     K = prefs.keep_at_most
     stream = torch.cuda.Stream(device=dev)
     p.set_stream(stream.cuda_stream)
+    p.set_prefilter_kernel({"default": 0, "direct": 1, "table": 2}[args.prefilter])
     fp64_peak = p.measure_fp64_peak()
 
     # ---- device-resident arm -------------------------------------------------------------------
@@ -278,16 +279,18 @@ def run_ours(args):
     pre_flops = 2.0 * R * S * E * sum_nq                 # 2RS flops per (query, edge, informative site)
     pre_ms = share["prefilter"]
     pre_tflops = pre_flops / (pre_ms * 1e-3) / 1e12 if pre_ms > 0 else 0.0
-    QT = 4                                               # queries sharing one pass over the supernodes (kernel tile)
-    pre_bytes = (8.0 * R * S + 4.0) * p.L * (E + 1) * ((Q + QT - 1) // QT) + Q * p.L + 8.0 * Q * (E + 1)
+    used = p.prefilter_kernel_used()
+    kname = {1: "prefilter_direct_kernel", 2: "prefilter_table_kernel"}.get(used, "?")
+    # compulsory HBM bytes: one pass over the prefilter copy of the supernodes + query codes + scores
+    pre_bytes = (8.0 * (R * S if used == 1 else 4) + 4.0) * p.L * (E + 1) + Q * p.L + 8.0 * Q * (E + 1)
     roofline = {
-        "kernel": "prefilter_direct_kernel", "bound": "fp64", "achieved": pre_tflops, "peak": fp64_peak,
+        "kernel": kname, "bound": "fp64", "achieved": pre_tflops, "peak": fp64_peak,
         "unit": "TFLOP/s", "frac": pre_tflops / fp64_peak if fp64_peak else None,
         "peak_source": "DFMA micro-benchmark in this run (pp_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
         "algorithmic_flops_per_launch": pre_flops, "ms_per_launch": pre_ms,
         "hbm": {"achieved": pre_bytes / (pre_ms * 1e-3) / 1e9 if pre_ms > 0 else 0.0, "peak": peaks.get("hbm_gbs"),
                 "unit": "GB/s", "peak_source": peaks_src, "bytes_per_launch": pre_bytes,
-                "note": "bytes the kernel's tiling requests (supernodes re-read per 4-query tile; L2 absorbs most)"},
+                "note": "compulsory bytes: one pass over the supernodes (or their four-base table) + query codes + scores"},
         "traffic": None,
         "share_of_step_ms": share, "step_ms": ms / args.steps,
     }
@@ -329,6 +332,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline sample budget")
     ap.add_argument("--ref-step-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prefilter", default="default", choices=["default", "direct", "table"],
+                    help="prefilter kernel: library default, the FMA form, or the four-base table form")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
