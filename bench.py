@@ -213,6 +213,7 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     p.set_stream(stream.cuda_stream)
     p.set_prefilter_kernel({"default": 0, "direct": 1, "table": 2}[args.prefilter])
+    p.set_three_tax_engine({"default": 0, "block": 1, "warp": 2}[args.tt_engine], args.tt_blocks_per_sm)
     fp64_peak = p.measure_fp64_peak()
 
     # ---- device-resident arm -------------------------------------------------------------------
@@ -334,6 +335,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prefilter", default="default", choices=["default", "direct", "table"],
                     help="prefilter kernel: library default, the FMA form, or the four-base table form")
+    ap.add_argument("--tt-engine", default="default", choices=["default", "block", "warp"],
+                    help="second-stage engine: library default, block-per-candidate, warp-per-candidate")
+    ap.add_argument("--tt-blocks-per-sm", type=int, default=0, help="cap on resident blocks of the warp engine (0 = max)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

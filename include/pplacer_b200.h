@@ -178,6 +178,13 @@ int pp_set_stream(pp_ctx *, void *cuda_stream);
 int pp_set_prefilter_kernel(pp_ctx *, int32_t kernel);
 int pp_prefilter_kernel_used(pp_ctx *);
 
+/* Which engine runs the second stage (Three_tax.optimize / calc_marg_prob, three_tax.ml:70-83,169-215):
+ * 0 = default (warp-per-candidate for the DNA Gamma-4 model, block-per-candidate otherwise),
+ * 1 = block-per-candidate, 2 = warp-per-candidate.  blocks_per_sm > 0 caps the resident thread blocks
+ * of the warp engine (8 candidates each); 0 = as many as fit.  pp_three_tax_engine_used: 1 or 2. */
+int pp_set_three_tax_engine(pp_ctx *, int32_t engine, int32_t blocks_per_sm);
+int pp_three_tax_engine_used(pp_ctx *);
+
 /* Counters for bench.py: kernels launched by this library on this context since the last reset,
  * and accumulated device time (ms, CUDA events) of the named phase kernels. */
 int64_t pp_kernel_launches(pp_ctx *, int32_t reset);

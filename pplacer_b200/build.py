@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpplacer_b200.so")
 SOURCES = ["api.cu", "model_host.cpp"]
-HEADERS = ["baseball.cuh", "device_common.cuh", "model_host.hpp", "precompute.cuh", "prefilter.cuh", "query.cuh", "threetax.cuh",
+HEADERS = ["baseball.cuh", "device_common.cuh", "model_host.hpp", "precompute.cuh", "prefilter.cuh", "query.cuh", "threetax.cuh", "threetax_warp.cuh",
            "qng_tables.h", os.path.join("..", "..", "include", "pplacer_b200.h")]
 
 

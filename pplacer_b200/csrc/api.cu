@@ -11,6 +11,7 @@
 #include <vector>
 
 #include <cub/device/device_segmented_sort.cuh>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "../../include/pplacer_b200.h"
 #include "baseball.cuh"
@@ -20,6 +21,7 @@
 #include "prefilter.cuh"
 #include "query.cuh"
 #include "threetax.cuh"
+#include "threetax_warp.cuh"
 
 using namespace ppb;
 
@@ -112,8 +114,17 @@ struct pp_ctx {
   cudaEvent_t ev[2] = {nullptr, nullptr};
   int tt_blocks = 0;
   size_t tt_smem = 0;
+  // warp-per-candidate engine (threetax_warp.cuh): DNA Gamma-4 only
+  int tt_engine = 0;          // pp_set_three_tax_engine: 0 default, 1 block-per-candidate, 2 warp-per-candidate
+  int ttw_blocks_per_sm = 0;  // 0 = occupancy maximum
+  int ttw_max_blocks = 0;
+  DevBuf<int32_t> ord_keys, ord_vals, ord_keys2, ord_vals2;
+  DevBuf<uint8_t> ord_tmp;
 };
 
+constexpr int kTTWarpsPerBlock = 8;
+constexpr int kTTWarpMinBlocks = 2;
+static bool ttw_supported(const pp_ctx *c) { return c->S == 4 && !c->gcat && c->R == 4; }
 static int tt_threads(const pp_ctx *c) { return c->S == 4 ? kTTThreadsDNA : kTTThreadsAA; }
 
 template <int S, bool G>
@@ -167,6 +178,7 @@ extern "C" void pp_destroy(pp_ctx *c) {
   c->chars.release(); c->codes.release(); c->sort_tmp.release(); c->qsite.release(); c->nq.release();
   c->prep_status.release(); c->rank_in.release(); c->rank_loc.release(); c->seg_off.release(); c->i32pool.release();
   c->n_out.release(); c->Tq.release(); c->scores.release(); c->keys_in.release(); c->keys_out.release();
+  c->ord_keys.release(); c->ord_vals.release(); c->ord_keys2.release(); c->ord_vals2.release(); c->ord_tmp.release();
   c->wbuf.release(); c->f64pool.release(); c->cand.release(); c->cand_out.release(); c->pp_out.release();
   c->place_out.release(); c->n_calls.release(); c->counters.release();
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -301,7 +313,18 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
     if (per_sm < 1) per_sm = 1;
     c->tt_blocks = per_sm * c->sm_count;
   });
-  if ((rc = c->wbuf.ensure((size_t)c->tt_blocks * c->K * c->Lp)) != PP_OK) { pp_destroy(c); return rc; }
+  size_t w_slots = (size_t)c->tt_blocks;
+  if (ttw_supported(c)) {
+    auto kern = tt_warp_kernel<4, kTTWarpsPerBlock, kTTWarpMinBlocks>;
+    const size_t smw = TTWarp<4>::smem_bytes(kTTWarpsPerBlock);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTTWarpsPerBlock * 32, smw));
+    if (per_sm < 1) per_sm = 1;
+    c->ttw_max_blocks = per_sm * c->sm_count;
+    w_slots = std::max(w_slots, (size_t)c->ttw_max_blocks * kTTWarpsPerBlock);
+  }
+  if ((rc = c->wbuf.ensure(w_slots * c->K * c->Lp)) != PP_OK) { pp_destroy(c); return rc; }
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaGetLastError());
   *out = c;
@@ -579,9 +602,36 @@ extern "C" int pp_prefilter_scores(pp_ctx *c, double start_pend, int64_t Q, cons
 // ---------------------------------------------------------------------------------------------
 // three-taxon launches
 // ---------------------------------------------------------------------------------------------
+static int launch_three_tax_warp(pp_ctx *c, const CandIn *in, CandOut *out, int n, const TTParams &prm) {
+  int rc;
+  // queue order: candidates sorted by edge so that concurrently running warps share darr/parr planes in L2
+  const int32_t *order = nullptr;
+  if (n > 1) {
+    if ((rc = c->ord_keys.ensure(n)) || (rc = c->ord_vals.ensure(n)) || (rc = c->ord_keys2.ensure(n)) || (rc = c->ord_vals2.ensure(n))) return rc;
+    cand_keys_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(in, n, c->ord_keys.p, c->ord_vals.p); LAUNCH_CHECK(c);
+    int end_bit = 1;
+    while ((1 << end_bit) < c->n_nodes && end_bit < 31) ++end_bit;
+    size_t tmp = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->ord_keys.p, c->ord_keys2.p, c->ord_vals.p, c->ord_vals2.p, n, 0, end_bit, c->stream));
+    if ((rc = c->ord_tmp.ensure(tmp))) return rc;
+    CK(cub::DeviceRadixSort::SortPairs(c->ord_tmp.p, tmp, c->ord_keys.p, c->ord_keys2.p, c->ord_vals.p, c->ord_vals2.p, n, 0, end_bit, c->stream));
+    c->launches += 1;
+    order = c->ord_vals2.p;
+  }
+  int blocks = c->ttw_max_blocks;
+  if (c->ttw_blocks_per_sm > 0) blocks = std::min(blocks, c->ttw_blocks_per_sm * c->sm_count);
+  blocks = std::min(blocks, (n + kTTWarpsPerBlock - 1) / kTTWarpsPerBlock);
+  tt_warp_kernel<4, kTTWarpsPerBlock, kTTWarpMinBlocks><<<blocks, kTTWarpsPerBlock * 32, TTWarp<4>::smem_bytes(kTTWarpsPerBlock), c->stream>>>(
+      c->dm, c->g, c->d_bl, c->codes.p, c->qsite.p, c->nq.p, in, order, out, n, prm, c->wbuf.p, c->counters.p);
+  LAUNCH_CHECK(c);
+  return PP_OK;
+}
+
 static int launch_three_tax(pp_ctx *c, const CandIn *in, CandOut *out, int n, const TTParams &prm) {
   if (n <= 0) return PP_OK;
   CK(cudaMemsetAsync(c->counters.p, 0, sizeof(int), c->stream));
+  if (ttw_supported(c) && c->tt_engine != 1) return launch_three_tax_warp(c, in, out, n, prm);
+  if (c->tt_engine == 2) return fail(PP_EINVAL, "three-taxon warp engine supports the four-state Gamma-4 mixture only");
   const int blocks = std::min(c->tt_blocks, n);
   DISPATCH_MODEL(c, {
     constexpr int TH = (S_ == 4) ? kTTThreadsDNA : kTTThreadsAA;
@@ -894,6 +944,15 @@ extern "C" int pp_set_prefilter_kernel(pp_ctx *c, int32_t kernel) {
   return PP_OK;
 }
 extern "C" int pp_prefilter_kernel_used(pp_ctx *c) { return c ? c->prefilter_kernel_used : -1; }
+
+extern "C" int pp_set_three_tax_engine(pp_ctx *c, int32_t engine, int32_t blocks_per_sm) {
+  if (!c || engine < 0 || engine > 2 || blocks_per_sm < 0) return fail(PP_EINVAL, "pp_set_three_tax_engine: engine must be 0, 1 or 2");
+  if (engine == 2 && !ttw_supported(c)) return fail(PP_EINVAL, "pp_set_three_tax_engine: the warp engine exists for the DNA Gamma-4 model only");
+  c->tt_engine = engine;
+  c->ttw_blocks_per_sm = blocks_per_sm;
+  return PP_OK;
+}
+extern "C" int pp_three_tax_engine_used(pp_ctx *c) { return !c ? -1 : (ttw_supported(c) && c->tt_engine != 1) ? 2 : 1; }
 
 extern "C" int64_t pp_kernel_launches(pp_ctx *c, int32_t reset) {
   if (!c) return -1;

@@ -63,8 +63,314 @@ __constant__ double c_qng_x1[5], c_qng_w10[5], c_qng_x2[5], c_qng_w21a[5], c_qng
 constexpr double kSqrtDblEps = 1.4901161193847656e-08;
 constexpr double kDblEps = 2.2204460492503131e-16;
 
+
+// ---------------------------------------------------------------------------------------------
+// The scalar part of the second stage, shared by the block-per-candidate engine below and the
+// warp-per-candidate engine of threetax_warp.cuh (CRTP: D supplies the likelihood passes).
+// D must provide:
+//   double f_pend(double pend)               set the pendant length, return Three_tax.log_like
+//   double f_dist(double dist, double prox)  set distal / proximal lengths, return log_like
+//   void   set_dist_prox(double, double), void cache_w(), double eval_full_cache()
+//   void   hint_brent(kind, left, right, start, v)   points Brent is about to evaluate (may batch)
+//   void   hint_begin() / hint_add(x) / hint_flush() pendant points QNG is about to evaluate
+// Every thread of the owning warp / block executes this code redundantly on identical values.
+// ---------------------------------------------------------------------------------------------
+struct Prior {
+  int kind;
+  double mean;
+  __device__ double operator()(double x) const {  // core.ml:87-92; gsl_ran_exponential_pdf
+    if (kind == 0) return 1.0;
+    if (x < 0.0) return 0.0;
+    return exp(-x / mean) / mean;
+  }
+};
+enum : int { OBJ_PEND = 0, OBJ_DIST = 1, OBJ_UPPER = 2 };
+
+template <class D>
+struct TTDriver {
+  double pend_bl, dist_bl, prox_bl;
+  int calls;
+  Prior prior;
+  double target_ll, base_ll, upper_limit, pp_rel_err;
+  int pp_status;
+
+  __device__ __forceinline__ D &self() { return *static_cast<D *>(this); }
+
+  __device__ __noinline__ double objective(int kind, double v) {
+    if (kind == OBJ_PEND) {  // three_tax.ml:51-54 with set_pend_bl
+      calls++;
+      return -self().f_pend(v);
+    }
+    if (kind == OBJ_DIST) {  // three_tax.ml:41-45,51-54 with set_dist_bl
+      calls++;
+      const double prox = (dist_bl + prox_bl) - v;
+      if (!(prox >= 0.0)) return __longlong_as_double(0x7ff8000000000000LL);
+      return -self().f_dist(v, prox);
+    }
+    // OBJ_UPPER: three_tax.ml:144-150
+    const double like = self().f_pend(v) + log(prior(v));
+    const double x = fabs(target_ll - like);
+    return (x == __longlong_as_double(0x7ff0000000000000LL)) ? 100000.0 : x;
+  }
+
+  // Minimization.brent (minimization.ml:83-101) with bisection_start_finder (:24-41) and GSL's
+  // gsl_min_fminimizer_set + brent (GSL 2.7 min/fsolver.c, min/brent.c; SURVEY.md App. A.1).
+  __device__ __noinline__ int brent(int kind, double raw_start, double left, double right, double tolerance,
+                                    int max_iters, double *xmin_out) {
+    auto f = [this, kind](double v) { return objective(kind, v); };
+    if (left >= raw_start || raw_start >= right) return ST_INVALID_START;
+    const double golden = 0.3819660;
+    // f(left), f(right), f(raw_start) and GSL's first interior point are known in advance
+    self().hint_brent(kind, left, right, raw_start, left + golden * (right - left));
+    const double lefty = f(left), righty = f(right);
+    const double smaller = (lefty < righty) ? left : right;
+    double miny = fmin(lefty, righty);
+    if (lefty != lefty || righty != righty) miny = __longlong_as_double(0x7ff8000000000000LL);
+    double start, prev = raw_start;
+    for (int iter = 1;; ++iter) {
+      const double pv = f(prev);
+      if (pv < miny) { start = prev; break; }
+      if (fabs(prev - smaller) < tolerance) { *xmin_out = smaller; return ST_OK; }  // FoundMin
+      if (iter > max_iters) return ST_FIND_START_FAILURE;
+      prev = (prev + smaller) / 2.0;
+    }
+    double x_minimum = start, x_lower = left, x_upper = right;
+    double f_lower = f(x_lower);
+    if (!isfinite(f_lower)) return ST_GSL_EBADFUNC;
+    double f_upper = f(x_upper);
+    if (!isfinite(f_upper)) return ST_GSL_EBADFUNC;
+    double f_minimum = f(x_minimum);
+    if (!isfinite(f_minimum)) return ST_GSL_EBADFUNC;
+    if (x_lower > x_upper) return ST_GSL_EINVAL;
+    if (x_minimum >= x_upper || x_minimum <= x_lower) return ST_GSL_EINVAL;
+    if (f_minimum >= f_lower || f_minimum >= f_upper) return ST_GSL_EINVAL;
+    double v = x_lower + golden * (x_upper - x_lower), wv = v, d = 0.0, e = 0.0;
+    const double f_vw = f(v);
+    if (!isfinite(f_vw)) return ST_GSL_EBADFUNC;
+    double f_v = f_vw, f_w = f_vw;
+    for (int step = 1;; ++step) {
+      if (step > max_iters) return ST_EXCEEDED_MAX_ITER;
+      const double x_left = x_lower, x_right = x_upper, z = x_minimum, f_z = f_minimum;
+      double dd = e, ee = d;  // GSL: d = state->e; e = state->d
+      double u;
+      const double w_lower = z - x_left, w_upper = x_right - z;
+      const double tol = kSqrtDblEps * fabs(z);
+      double p = 0.0, q = 0.0, r = 0.0;
+      const double midpoint = 0.5 * (x_left + x_right);
+      if (fabs(ee) > tol) {
+        r = (z - wv) * (f_z - f_v);
+        q = (z - v) * (f_z - f_w);
+        p = (z - v) * q - (z - wv) * r;
+        q = 2.0 * (q - r);
+        if (q > 0.0) p = -p; else q = -q;
+        r = ee;
+        ee = dd;
+      }
+      if (fabs(p) < fabs(0.5 * q * r) && p < q * w_lower && p < q * w_upper) {
+        const double t2 = 2.0 * tol;
+        dd = p / q;
+        u = z + dd;
+        if ((u - x_left) < t2 || (x_right - u) < t2) dd = (z < midpoint) ? tol : -tol;
+      } else {
+        ee = (z < midpoint) ? x_right - z : -(z - x_left);
+        dd = golden * ee;
+      }
+      if (fabs(dd) >= tol) u = z + dd; else u = z + ((dd > 0.0) ? tol : -tol);
+      e = ee;
+      d = dd;
+      const double f_u = f(u);
+      if (!isfinite(f_u)) return ST_GSL_EBADFUNC;
+      if (f_u <= f_z) {
+        if (u < z) { x_upper = z; f_upper = f_z; } else { x_lower = z; f_lower = f_z; }
+        v = wv; f_v = f_w; wv = z; f_w = f_z; x_minimum = u; f_minimum = f_u;
+      } else {
+        if (u < z) { x_lower = u; f_lower = f_u; } else { x_upper = u; f_upper = f_u; }
+        if (f_u <= f_w || wv == z) { v = wv; f_v = f_w; wv = u; f_w = f_u; }
+        else if (f_u <= f_v || v == z || v == wv) { v = u; f_v = f_u; }
+      }
+      if (x_upper - x_lower < tolerance) { *xmin_out = x_minimum; return ST_OK; }
+    }
+  }
+
+  // Three_tax.optimize (three_tax.ml:70-83)
+  __device__ __noinline__ int optimize(double tolerance, double max_pend, int max_iter) {
+    double prev_pend = pend_bl, prev_dist = dist_bl;
+    for (int step = 1;; ++step) {
+      if (step > max_iter) return ST_EXCEEDED_MAX_ITER;
+      double curr_pend = pend_bl, curr_dist = dist_bl;
+      if (1e-8 != max_pend) {
+        self().cache_w();  // w = (statd*prox_ev)*dist_ev per site, for the pendant-only evaluations
+        const int st = brent(OBJ_PEND, pend_bl, 1e-8, max_pend, tolerance, 100, &curr_pend);
+        if (st != ST_OK) return st;
+      }
+      const double cut = dist_bl + prox_bl;
+      if (0.0 != cut) {
+        const int st = brent(OBJ_DIST, dist_bl, 0.0, cut, tolerance, 100, &curr_dist);
+        if (st != ST_OK) return st;
+      }
+      if (fabs(prev_pend - curr_pend) > tolerance || fabs(prev_dist - curr_dist) > tolerance) {
+        prev_pend = curr_pend;
+        prev_dist = curr_dist;
+      } else
+        return ST_OK;
+    }
+  }
+
+  // ---- --pp : Three_tax.calc_marg_prob (three_tax.ml:169-215) ----
+  __device__ int find_upper_limit(double max_pend, double orig_ll, double *out) {  // :124-159
+    const double orig_pend = pend_bl;
+    if (prior(orig_pend) == 0.0) {
+      double curr = orig_pend;
+      for (;;) {
+        const double next = curr / 2.0;
+        if (prior(next) > exp(-10.0)) { *out = curr; return ST_OK; }
+        curr = next;
+      }
+    }
+    target_ll = -10.0 + orig_ll + log(prior(orig_pend));
+    const double start = orig_pend + ((max_pend - orig_pend) / 2.0);
+    const int st = brent(OBJ_UPPER, start, orig_pend, max_pend, 0.02, 10, out);
+    if (st == ST_GSL_EINVAL) { *out = max_pend; return ST_OK; }
+    return st;
+  }
+
+  static __device__ double rescale_error(double err, double result_abs, double result_asc) {
+    err = fabs(err);
+    if (result_asc != 0.0 && err != 0.0) {
+      const double scale = pow((200.0 * err / result_asc), 1.5);
+      err = (scale < 1.0) ? result_asc * scale : result_asc;
+    }
+    if (result_abs > 2.2250738585072014e-308 / (50.0 * kDblEps)) {
+      const double min_err = 50.0 * kDblEps * result_abs;
+      if (min_err > err) err = min_err;
+    }
+    return err;
+  }
+
+  // integrands: inner (three_tax.ml:187-189) and outer (:192-197)
+  __device__ __noinline__ double integrand_inner(double pend) {
+    return exp(self().f_pend(pend) - base_ll) * prior(pend);
+  }
+  __device__ __noinline__ double integrand_outer(double dist) {
+    if (pp_status) return 0.0;  // the reference's exception is already unwinding
+    const double prox = (dist_bl + prox_bl) - dist;
+    if (!(prox >= 0.0)) { pp_status = ST_ASSERT; return 0.0; }
+    self().set_dist_prox(dist, prox);
+    self().cache_w();
+    double res;
+    const int st = qng<false>(0.0, upper_limit, 0.0, pp_rel_err, &res);
+    if (st) pp_status = st;
+    return res;
+  }
+
+  // gsl_integration_qng (GSL 2.7 integration/qng.c).  The abscissae of each
+  // rule are announced to the engine (hint_*) before the rule is evaluated, in evaluation order.
+  template <bool OUTER>
+  __device__ __noinline__ int qng(double a, double b, double epsabs, double epsrel, double *result) {
+    auto f = [this](double v) { return OUTER ? integrand_outer(v) : integrand_inner(v); };
+    double fv1[5], fv2[5], fv3[5], fv4[5], savfun[21];
+    const double half_length = 0.5 * (b - a), abs_half_length = fabs(half_length), center = 0.5 * (b + a);
+    if (!OUTER) {
+      self().hint_begin();
+      self().hint_add(center);
+      for (int k = 0; k < 5; ++k) { const double ab = half_length * c_qng_x1[k]; self().hint_add(center + ab); self().hint_add(center - ab); }
+      for (int k = 0; k < 5; ++k) { const double ab = half_length * c_qng_x2[k]; self().hint_add(center + ab); self().hint_add(center - ab); }
+      self().hint_flush();
+    }
+    const double f_center = f(center);
+    if (epsabs <= 0.0 && (epsrel < 50.0 * kDblEps || epsrel < 0.5e-28)) { *result = 0.0; return ST_GSL_EBADTOL; }
+    double res10 = 0.0, res21 = c_qng_w21b[5] * f_center, resabs = c_qng_w21b[5] * fabs(f_center);
+    for (int k = 0; k < 5; ++k) {
+      const double ab = half_length * c_qng_x1[k];
+      const double f1 = f(center + ab), f2 = f(center - ab), fv = f1 + f2;
+      res10 += c_qng_w10[k] * fv;
+      res21 += c_qng_w21a[k] * fv;
+      resabs += c_qng_w21a[k] * (fabs(f1) + fabs(f2));
+      savfun[k] = fv; fv1[k] = f1; fv2[k] = f2;
+    }
+    for (int k = 0; k < 5; ++k) {
+      const double ab = half_length * c_qng_x2[k];
+      const double f1 = f(center + ab), f2 = f(center - ab), fv = f1 + f2;
+      res21 += c_qng_w21b[k] * fv;
+      resabs += c_qng_w21b[k] * (fabs(f1) + fabs(f2));
+      savfun[k + 5] = fv; fv3[k] = f1; fv4[k] = f2;
+    }
+    resabs *= abs_half_length;
+    const double mean = 0.5 * res21;
+    double resasc = c_qng_w21b[5] * fabs(f_center - mean);
+    for (int k = 0; k < 5; ++k)
+      resasc += (c_qng_w21a[k] * (fabs(fv1[k] - mean) + fabs(fv2[k] - mean)) +
+                 c_qng_w21b[k] * (fabs(fv3[k] - mean) + fabs(fv4[k] - mean)));
+    resasc *= abs_half_length;
+    double result_kronrod = res21 * half_length;
+    double err = rescale_error((res21 - res10) * half_length, resabs, resasc);
+    if (err < epsabs || err < epsrel * fabs(result_kronrod)) { *result = result_kronrod; return ST_OK; }
+    if (!OUTER) {
+      self().hint_begin();
+      for (int k = 0; k < 11; ++k) { const double ab = half_length * c_qng_x3[k]; self().hint_add(center + ab); self().hint_add(center - ab); }
+      self().hint_flush();
+    }
+    double res43 = c_qng_w43b[11] * f_center;
+    for (int k = 0; k < 10; ++k) res43 += savfun[k] * c_qng_w43a[k];
+    for (int k = 0; k < 11; ++k) {
+      const double ab = half_length * c_qng_x3[k];
+      const double fv = f(center + ab) + f(center - ab);
+      res43 += fv * c_qng_w43b[k];
+      savfun[k + 10] = fv;
+    }
+    result_kronrod = res43 * half_length;
+    err = rescale_error((res43 - res21) * half_length, resabs, resasc);
+    if (err < epsabs || err < epsrel * fabs(result_kronrod)) { *result = result_kronrod; return ST_OK; }
+    if (!OUTER) {
+      self().hint_begin();
+      for (int k = 0; k < 22; ++k) { const double ab = half_length * c_qng_x4[k]; self().hint_add(center + ab); self().hint_add(center - ab); }
+      self().hint_flush();
+    }
+    double res87 = c_qng_w87b[22] * f_center;
+    for (int k = 0; k < 21; ++k) res87 += savfun[k] * c_qng_w87a[k];
+    for (int k = 0; k < 22; ++k) {
+      const double ab = half_length * c_qng_x4[k];
+      res87 += c_qng_w87b[k] * (f(center + ab) + f(center - ab));
+    }
+    result_kronrod = res87 * half_length;
+    err = rescale_error((res87 - res43) * half_length, resabs, resasc);
+    *result = result_kronrod;
+    if (err < epsabs || err < epsrel * fabs(result_kronrod)) return ST_OK;
+    return ST_GSL_ETOL;
+  }
+
+  __device__ int calc_marg_prob(double rel_err, double max_pend, double *out) {
+    pp_rel_err = rel_err;
+    base_ll = self().eval_full_cache();
+    const double cut_bl = dist_bl + prox_bl;
+    int st = find_upper_limit(max_pend, base_ll, &upper_limit);
+    if (st) return st;
+    for (int n_exceptions = 0;; ++n_exceptions) {
+      if (n_exceptions >= 10) { *out = base_ll; return ST_OK; }
+      pp_status = 0;
+      double val;
+      if (fabs(cut_bl - 0.0) < 1e-5) {  // cut_bl =~ 0.  (ppatteries.ml:96)
+        self().set_dist_prox(cut_bl / 2.0, (dist_bl + prox_bl) - cut_bl / 2.0);
+        self().cache_w();
+        pp_status = qng<false>(0.0, upper_limit, 0.0, rel_err, &val);
+      } else {
+        double res;
+        const int so = qng<true>(0.0, cut_bl, 0.0, rel_err, &res);
+        if (!pp_status && so) pp_status = so;
+        val = res / cut_bl;
+      }
+      if (pp_status == ST_GSL_ETOL) { upper_limit = upper_limit / 2.0; continue; }
+      if (pp_status) return pp_status;
+      *out = base_ll + log(val);
+      return ST_OK;
+    }
+  }
+};
+
 template <int S, bool GCAT, int THREADS>
-struct ThreeTax {
+struct ThreeTax : TTDriver<ThreeTax<S, GCAT, THREADS>> {
+  using Base = TTDriver<ThreeTax<S, GCAT, THREADS>>;
+  using Base::pend_bl; using Base::dist_bl; using Base::prox_bl; using Base::calls;
   static constexpr int RS = p_rstride<S, GCAT>();
   // ---- shared memory views ----
   double *statd, *lam, *x, *xit, *rates, *ex, *Pd, *Pp, *Pq, *Tp, *red;
@@ -79,8 +385,6 @@ struct ThreeTax {
   int64_t wstride;
   int nq, loc;
   double e_tot_ln2, rate_term;
-  double pend_bl, dist_bl, prox_bl;
-  int calls;
 
   static __host__ __device__ size_t smem_doubles(int Rt, int nc) {
     size_t n = 0;
@@ -231,274 +535,14 @@ struct ThreeTax {
     set_dist_prox(distal, cut_bl - distal);
   }
 
-  // ---- objective functions ----
-  struct Prior {
-    int kind;
-    double mean;
-    __device__ double operator()(double x) const {  // core.ml:87-92; gsl_ran_exponential_pdf
-      if (kind == 0) return 1.0;
-      if (x < 0.0) return 0.0;
-      return exp(-x / mean) / mean;
-    }
-  };
-  enum : int { OBJ_PEND = 0, OBJ_DIST = 1, OBJ_UPPER = 2 };
-  Prior prior;
-  double target_ll, base_ll, upper_limit, pp_rel_err;
-  int pp_status;
-
-  __device__ __noinline__ double objective(int kind, double v) {
-    if (kind == OBJ_PEND) {  // three_tax.ml:51-54 with set_pend_bl
-      calls++;
-      set_pend(v);
-      return -eval_pend_cached();
-    }
-    if (kind == OBJ_DIST) {  // three_tax.ml:41-45,51-54 with set_dist_bl
-      calls++;
-      const double prox = (dist_bl + prox_bl) - v;
-      if (!(prox >= 0.0)) return __longlong_as_double(0x7ff8000000000000LL);
-      set_dist_prox(v, prox);
-      return -eval_full_plain();
-    }
-    // OBJ_UPPER: three_tax.ml:144-150
-    set_pend(v);
-    const double like = eval_pend_cached() + log(prior(v));
-    const double x = fabs(target_ll - like);
-    return (x == __longlong_as_double(0x7ff0000000000000LL)) ? 100000.0 : x;
-  }
-
-  // Minimization.brent (minimization.ml:83-101) with bisection_start_finder (:24-41) and GSL's
-  // gsl_min_fminimizer_set + brent (GSL 2.7 min/fsolver.c, min/brent.c; SURVEY.md App. A.1).
-  __device__ __noinline__ int brent(int kind, double raw_start, double left, double right, double tolerance,
-                                    int max_iters, double *xmin_out) {
-    auto f = [this, kind](double v) { return objective(kind, v); };
-    if (left >= raw_start || raw_start >= right) return ST_INVALID_START;
-    const double lefty = f(left), righty = f(right);
-    const double smaller = (lefty < righty) ? left : right;
-    double miny = fmin(lefty, righty);
-    if (lefty != lefty || righty != righty) miny = __longlong_as_double(0x7ff8000000000000LL);
-    double start, prev = raw_start;
-    for (int iter = 1;; ++iter) {
-      const double pv = f(prev);
-      if (pv < miny) { start = prev; break; }
-      if (fabs(prev - smaller) < tolerance) { *xmin_out = smaller; return ST_OK; }  // FoundMin
-      if (iter > max_iters) return ST_FIND_START_FAILURE;
-      prev = (prev + smaller) / 2.0;
-    }
-    double x_minimum = start, x_lower = left, x_upper = right;
-    double f_lower = f(x_lower);
-    if (!isfinite(f_lower)) return ST_GSL_EBADFUNC;
-    double f_upper = f(x_upper);
-    if (!isfinite(f_upper)) return ST_GSL_EBADFUNC;
-    double f_minimum = f(x_minimum);
-    if (!isfinite(f_minimum)) return ST_GSL_EBADFUNC;
-    if (x_lower > x_upper) return ST_GSL_EINVAL;
-    if (x_minimum >= x_upper || x_minimum <= x_lower) return ST_GSL_EINVAL;
-    if (f_minimum >= f_lower || f_minimum >= f_upper) return ST_GSL_EINVAL;
-    const double golden = 0.3819660;
-    double v = x_lower + golden * (x_upper - x_lower), wv = v, d = 0.0, e = 0.0;
-    const double f_vw = f(v);
-    if (!isfinite(f_vw)) return ST_GSL_EBADFUNC;
-    double f_v = f_vw, f_w = f_vw;
-    for (int step = 1;; ++step) {
-      if (step > max_iters) return ST_EXCEEDED_MAX_ITER;
-      const double x_left = x_lower, x_right = x_upper, z = x_minimum, f_z = f_minimum;
-      double dd = e, ee = d;  // GSL: d = state->e; e = state->d
-      double u;
-      const double w_lower = z - x_left, w_upper = x_right - z;
-      const double tol = kSqrtDblEps * fabs(z);
-      double p = 0.0, q = 0.0, r = 0.0;
-      const double midpoint = 0.5 * (x_left + x_right);
-      if (fabs(ee) > tol) {
-        r = (z - wv) * (f_z - f_v);
-        q = (z - v) * (f_z - f_w);
-        p = (z - v) * q - (z - wv) * r;
-        q = 2.0 * (q - r);
-        if (q > 0.0) p = -p; else q = -q;
-        r = ee;
-        ee = dd;
-      }
-      if (fabs(p) < fabs(0.5 * q * r) && p < q * w_lower && p < q * w_upper) {
-        const double t2 = 2.0 * tol;
-        dd = p / q;
-        u = z + dd;
-        if ((u - x_left) < t2 || (x_right - u) < t2) dd = (z < midpoint) ? tol : -tol;
-      } else {
-        ee = (z < midpoint) ? x_right - z : -(z - x_left);
-        dd = golden * ee;
-      }
-      if (fabs(dd) >= tol) u = z + dd; else u = z + ((dd > 0.0) ? tol : -tol);
-      e = ee;
-      d = dd;
-      const double f_u = f(u);
-      if (!isfinite(f_u)) return ST_GSL_EBADFUNC;
-      if (f_u <= f_z) {
-        if (u < z) { x_upper = z; f_upper = f_z; } else { x_lower = z; f_lower = f_z; }
-        v = wv; f_v = f_w; wv = z; f_w = f_z; x_minimum = u; f_minimum = f_u;
-      } else {
-        if (u < z) { x_lower = u; f_lower = f_u; } else { x_upper = u; f_upper = f_u; }
-        if (f_u <= f_w || wv == z) { v = wv; f_v = f_w; wv = u; f_w = f_u; }
-        else if (f_u <= f_v || v == z || v == wv) { v = u; f_v = f_u; }
-      }
-      if (x_upper - x_lower < tolerance) { *xmin_out = x_minimum; return ST_OK; }
-    }
-  }
-
-  // Three_tax.optimize (three_tax.ml:70-83)
-  __device__ __noinline__ int optimize(double tolerance, double max_pend, int max_iter) {
-    double prev_pend = pend_bl, prev_dist = dist_bl;
-    for (int step = 1;; ++step) {
-      if (step > max_iter) return ST_EXCEEDED_MAX_ITER;
-      double curr_pend = pend_bl, curr_dist = dist_bl;
-      if (1e-8 != max_pend) {
-        (void)eval_full_cache();  // cache w for the pendant-only evaluations
-        const int st = brent(OBJ_PEND, pend_bl, 1e-8, max_pend, tolerance, 100, &curr_pend);
-        if (st != ST_OK) return st;
-      }
-      const double cut = dist_bl + prox_bl;
-      if (0.0 != cut) {
-        const int st = brent(OBJ_DIST, dist_bl, 0.0, cut, tolerance, 100, &curr_dist);
-        if (st != ST_OK) return st;
-      }
-      if (fabs(prev_pend - curr_pend) > tolerance || fabs(prev_dist - curr_dist) > tolerance) {
-        prev_pend = curr_pend;
-        prev_dist = curr_dist;
-      } else
-        return ST_OK;
-    }
-  }
-
-  // ---- --pp : Three_tax.calc_marg_prob (three_tax.ml:169-215) ----
-  __device__ int find_upper_limit(double max_pend, double orig_ll, double *out) {  // :124-159
-    const double orig_pend = pend_bl;
-    if (prior(orig_pend) == 0.0) {
-      double curr = orig_pend;
-      for (;;) {
-        const double next = curr / 2.0;
-        if (prior(next) > exp(-10.0)) { *out = curr; return ST_OK; }
-        curr = next;
-      }
-    }
-    target_ll = -10.0 + orig_ll + log(prior(orig_pend));
-    const double start = orig_pend + ((max_pend - orig_pend) / 2.0);
-    const int st = brent(OBJ_UPPER, start, orig_pend, max_pend, 0.02, 10, out);
-    if (st == ST_GSL_EINVAL) { *out = max_pend; return ST_OK; }
-    return st;
-  }
-
-  static __device__ double rescale_error(double err, double result_abs, double result_asc) {
-    err = fabs(err);
-    if (result_asc != 0.0 && err != 0.0) {
-      const double scale = pow((200.0 * err / result_asc), 1.5);
-      err = (scale < 1.0) ? result_asc * scale : result_asc;
-    }
-    if (result_abs > 2.2250738585072014e-308 / (50.0 * kDblEps)) {
-      const double min_err = 50.0 * kDblEps * result_abs;
-      if (min_err > err) err = min_err;
-    }
-    return err;
-  }
-
-  // integrands: inner (three_tax.ml:187-189) and outer (:192-197)
-  __device__ __noinline__ double integrand_inner(double pend) {
-    set_pend(pend);
-    return exp(eval_pend_cached() - base_ll) * prior(pend);
-  }
-  __device__ __noinline__ double integrand_outer(double dist) {
-    if (pp_status) return 0.0;  // the reference's exception is already unwinding
-    const double prox = (dist_bl + prox_bl) - dist;
-    if (!(prox >= 0.0)) { pp_status = ST_ASSERT; return 0.0; }
-    set_dist_prox(dist, prox);
-    (void)eval_full_cache();
-    double res;
-    const int st = qng<false>(0.0, upper_limit, 0.0, pp_rel_err, &res);
-    if (st) pp_status = st;
-    return res;
-  }
-
-  // gsl_integration_qng (GSL 2.7 integration/qng.c)
-  template <bool OUTER>
-  __device__ __noinline__ int qng(double a, double b, double epsabs, double epsrel, double *result) {
-    auto f = [this](double v) { return OUTER ? integrand_outer(v) : integrand_inner(v); };
-    double fv1[5], fv2[5], fv3[5], fv4[5], savfun[21];
-    const double half_length = 0.5 * (b - a), abs_half_length = fabs(half_length), center = 0.5 * (b + a);
-    const double f_center = f(center);
-    if (epsabs <= 0.0 && (epsrel < 50.0 * kDblEps || epsrel < 0.5e-28)) { *result = 0.0; return ST_GSL_EBADTOL; }
-    double res10 = 0.0, res21 = c_qng_w21b[5] * f_center, resabs = c_qng_w21b[5] * fabs(f_center);
-    for (int k = 0; k < 5; ++k) {
-      const double ab = half_length * c_qng_x1[k];
-      const double f1 = f(center + ab), f2 = f(center - ab), fv = f1 + f2;
-      res10 += c_qng_w10[k] * fv;
-      res21 += c_qng_w21a[k] * fv;
-      resabs += c_qng_w21a[k] * (fabs(f1) + fabs(f2));
-      savfun[k] = fv; fv1[k] = f1; fv2[k] = f2;
-    }
-    for (int k = 0; k < 5; ++k) {
-      const double ab = half_length * c_qng_x2[k];
-      const double f1 = f(center + ab), f2 = f(center - ab), fv = f1 + f2;
-      res21 += c_qng_w21b[k] * fv;
-      resabs += c_qng_w21b[k] * (fabs(f1) + fabs(f2));
-      savfun[k + 5] = fv; fv3[k] = f1; fv4[k] = f2;
-    }
-    resabs *= abs_half_length;
-    const double mean = 0.5 * res21;
-    double resasc = c_qng_w21b[5] * fabs(f_center - mean);
-    for (int k = 0; k < 5; ++k)
-      resasc += (c_qng_w21a[k] * (fabs(fv1[k] - mean) + fabs(fv2[k] - mean)) +
-                 c_qng_w21b[k] * (fabs(fv3[k] - mean) + fabs(fv4[k] - mean)));
-    resasc *= abs_half_length;
-    double result_kronrod = res21 * half_length;
-    double err = rescale_error((res21 - res10) * half_length, resabs, resasc);
-    if (err < epsabs || err < epsrel * fabs(result_kronrod)) { *result = result_kronrod; return ST_OK; }
-    double res43 = c_qng_w43b[11] * f_center;
-    for (int k = 0; k < 10; ++k) res43 += savfun[k] * c_qng_w43a[k];
-    for (int k = 0; k < 11; ++k) {
-      const double ab = half_length * c_qng_x3[k];
-      const double fv = f(center + ab) + f(center - ab);
-      res43 += fv * c_qng_w43b[k];
-      savfun[k + 10] = fv;
-    }
-    result_kronrod = res43 * half_length;
-    err = rescale_error((res43 - res21) * half_length, resabs, resasc);
-    if (err < epsabs || err < epsrel * fabs(result_kronrod)) { *result = result_kronrod; return ST_OK; }
-    double res87 = c_qng_w87b[22] * f_center;
-    for (int k = 0; k < 21; ++k) res87 += savfun[k] * c_qng_w87a[k];
-    for (int k = 0; k < 22; ++k) {
-      const double ab = half_length * c_qng_x4[k];
-      res87 += c_qng_w87b[k] * (f(center + ab) + f(center - ab));
-    }
-    result_kronrod = res87 * half_length;
-    err = rescale_error((res87 - res43) * half_length, resabs, resasc);
-    *result = result_kronrod;
-    if (err < epsabs || err < epsrel * fabs(result_kronrod)) return ST_OK;
-    return ST_GSL_ETOL;
-  }
-
-  __device__ int calc_marg_prob(double rel_err, double max_pend, double *out) {
-    pp_rel_err = rel_err;
-    base_ll = eval_full_cache();
-    const double cut_bl = dist_bl + prox_bl;
-    int st = find_upper_limit(max_pend, base_ll, &upper_limit);
-    if (st) return st;
-    for (int n_exceptions = 0;; ++n_exceptions) {
-      if (n_exceptions >= 10) { *out = base_ll; return ST_OK; }
-      pp_status = 0;
-      double val;
-      if (fabs(cut_bl - 0.0) < 1e-5) {  // cut_bl =~ 0.  (ppatteries.ml:96)
-        set_dist_prox(cut_bl / 2.0, (dist_bl + prox_bl) - cut_bl / 2.0);
-        (void)eval_full_cache();
-        pp_status = qng<false>(0.0, upper_limit, 0.0, rel_err, &val);
-      } else {
-        double res;
-        const int so = qng<true>(0.0, cut_bl, 0.0, rel_err, &res);
-        if (!pp_status && so) pp_status = so;
-        val = res / cut_bl;
-      }
-      if (pp_status == ST_GSL_ETOL) { upper_limit = upper_limit / 2.0; continue; }
-      if (pp_status) return pp_status;
-      *out = base_ll + log(val);
-      return ST_OK;
-    }
-  }
+  // ---- TTDriver engine interface: one likelihood pass per objective call ----
+  __device__ __forceinline__ double f_pend(double v) { set_pend(v); return eval_pend_cached(); }
+  __device__ __forceinline__ double f_dist(double d, double p) { set_dist_prox(d, p); return eval_full_plain(); }
+  __device__ __forceinline__ void cache_w() { (void)eval_full_cache(); }
+  __device__ __forceinline__ void hint_brent(int, double, double, double, double) {}
+  __device__ __forceinline__ void hint_begin() {}
+  __device__ __forceinline__ void hint_add(double) {}
+  __device__ __forceinline__ void hint_flush() {}
 };
 
 // Persistent kernel: blocks pull candidates from `counter` until n are done.

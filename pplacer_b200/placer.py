@@ -185,6 +185,13 @@ class Placer:
     def prefilter_kernel_used(self) -> int:
         return int(_lib.load().pp_prefilter_kernel_used(self.ctx))
 
+    def set_three_tax_engine(self, engine: int, blocks_per_sm: int = 0):
+        """0 default, 1 block-per-candidate, 2 warp-per-candidate (DNA Gamma-4 only)."""
+        _lib.check(_lib.load().pp_set_three_tax_engine(self.ctx, int(engine), int(blocks_per_sm)))
+
+    def three_tax_engine_used(self) -> int:
+        return int(_lib.load().pp_three_tax_engine_used(self.ctx))
+
     # ---- instrumentation ------------------------------------------------------------------
     def kernel_launches(self, reset: bool = False) -> int:
         return int(_lib.load().pp_kernel_launches(self.ctx, 1 if reset else 0))

@@ -1,0 +1,79 @@
+"""`pplacer -c REFPKG queries.fasta` for the placement path, without the OCaml host:
+refpkg + query FASTA -> Problem (pre-mask, de-duplicate; pplacer_run.ml:59-253) -> pp_place on one
+GPU or sharded over the ranks of a torch.distributed job -> jplace (placerun_io.ml:58-89).
+This is the thin host front-end of SURVEY.md section 8(f) rows 1-2; flag names follow prefs.ml:185-290.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import jplace, refpkg, seqio
+from .placer import Placer
+from .reference import build_problem
+
+
+def place_problem(prob, device: int = 0, pp: bool = False, **prefs_kw):
+    with Placer(prob, device=device) as p:
+        p.precompute()
+        prefs = p.prefs(pp=pp, **prefs_kw)
+        out, n_out, st, _ = p.place(prob.query_chars, prefs)
+    return out, n_out, st
+
+
+def run_file(refpkg_path: str, query_fasta: str, out_path: Optional[str] = None, pp: bool = False,
+             device: int = 0, pre_mask: bool = True, discard_nonoverlapped: bool = False, invocation: str = "",
+             **prefs_kw):
+    """Pplacer_run.run_file (pplacer_run.ml:682-783) for a refpkg and one query file."""
+    tree, aln, model = refpkg.load(refpkg_path)
+    queries = seqio.read_fasta(query_fasta, upper=True)          # pplacer_run.ml:409
+    prob = build_problem(tree, model, aln, queries, pre_mask=pre_mask, discard_nonoverlapped=discard_nonoverlapped)
+    out, n_out, st = place_problem(prob, device=device, pp=pp, **prefs_kw)
+    bad = np.nonzero(st != 0)[0]
+    for q in bad:
+        sys.stderr.write("Warning: %s: no placement (status %d)\n" % (prob.query_names[q][0], st[q]))
+    if out_path is None:
+        stem = os.path.basename(query_fasta)
+        for ext in (".gz", ".fasta", ".fa", ".fna", ".faa"):
+            if stem.endswith(ext):
+                stem = stem[: -len(ext)]
+        out_path = stem + ".jplace"
+    jplace.write_jplace(out_path, prob.tree, prob.query_names, out, n_out, st, pp=pp,
+                        invocation=invocation or "pplacer_b200 -c %s %s" % (refpkg_path, query_fasta))
+    return out_path, prob, (out, n_out, st)
+
+
+def main(argv: Optional[List[str]] = None) -> int:
+    ap = argparse.ArgumentParser(prog="pplacer_b200", description=__doc__.split("\n")[0])
+    ap.add_argument("-c", dest="refpkg", required=True, help="reference package path")
+    ap.add_argument("-o", dest="out", default=None, help="output jplace file")
+    ap.add_argument("-p", dest="pp", action="store_true", help="posterior probability mode (prefs.ml:198-203)")
+    ap.add_argument("--keep-at-most", type=int)
+    ap.add_argument("--keep-factor", type=float)
+    ap.add_argument("--max-strikes", type=int)
+    ap.add_argument("--strike-box", type=float)
+    ap.add_argument("--max-pitches", type=int)
+    ap.add_argument("--max-pend", type=float)
+    ap.add_argument("--no-pre-mask", action="store_true")
+    ap.add_argument("--discard-nonoverlapped", action="store_true")
+    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("queries")
+    a = ap.parse_args(argv)
+    kw = {k: getattr(a, k) for k in ("keep_at_most", "keep_factor", "max_strikes", "strike_box", "max_pitches", "max_pend")
+          if getattr(a, k) is not None}
+    t0 = time.perf_counter()
+    path, prob, (out, n_out, st) = run_file(a.refpkg, a.queries, a.out, pp=a.pp, device=a.device, pre_mask=not a.no_pre_mask,
+                                           discard_nonoverlapped=a.discard_nonoverlapped,
+                                           invocation=" ".join(["pplacer_b200"] + (argv if argv is not None else sys.argv[1:])), **kw)
+    sys.stderr.write("placed %d unique queries (%d names) in %.2f s -> %s\n"
+                     % (int((st == 0).sum()), sum(len(n) for n in prob.query_names), time.perf_counter() - t0, path))
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -29,7 +29,10 @@ base = os.path.join(REF, "donovan-test", "ar53_pplacer_testset")
 out = {}
 for tag in ("GOLDEN", "TEST"):
     j = json.load(open(os.path.join(base, "ar53_test_genomes.%s.json" % tag)))
+    import hashlib
     out[tag] = {"fields": j["fields"], "version": j.get("version"),
+                "tree_sha256": hashlib.sha256(j["tree"].encode()).hexdigest(), "tree_len": len(j["tree"]),
+                "invocation": j["metadata"]["invocation"],
                 "placements": [{"nm": pq.get("nm", pq.get("n")), "p": pq["p"]} for pq in j["placements"]]}
 json.dump(out, open(os.path.join(HERE, "ar53_golden.json"), "w"), indent=1)
 
