@@ -37,7 +37,16 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 METRIC = "placements/sec"
-WORKLOAD = "C2: 16S shape, 800-taxon tree (E=1597), 1500 columns, GTR+G4, synthetic reads 250-1500 columns"
+WORKLOADS = {
+    # name: (taxa, seed, description, pplacer flags, -p?, prefs overrides)
+    "c2": (800, 2, "C2: 16S shape, 800-taxon tree (E=1597), 1500 columns, GTR+G4, synthetic reads 250-1500 columns",
+           "pplacer defaults (keep_at_most 7, max_strikes 6, max_pitches 40)", False, {}),
+    "c4": (10_000, 4, "C4: 10k-taxon synthetic 16S tree (E=19997), 1500 columns, GTR+G4, synthetic reads 250-1500 columns",
+           "pplacer defaults (keep_at_most 7, max_strikes 6, max_pitches 40)", False, {}),
+    "c5": (800, 2, "C5: C2 shape in posterior-probability mode",
+           "-p --keep-at-most 40 (calc_pp, keep_factor 0.001, max_strikes 20)", True, {"keep_at_most": 40}),
+}
+WORKLOAD = WORKLOADS["c2"][2]
 
 
 def env_int(k, d):
@@ -105,21 +114,28 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
-def build_c2(Q: int, rank: int):
+def build_workload(name: str, Q: int, rank: int):
     from pplacer_b200 import synth
     from pplacer_b200.reference import build_problem
-    s = synth.simulate_reference(800, 1500, seed=2, alpha=0.5)
-    queries = synth.simulate_queries(s, Q, seed=2 + 1000 * rank)
+    taxa, seed = WORKLOADS[name][0], WORKLOADS[name][1]
+    s = synth.simulate_reference(taxa, 1500, seed=seed, alpha=0.5)
+    queries = synth.simulate_queries(s, Q, seed=seed + 1000 * rank)
     return build_problem(s.tree, s.model, s.ref_align, queries)
 
 
-def oracle_rate(prob, n_threads: int, target_s: float):
+def build_c2(Q: int, rank: int):
+    return build_workload("c2", Q, rank)
+
+
+def oracle_rate(prob, n_threads: int, target_s: float, pp: bool = False, **prefs_kw):
     """Times the CPU oracle port on a bounded sample; returns (placements/s, n_sample, seconds)."""
     from oracle import binding as ob
     from pplacer_b200 import reference
     o = ob.Oracle(prob)
     o.precompute()
-    pf = ob.default_prefs(prior_mean=reference.flat_exp_prior_mean(prob.tree))
+    if pp:   # prefs.ml:198-203
+        prefs_kw = dict(dict(calc_pp=1, keep_at_most=20, keep_factor=0.001, max_strikes=20), **prefs_kw)
+    pf = ob.default_prefs(prior_mean=reference.flat_exp_prior_mean(prob.tree), **prefs_kw)
     Q = prob.query_chars.shape[0]
     n0 = min(Q, 2 * n_threads)
     t = time.perf_counter()
@@ -141,7 +157,7 @@ def run_reference(args):
     from oracle import binding as ob
     from pplacer_b200 import reference
     cores = os.cpu_count() or 1
-    prob = build_c2(min(args.queries, 4096), 0)
+    prob = build_c2(min(args.queries if args.queries > 0 else 10_000, 4096), 0)
     o = ob.Oracle(prob)
     o.precompute()
     pf = ob.default_prefs(prior_mean=reference.flat_exp_prior_mean(prob.tree))
@@ -203,12 +219,13 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    Q = args.queries
-    prob = build_c2(Q, rank)
+    wl = WORKLOADS[args.workload]
+    Q = args.queries if args.queries > 0 else (2000 if args.workload == "c5" else 10_000)
+    prob = build_workload(args.workload, Q, rank)
     Q = prob.query_chars.shape[0]
     p = Placer(prob, device=local)
     t0 = time.perf_counter(); p.precompute(); torch.cuda.synchronize(); precompute_ms = (time.perf_counter() - t0) * 1e3
-    prefs = p.prefs()
+    prefs = p.prefs(pp=wl[4], **wl[5])
     K = prefs.keep_at_most
     stream = torch.cuda.Stream(device=dev)
     p.set_stream(stream.cuda_stream)
@@ -300,7 +317,7 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        rate, n_s, dt = oracle_rate(prob, cores, args.cpu_seconds)
+        rate, n_s, dt = oracle_rate(prob, cores, args.cpu_seconds, pp=wl[4], **wl[5])
         cpu = {"value": rate, "unit": "placements/s", "cores": cores, "kind": "port",
                "sample": "first %d queries of the workload, %.1f s, oracle port with %d threads" % (n_s, dt, cores)}
 
@@ -308,7 +325,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "placements/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "queries_per_gpu_per_step": Q, "flags": "pplacer defaults (keep_at_most 7, max_strikes 6, max_pitches 40)",
+        "config": {"workload": wl[2], "queries_per_gpu_per_step": Q, "flags": wl[3],
                    "sharding": "queries sharded over ranks, reference GLVs replicated, no data-path collective",
                    "l2": "inputs larger than L2: supernodes %.0f MB + darr/parr %.0f MB per pass" % (
                        8.0 * R * S * p.L * (E + 1) / 1e6, 16.0 * R * S * p.L * (E + 1) / 1e6),
@@ -329,7 +346,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--queries", type=int, default=10_000, help="queries per GPU per step (C2: 10k)")
+    ap.add_argument("--queries", type=int, default=0, help="queries per GPU per step (default: C2/C4 10k, C5 2k)")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="BASELINE.json config (the bench line is C2)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline sample budget")
     ap.add_argument("--ref-step-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -123,7 +123,7 @@ struct pp_ctx {
 };
 
 constexpr int kTTWarpsPerBlock = 8;
-constexpr int kTTWarpMinBlocks = 2;
+constexpr int kTTWarpDefaultBlocks = 2;
 static bool ttw_supported(const pp_ctx *c) { return c->S == 4 && !c->gcat && c->R == 4; }
 static int tt_threads(const pp_ctx *c) { return c->S == 4 ? kTTThreadsDNA : kTTThreadsAA; }
 
@@ -196,6 +196,7 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
   if (m->n_rates < 1 || m->n_rates > kMaxRates) return fail(PP_EINVAL, "pp_create: n_rates out of range");
   if (m->model_class == 1 && (!m->site_cat || !m->rates)) return fail(PP_EINVAL, "pp_create: Gcat needs rates and site_cat");
   if (L < 1 || t->n_nodes < 2) return fail(PP_EINVAL, "pp_create: empty problem");
+  if (L > kSiteMask) return fail(PP_EINVAL, "pp_create: alignment longer than 2^24 - 1 columns");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(PP_ENODEVICE, "pp_create: no CUDA device (libpplacer_b200 has no CPU fallback)"); }
   if (device < 0 || device >= ndev) return fail(PP_EINVAL, "pp_create: bad device index");
@@ -315,13 +316,12 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
   });
   size_t w_slots = (size_t)c->tt_blocks;
   if (ttw_supported(c)) {
-    auto kern = tt_warp_kernel<4, kTTWarpsPerBlock, kTTWarpMinBlocks>;
     const size_t smw = TTWarp<4>::smem_bytes(kTTWarpsPerBlock);
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
+    CK(cudaFuncSetAttribute(tt_warp_kernel<4, kTTWarpsPerBlock, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
+    CK(cudaFuncSetAttribute(tt_warp_kernel<4, kTTWarpsPerBlock, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTTWarpsPerBlock * 32, smw));
-    if (per_sm < 1) per_sm = 1;
-    c->ttw_max_blocks = per_sm * c->sm_count;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tt_warp_kernel<4, kTTWarpsPerBlock, 3>, kTTWarpsPerBlock * 32, smw));
+    c->ttw_max_blocks = std::max(per_sm, 2) * c->sm_count;
     w_slots = std::max(w_slots, (size_t)c->ttw_max_blocks * kTTWarpsPerBlock);
   }
   if ((rc = c->wbuf.ensure(w_slots * c->K * c->Lp)) != PP_OK) { pp_destroy(c); return rc; }
@@ -618,11 +618,18 @@ static int launch_three_tax_warp(pp_ctx *c, const CandIn *in, CandOut *out, int 
     c->launches += 1;
     order = c->ord_vals2.p;
   }
-  int blocks = c->ttw_max_blocks;
-  if (c->ttw_blocks_per_sm > 0) blocks = std::min(blocks, c->ttw_blocks_per_sm * c->sm_count);
+  // two builds of the kernel: <=128 registers (two blocks = 16 candidates per SM) and <=80 registers
+  // (three blocks = 24 candidates per SM); ttw_blocks_per_sm picks (default kTTWarpDefaultBlocks)
+  const int per_sm = c->ttw_blocks_per_sm > 0 ? std::min(c->ttw_blocks_per_sm, 3) : kTTWarpDefaultBlocks;
+  int blocks = std::min(c->ttw_max_blocks, per_sm * c->sm_count);
   blocks = std::min(blocks, (n + kTTWarpsPerBlock - 1) / kTTWarpsPerBlock);
-  tt_warp_kernel<4, kTTWarpsPerBlock, kTTWarpMinBlocks><<<blocks, kTTWarpsPerBlock * 32, TTWarp<4>::smem_bytes(kTTWarpsPerBlock), c->stream>>>(
-      c->dm, c->g, c->d_bl, c->codes.p, c->qsite.p, c->nq.p, in, order, out, n, prm, c->wbuf.p, c->counters.p);
+  const size_t smw = TTWarp<4>::smem_bytes(kTTWarpsPerBlock);
+  if (per_sm >= 3)
+    tt_warp_kernel<4, kTTWarpsPerBlock, 3><<<blocks, kTTWarpsPerBlock * 32, smw, c->stream>>>(
+        c->dm, c->g, c->d_bl, c->codes.p, c->qsite.p, c->nq.p, in, order, out, n, prm, c->wbuf.p, c->counters.p);
+  else
+    tt_warp_kernel<4, kTTWarpsPerBlock, 2><<<blocks, kTTWarpsPerBlock * 32, smw, c->stream>>>(
+        c->dm, c->g, c->d_bl, c->codes.p, c->qsite.p, c->nq.p, in, order, out, n, prm, c->wbuf.p, c->counters.p);
   LAUNCH_CHECK(c);
   return PP_OK;
 }

@@ -15,6 +15,8 @@ namespace ppb {
 constexpr int kMaxS = 20;
 constexpr int kMaxRates = 64;
 constexpr int kMaxCodesDev = 32;
+constexpr int kSiteCodeShift = 24;           // qsite entries: site index | alphabet code << 24
+constexpr int kSiteMask = (1 << kSiteCodeShift) - 1;
 constexpr double kLn2 = 0.693147180559945309417232121458;
 
 struct DevModel {

@@ -9,7 +9,8 @@
 namespace ppb {
 
 // chars[Q][L] -> codes[Q][Lp] (alphabet code | 0x80 if uninformative), qsite[Q][Lp] = informative
-// site indices in ascending order (Core.mask_reindex, core.ml:26-29), nq[Q], status[Q].
+// site indices in ascending order (Core.mask_reindex, core.ml:26-29) with the site's alphabet code
+// packed into bits 24-30 (kSiteMask extracts the index; one load serves both), nq[Q], status[Q].
 constexpr int kPrepThreads = 256;
 __global__ void __launch_bounds__(kPrepThreads)
 query_prep_kernel(const uint8_t *__restrict__ chars, const uint8_t *__restrict__ code_of_char, int L, int Lp,
@@ -41,7 +42,7 @@ query_prep_kernel(const uint8_t *__restrict__ chars, const uint8_t *__restrict__
     __syncthreads();
     int off = base_s;
     for (int w = 0; w < warp; ++w) off += warp_tot[w];
-    if (inf) srow[off + within] = site;
+    if (inf) srow[off + within] = site | ((int)code << kSiteCodeShift);
     __syncthreads();
     if (threadIdx.x == 0) {
       int t = 0;

@@ -473,7 +473,7 @@ struct ThreeTax : TTDriver<ThreeTax<S, GCAT, THREADS>> {
     const double *dbase = g.a[0] + (int64_t)loc * g.a_stride;
     const double *pbase = g.a[1] + (int64_t)loc * g.a_stride;
     for (int i = threadIdx.x; i < nq; i += THREADS) {
-      const int site = qsite[i];
+      const int site = qsite[i] & kSiteMask;
       const int code = qcode[site] & 0x7f;
       const int cat = GCAT ? site_cat[site] : 0;
       double u = 0.0;
@@ -508,7 +508,7 @@ struct ThreeTax : TTDriver<ThreeTax<S, GCAT, THREADS>> {
     LogProd lp;
     lp.init();
     for (int i = threadIdx.x; i < nq; i += THREADS) {
-      const int site = qsite[i];
+      const int site = qsite[i] & kSiteMask;
       const int code = qcode[site] & 0x7f;
       const int cat = GCAT ? site_cat[site] : 0;
       double u = 0.0;
@@ -525,7 +525,7 @@ struct ThreeTax : TTDriver<ThreeTax<S, GCAT, THREADS>> {
     loc = loc_;
     long long es = 0;
     for (int i = threadIdx.x; i < nq; i += THREADS) {
-      const int site = qsite[i];
+      const int site = qsite[i] & kSiteMask;
       es += (long long)g.e[0][(int64_t)loc * g.Lp + site] + (long long)g.e[1][(int64_t)loc * g.Lp + site];
     }
     es = block_sum_ll<THREADS>(es, reinterpret_cast<long long *>(red));

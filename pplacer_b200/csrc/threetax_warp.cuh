@@ -22,35 +22,71 @@
 
 namespace ppb {
 
+// running product of per-site likelihoods as (mantissa in [1,2), exponent); non-finite logs go to
+// a per-point shared slot (see LogProd in device_common.cuh for the idea).  Subnormal factors are
+// rescaled into the normal path, so the slot only ever receives -inf / +inf / NaN, whose sum does
+// not depend on the order of the additions.
+struct WarpProd {
+  double m;
+  int e;
+  __device__ __forceinline__ void init() { m = 1.0; e = 0; }
+  __device__ __forceinline__ void mul(double u, double *bad_slot) {
+    int hi = __double2hiint(u);
+    const int ef = (hi >> 20) & 0x7ff;
+    if (hi < 0 || ef == 0 || ef == 0x7ff) {
+      if (u > 0.0 && ef == 0) { u *= 0x1p600; e -= 600; }   // subnormal: exact rescale
+      else {  // log(0) = -inf, log(negative) = log(NaN) = NaN, log(+inf) = +inf (linear_c.c:418 sums log(util))
+        const double inf = __longlong_as_double(0x7ff0000000000000LL);
+        atomicAdd(bad_slot, u == 0.0 ? -inf : (u == inf ? inf : __longlong_as_double(0x7ff8000000000000LL)));
+        return;
+      }
+    }
+    const double p = m * u;  // m in [1,2), u normal  =>  p normal, no overflow
+    const int phi = __double2hiint(p);
+    e += ((phi >> 20) & 0x7ff) - 1023;
+    m = __hiloint2double((phi & 0x800fffff) | 0x3ff00000, __double2loint(p));
+  }
+};
+
+extern __shared__ double2 ppb_ttw_smem[];
+
 template <int R>
 struct TTWarp : TTDriver<TTWarp<R>> {
   using Base = TTDriver<TTWarp<R>>;
   using Base::pend_bl; using Base::dist_bl; using Base::prox_bl; using Base::calls;
   static constexpr int S = 4, K = 4 * R, PM = 16 * R;
-  static constexpr int NBP = 8;    // pendant points per pass
+  static constexpr int PQS = PM + K;  // a pendant matrix set: P [R][4][4] then QN [R][4] (row sums, for 'N')
+  static constexpr int NBP = 6;    // pendant points per pass
   static constexpr int NBD = 4;    // distal points per pass
-  static constexpr int MEMO = 44;  // largest QNG rule extension
+  static constexpr int MEMO = 24;  // QNG's 21- and 22-point rule extensions (the 44-point one is batched in part)
+  static constexpr unsigned FULL = 0xffffffffu;
   // block-shared constants (doubles): statd[4] lam[4] x[16] xit[16] rates[R]
-  static constexpr int C_STATD = 0, C_LAM = 4, C_X = 8, C_XIT = 24, C_RATES = 40, C_TOTAL = 40 + R;
-  // per-warp shared layout (doubles)
-  static constexpr int OFF_EX = 0;                // [8][K] exp scratch
-  static constexpr int OFF_PQ = OFF_EX + 8 * K;   // current pendant P [R][4][4]
-  static constexpr int OFF_PD = OFF_PQ + PM;      // current distal P, then proximal P
-  static constexpr int OFF_PB = OFF_PD + 2 * PM;  // batch: pendant [NBP][PM] | distal [NBD][2][PM]
-  static constexpr int OFF_MX = OFF_PB + 8 * PM;  // memo: argument
-  static constexpr int OFF_MA = OFF_MX + MEMO;    //       proximal length (distal memo) or 0
-  static constexpr int OFF_MF = OFF_MA + MEMO;    //       log-likelihood
-  static constexpr int PER_WARP = OFF_MF + MEMO;
-  static_assert(NBD * 2 <= 8 && NBP <= 8, "batch matrices share one region");
+  static constexpr int C_STATD = 0, C_LAM = 4, C_X = 8, C_XIT = 24, C_RATES = 40, C_TOTAL = (40 + R + 1) & ~1;
+  // per-warp shared layout (doubles; every offset even so that double2 loads are 16-byte aligned)
+  static constexpr int OFF_EX = 0;                 // [8][K] exp scratch
+  static constexpr int OFF_BL = OFF_EX + 8 * K;    // [8] branch lengths handed to build_P
+  static constexpr int OFF_OUT = OFF_BL + 8;       // [8] pass results
+  static constexpr int OFF_BAD = OFF_OUT + 8;      // [8] non-finite log terms per point
+  static constexpr int OFF_PQ = OFF_BAD + 8;       // current pendant set (PQS)
+  static constexpr int OFF_PD = OFF_PQ + PQS;      // current distal P, then proximal P
+  static constexpr int OFF_PB = OFF_PD + 2 * PM;   // batch: pendant [NBP][PQS] | distal [NBD][2][PM]
+  static constexpr int PB_SIZE = NBP * PQS > NBD * 2 * PM ? NBP * PQS : NBD * 2 * PM;
+  static constexpr int OFF_MX = OFF_PB + PB_SIZE;  // memo: argument
+  static constexpr int OFF_MA = OFF_MX + MEMO;     //       proximal length (distal memo) or 0
+  static constexpr int OFF_MF = OFF_MA + MEMO;     //       log-likelihood
+  static constexpr int OFF_OBJ = OFF_MF + MEMO;     // the TTWarp object itself
+  static constexpr int OBJ_DOUBLES = 64;
+  static constexpr int PER_WARP = OFF_OBJ + OBJ_DOUBLES;
+  static_assert(NBD * 2 <= 8 && NBP <= 8, "scratch holds eight branch lengths");
+  static_assert((PQS % 2) == 0 && (PM % 2) == 0 && (MEMO % 2) == 0 && (K % 2) == 0, "keep double2 alignment");
 
-  const double *cst;  // block-shared constants
-  double *sw;         // this warp's shared region
-  int lane;
+  // The object itself lives in this warp's shared region (every member is warp-uniform; all lanes
+  // store identical values), so neither `this` nor the optimiser state ever touches local memory.
+  int sw_off;  // this warp's region, in doubles from the start of dynamic shared memory
   // candidate
   const double *dbase, *pbase;
   const int32_t *ebase_d, *ebase_p;
   const int32_t *qsite;
-  const uint8_t *qcode;
   double *w;
   int64_t Lp;
   int nq;
@@ -58,191 +94,279 @@ struct TTWarp : TTDriver<TTWarp<R>> {
   bool w_stale;
   int memo_n, memo_pending, memo_kind;  // memo_kind: -1 none, 0 pendant values, 1 distal values
 
-  static __host__ __device__ constexpr size_t smem_bytes(int warps) { return sizeof(double) * (size_t)(C_TOTAL + 1 + warps * PER_WARP); }
+  static __host__ __device__ constexpr size_t smem_bytes(int warps) { return sizeof(double) * (size_t)(C_TOTAL + warps * PER_WARP); }
+
+  // shared-memory views (rebuilt from the extern symbol so that the compiler emits LDS/STS)
+  __device__ __forceinline__ static const double *CST() { return reinterpret_cast<const double *>(ppb_ttw_smem); }
+  __device__ __forceinline__ double *SW() const { return reinterpret_cast<double *>(ppb_ttw_smem) + sw_off; }
+  __device__ __forceinline__ static int lane_id() { return threadIdx.x & 31; }
 
   __device__ __forceinline__ static double warp_sum(double v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
   }
 
-  // Diagd.multi_exp (diagd.ml:79-98; linear_c.c:92-146) for n branch lengths at once:
-  // dst + b*stride receives P(bls[b]); the lanes split the exponentials and the matrix entries.
-  template <int N>
-  __device__ __forceinline__ void build_P_n(double *dst, int stride, const double (&bls)[N]) {
-    double *ex = sw + OFF_EX;
+  // Diagd.multi_exp (diagd.ml:79-98; linear_c.c:92-146) for the n branch lengths in SW()[OFF_BL..]:
+  // dst + b*stride receives P(bl_b) and, when qn, the row sums ((P0+P1)+P2)+P3 used for the all-ones
+  // character 'N' (the evolved indicator vector of an ambiguity code is the sum of the selected
+  // columns in ascending state order: lv_of_nuc, nuc_models.ml:49-54 through gemmish_c, linear_c.c:29-90).
+  __device__ __noinline__ void build_P(int dst_off, int stride, int n, bool qn) {
+    double *s = SW();
+    const double *c = CST();
+    double *ex = s + OFF_EX, *dst = s + dst_off;
     __syncwarp();
-    for (int t = lane; t < N * K; t += 32) {
+    for (int t = lane_id(); t < n * K; t += 32) {
       const int b = t / K, kk = t - b * K;
-      double blv = bls[0];
-#pragma unroll
-      for (int bb = 1; bb < N; ++bb) blv = (b == bb) ? bls[bb] : blv;
-      ex[t] = exp(cst[C_RATES + (kk >> 2)] * blv * cst[C_LAM + (kk & 3)]);
+      ex[t] = exp(c[C_RATES + (kk >> 2)] * s[OFF_BL + b] * c[C_LAM + (kk & 3)]);
     }
     __syncwarp();
-    for (int t = lane; t < N * PM; t += 32) {
+    for (int t = lane_id(); t < n * PM; t += 32) {
       const int b = t / PM, e = t - b * PM;
       const int r = e >> 4, i = (e >> 2) & 3, j = e & 3;
       double acc = 0.0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) acc = fma(ex[b * K + r * 4 + k] * cst[C_X + i * 4 + k], cst[C_XIT + j * 4 + k], acc);
+      for (int k = 0; k < 4; ++k) acc = fma(ex[b * K + r * 4 + k] * c[C_X + i * 4 + k], c[C_XIT + j * 4 + k], acc);
       dst[b * stride + e] = acc;
     }
     __syncwarp();
+    if (qn) {
+      for (int t = lane_id(); t < n * K; t += 32) {
+        const int b = t / K, rs = t - b * K;
+        const double *row = dst + b * stride + rs * 4;
+        dst[b * stride + PM + rs] = (((0.0 + row[0]) + row[1]) + row[2]) + row[3];
+      }
+      __syncwarp();
+    }
   }
-  __device__ __noinline__ void build_P(double *dst, double bl) { const double b1[1] = {bl}; build_P_n<1>(dst, 0, b1); }
+  __device__ __forceinline__ void put_bl(int b, double v) { if (lane_id() == 0) SW()[OFF_BL + b] = v; }
 
   __device__ void memo_clear(int kind) { memo_n = 0; memo_pending = 0; memo_kind = kind; }
   __device__ void memo_put(double x, double aux, double f) {
     if (memo_n >= MEMO) return;
+    double *s = SW();
     __syncwarp();
-    if (lane == 0) { sw[OFF_MX + memo_n] = x; sw[OFF_MA + memo_n] = aux; sw[OFF_MF + memo_n] = f; }
+    if (lane_id() == 0) { s[OFF_MX + memo_n] = x; s[OFF_MA + memo_n] = aux; s[OFF_MF + memo_n] = f; }
     __syncwarp();
     ++memo_n;
   }
   __device__ bool memo_get(int kind, double x, double aux, double *f) const {
     if (memo_kind != kind) return false;
+    const double *s = SW();
     for (int i = 0; i < memo_n; ++i)
-      if (sw[OFF_MX + i] == x && sw[OFF_MA + i] == aux) { *f = sw[OFF_MF + i]; return true; }
+      if (s[OFF_MX + i] == x && s[OFF_MA + i] == aux) { *f = s[OFF_MF + i]; return true; }
     return false;
   }
 
   // Glv_edge.set_bl (glv_edge.ml:33-35) on the three edges: only the rate matrices change here
   __device__ void set_pend(double bl) {
     pend_bl = bl;
-    build_P(sw + OFF_PQ, bl);
+    __syncwarp();
+    put_bl(0, bl);
+    build_P(OFF_PQ, PQS, 1, true);
     if (memo_kind == 1) memo_kind = -1;  // distal values were computed for another pendant length
   }
   __device__ void set_dist_prox(double d, double p) {
     dist_bl = d; prox_bl = p;
-    const double b2[2] = {d, p};
-    build_P_n<2>(sw + OFF_PD, PM, b2);
+    __syncwarp();
+    put_bl(0, d); put_bl(1, p);
+    build_P(OFF_PD, PM, 2, false);
     w_stale = true;
     if (memo_kind == 0) memo_kind = -1;
   }
 
-  // evolved pendant GLV entry for state row rs = r*4+s of matrix set Pq: sum of the columns of
-  // P_r(pendant) selected by the query character (lv_of_nuc, nuc_models.ml:49-54; core.ml:137-141)
-  __device__ __forceinline__ static double q_entry(const double *Pq, int rs, int col, uint32_t mask, bool single) {
-    const double *row = Pq + rs * 4;
-    if (single) return row[col];
+  // Per-row (32 sites) query-character decode, uniform across the warp.  The evolved pendant GLV
+  // entry for state row rs is P[rs][col] for a plain base, QN[rs] for 'N' (fast: one shared load at
+  // set[rs*qmul + qadd]); any other ambiguity code in the row sends the whole row down the slow path
+  // (sum of the selected columns in ascending order - exact for plain bases too, since 0 + x = x).
+  struct RowCodes {
+    uint32_t mask;
+    int qmul, qadd;
+    bool fast;
+  };
+  __device__ __forceinline__ static RowCodes decode(int packed) {
+    RowCodes c;
+    c.mask = ((uint32_t)packed >> kSiteCodeShift) & 0x7f;
+    const bool single = (c.mask & (c.mask - 1)) == 0;
+    c.qmul = single ? 4 : 1;
+    c.qadd = single ? __ffs(c.mask) - 1 : PM;
+    c.fast = __all_sync(FULL, single || c.mask == 15u);
+    return c;
+  }
+  __device__ __forceinline__ static double q_slow(const double *set, int rs, uint32_t mask) {
+    const double *row = set + rs * 4;
     double acc = 0.0;
-    while (mask) { const int j = __ffs(mask) - 1; mask &= mask - 1; acc += row[j]; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc = ((mask >> j) & 1u) ? acc + row[j] : acc;
     return acc;
   }
 
-  __device__ __forceinline__ double finish(const LogProd &lp) const { return warp_sum(lp.value()) - rate_term + e_tot_ln2; }
+  // natural log of the accumulated product, summed over the warp, plus the constant terms
+  __device__ __noinline__ double finish(double m, int e, int b) {
+    const double v = warp_sum(log(m) + (double)e * kLn2);
+    return (v + SW()[OFF_BAD + b]) - rate_term + e_tot_ln2;
+  }
 
-  // Three_tax.log_like at NB (distal, proximal) pairs with the current pendant matrices: Pm holds
-  // NB x {P(distal), P(proximal)}.  One pass over darr/parr planes at the query's sites.
+  // de = P_d d, pe = P_p p, ww[s] = (statd_s * pe_s) * de_s   (log_like3's ((statd*x)*y), x = prox,
+  // y = dist: three_tax.ml:31-36, linear_c.c:367-424) for one rate category
+  __device__ __forceinline__ static void site_w(const double *Pd, const double *Pp, const double (&d)[4], const double (&p)[4],
+                                                const double *st, double (&ww)[4]) {
+    const double2 *Pd2 = reinterpret_cast<const double2 *>(Pd), *Pp2 = reinterpret_cast<const double2 *>(Pp);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const double2 a0 = Pd2[s * 2], a1 = Pd2[s * 2 + 1], b0 = Pp2[s * 2], b1 = Pp2[s * 2 + 1];
+      double de = fma(a0.x, d[0], 0.0), pe = fma(b0.x, p[0], 0.0);
+      de = fma(a0.y, d[1], de); pe = fma(b0.y, p[1], pe);
+      de = fma(a1.x, d[2], de); pe = fma(b1.x, p[2], pe);
+      de = fma(a1.y, d[3], de); pe = fma(b1.y, p[3], pe);
+      ww[s] = (st[s] * pe) * de;
+    }
+  }
+
+  __device__ __forceinline__ void pass_begin() {
+    double *s = SW();
+    __syncwarp();
+    if (lane_id() < 8) s[OFF_BAD + lane_id()] = 0.0;
+    __syncwarp();
+  }
+
+  // Three_tax.log_like at NB (distal, proximal) pairs with the current pendant matrices: the set at
+  // pm_off holds NB x {P(distal), P(proximal)}.  One pass over darr/parr planes at the query's sites;
+  // results go to SW()[OFF_OUT + b].
   template <int NB>
-  __device__ __forceinline__ void pass_dist(const double *Pm, double (&out)[NB]) {
-    LogProd lp[NB];
+  __device__ __forceinline__ void pass_dist(int pm_off) {
+    pass_begin();
+    double *s = SW();
+    const double *Pm = s + pm_off, *Pq = s + OFF_PQ, *st = CST() + C_STATD;
+    WarpProd lp[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) lp[b].init();
-    const double *Pq = sw + OFF_PQ;
-    const double st0 = cst[C_STATD], st1 = cst[C_STATD + 1], st2 = cst[C_STATD + 2], st3 = cst[C_STATD + 3];
-    for (int i = lane; i < nq; i += 32) {
-      const int site = qsite[i];
-      const uint32_t mask = qcode[site] & 0x7f;
-      const bool single = (mask & (mask - 1)) == 0;
-      const int col = __ffs(mask) - 1;
+    int packed_next = qsite[min(lane_id(), nq - 1)];
+    for (int base = 0; base < nq; base += 32) {
+      const int i = base + lane_id();
+      const bool act = i < nq;
+      const int packed = packed_next;
+      packed_next = qsite[min(i + 32, nq - 1)];  // next row's sites are in flight while this row computes
+      const int site = packed & kSiteMask;
+      const RowCodes c = decode(packed);
+      const double *dp = dbase + site, *pp = pbase + site;
       double u[NB];
 #pragma unroll
       for (int b = 0; b < NB; ++b) u[b] = 0.0;
-#pragma unroll
+#pragma unroll(NB == 1 ? R : 1)
       for (int r = 0; r < R; ++r) {
         double d[4], p[4], q[4];
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          d[s] = __ldg(dbase + (int64_t)(r * 4 + s) * Lp + site);
-          p[s] = __ldg(pbase + (int64_t)(r * 4 + s) * Lp + site);
-          q[s] = q_entry(Pq, r * 4 + s, col, mask, single);
+        for (int k = 0; k < 4; ++k) {
+          d[k] = __ldg(dp + (int64_t)(r * 4 + k) * Lp);
+          p[k] = __ldg(pp + (int64_t)(r * 4 + k) * Lp);
+        }
+        if (c.fast) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) q[k] = Pq[(r * 4 + k) * c.qmul + c.qadd];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) q[k] = q_slow(Pq, r * 4 + k, c.mask);
         }
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-          const double *Pd = Pm + b * 2 * PM + r * 16, *Pp = Pd + PM;
+          double ww[4];
+          site_w(Pm + b * 2 * PM + r * 16, Pm + b * 2 * PM + PM + r * 16, d, p, st, ww);
 #pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            double de = 0.0, pe = 0.0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { de = fma(Pd[s * 4 + j], d[j], de); pe = fma(Pp[s * 4 + j], p[j], pe); }
-            const double st = s == 0 ? st0 : s == 1 ? st1 : s == 2 ? st2 : st3;
-            const double ww = (st * pe) * de;  // ((statd*x)*y), x = prox, y = dist (three_tax.ml:31-36)
-            u[b] = fma(ww, q[s], u[b]);
-          }
+          for (int k = 0; k < 4; ++k) u[b] = fma(ww[k], q[k], u[b]);
         }
       }
+      if (act) {
 #pragma unroll
-      for (int b = 0; b < NB; ++b) lp[b].mul(u[b]);
+        for (int b = 0; b < NB; ++b) lp[b].mul(u[b], s + OFF_BAD + b);
+      }
     }
+    __syncwarp();
 #pragma unroll
-    for (int b = 0; b < NB; ++b) out[b] = finish(lp[b]);
+    for (int b = 0; b < NB; ++b) {
+      const double v = finish(lp[b].m, lp[b].e, b);
+      if (lane_id() == 0) s[OFF_OUT + b] = v;
+    }
+    __syncwarp();
   }
 
-  // log_like at NB pendant lengths (matrices Pqm[b]) with the current distal / proximal matrices.
-  // FUSED: recompute w from darr/parr and store it; otherwise read the cached w.
+  // log_like at NB pendant lengths (sets at pq_off + b*PQS) with the current distal / proximal
+  // matrices.  FUSED: recompute w from darr/parr and store it; otherwise read the cached w.  w is
+  // streamed (evict-first) so that it does not push the shared darr/parr planes out of L2.
   template <int NB, bool FUSED>
-  __device__ __forceinline__ void pass_pend(const double *Pqm, double (&out)[NB]) {
-    LogProd lp[NB];
+  __device__ __forceinline__ void pass_pend(int pq_off) {
+    pass_begin();
+    double *s = SW();
+    const double *Pqm = s + pq_off, *Pd0 = s + OFF_PD, *st = CST() + C_STATD;
+    WarpProd lp[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) lp[b].init();
-    const double *Pd0 = sw + OFF_PD;
-    const double st0 = cst[C_STATD], st1 = cst[C_STATD + 1], st2 = cst[C_STATD + 2], st3 = cst[C_STATD + 3];
-    for (int i = lane; i < nq; i += 32) {
-      const int site = qsite[i];
-      const uint32_t mask = qcode[site] & 0x7f;
-      const bool single = (mask & (mask - 1)) == 0;
-      const int col = __ffs(mask) - 1;
+    int packed_next = qsite[min(lane_id(), nq - 1)];
+    for (int base = 0; base < nq; base += 32) {
+      const int i = base + lane_id();
+      const bool act = i < nq;
+      const int ic = act ? i : nq - 1;
+      const int packed = packed_next;
+      packed_next = qsite[min(i + 32, nq - 1)];
+      const int site = packed & kSiteMask;
+      const RowCodes c = decode(packed);
+      const double *dp = dbase + site, *pp = pbase + site;
+      double *wp = w + ic;
       double u[NB];
 #pragma unroll
       for (int b = 0; b < NB; ++b) u[b] = 0.0;
-#pragma unroll
+#pragma unroll(NB == 1 ? R : 1)
       for (int r = 0; r < R; ++r) {
         double ww[4];
         if (FUSED) {
           double d[4], p[4];
 #pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            d[s] = __ldg(dbase + (int64_t)(r * 4 + s) * Lp + site);
-            p[s] = __ldg(pbase + (int64_t)(r * 4 + s) * Lp + site);
+          for (int k = 0; k < 4; ++k) {
+            d[k] = __ldg(dp + (int64_t)(r * 4 + k) * Lp);
+            p[k] = __ldg(pp + (int64_t)(r * 4 + k) * Lp);
           }
-          const double *Pd = Pd0 + r * 16, *Pp = Pd + PM;
+          site_w(Pd0 + r * 16, Pd0 + PM + r * 16, d, p, st, ww);
+          if (act) {
 #pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            double de = 0.0, pe = 0.0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { de = fma(Pd[s * 4 + j], d[j], de); pe = fma(Pp[s * 4 + j], p[j], pe); }
-            const double st = s == 0 ? st0 : s == 1 ? st1 : s == 2 ? st2 : st3;
-            ww[s] = (st * pe) * de;
-            w[(int64_t)(r * 4 + s) * Lp + i] = ww[s];
+            for (int k = 0; k < 4; ++k) __stcs(wp + (int64_t)(r * 4 + k) * Lp, ww[k]);
           }
         } else {
 #pragma unroll
-          for (int s = 0; s < 4; ++s) ww[s] = w[(int64_t)(r * 4 + s) * Lp + i];
+          for (int k = 0; k < 4; ++k) ww[k] = __ldcs(wp + (int64_t)(r * 4 + k) * Lp);
         }
+        if (c.fast) {
 #pragma unroll
-        for (int b = 0; b < NB; ++b)
+          for (int b = 0; b < NB; ++b)
 #pragma unroll
-          for (int s = 0; s < 4; ++s) u[b] = fma(ww[s], q_entry(Pqm + b * PM, r * 4 + s, col, mask, single), u[b]);
+            for (int k = 0; k < 4; ++k) u[b] = fma(ww[k], Pqm[b * PQS + (r * 4 + k) * c.qmul + c.qadd], u[b]);
+        } else {
+#pragma unroll
+          for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) u[b] = fma(ww[k], q_slow(Pqm + b * PQS, r * 4 + k, c.mask), u[b]);
+        }
       }
+      if (act) {
 #pragma unroll
-      for (int b = 0; b < NB; ++b) lp[b].mul(u[b]);
+        for (int b = 0; b < NB; ++b) lp[b].mul(u[b], s + OFF_BAD + b);
+      }
     }
+    __syncwarp();
 #pragma unroll
-    for (int b = 0; b < NB; ++b) out[b] = finish(lp[b]);
+    for (int b = 0; b < NB; ++b) {
+      const double v = finish(lp[b].m, lp[b].e, b);
+      if (lane_id() == 0) s[OFF_OUT + b] = v;
+    }
+    __syncwarp();
   }
 
-  __device__ __noinline__ double pend_single_cached() { double o[1]; pass_pend<1, false>(sw + OFF_PQ, o); return o[0]; }
-  __device__ __noinline__ double pend_single_fused() { double o[1]; pass_pend<1, true>(sw + OFF_PQ, o); w_stale = false; return o[0]; }
-  __device__ __noinline__ double dist_single() { double o[1]; pass_dist<1>(sw + OFF_PD, o); return o[0]; }
-  __device__ __noinline__ void pend_batch4(double (&o)[4]) {
-    if (w_stale) { pass_pend<4, true>(sw + OFF_PB, o); w_stale = false; } else pass_pend<4, false>(sw + OFF_PB, o);
-  }
-  __device__ __noinline__ void pend_batch8(double (&o)[8]) {
-    if (w_stale) { pass_pend<8, true>(sw + OFF_PB, o); w_stale = false; } else pass_pend<8, false>(sw + OFF_PB, o);
-  }
-  __device__ __noinline__ void dist_batch4(double (&o)[4]) { pass_dist<4>(sw + OFF_PB, o); }
+  __device__ __noinline__ double pend_single_cached() { pass_pend<1, false>(OFF_PQ); return SW()[OFF_OUT]; }
+  __device__ __noinline__ double pend_single_fused() { pass_pend<1, true>(OFF_PQ); w_stale = false; return SW()[OFF_OUT]; }
+  __device__ __noinline__ double dist_single() { pass_dist<1>(OFF_PD); return SW()[OFF_OUT]; }
+  __device__ __noinline__ void pend_batch_cached() { pass_pend<NBP, false>(OFF_PB); }
+  __device__ __noinline__ void pend_batch_fused() { pass_pend<NBP, true>(OFF_PB); w_stale = false; }
+  __device__ void pend_batch() { if (w_stale) pend_batch_fused(); else pend_batch_cached(); }
+  __device__ __noinline__ void dist_batch() { pass_dist<NBD>(OFF_PB); }
 
   // ---- TTDriver engine interface ----
   __device__ double f_pend(double v) {
@@ -261,12 +385,17 @@ struct TTWarp : TTDriver<TTWarp<R>> {
   __device__ double eval_full_cache() { return w_stale ? pend_single_fused() : pend_single_cached(); }
   __device__ double eval_full_plain() { return dist_single(); }
 
-  __device__ __noinline__ void hint_brent(int kind, double left, double right, double start, double v) {
+  // Brent's first calls are known in advance: f(left), f(right), f(start), GSL's repeats of the same
+  // three, f(lower + golden*(upper - lower)) and - for the pendant objective - the first golden-section
+  // step from (z = start, d = e = 0).  hint_prepare builds their matrices and memo keys, the caller
+  // runs ONE batched pass (run_batch), hint_commit stores the values.
+  __device__ void hint_prepare(int kind, double left, double right, double start, double v) {
+    double *s = SW();
     if (kind == OBJ_DIST) {
-      // replay the drift of cut = dist + prox over the seven calls (set_dist_bl, three_tax.ml:41-45)
+      // replay the drift of cut = dist + prox over the seven calls (set_dist_bl, three_tax.ml:41-45);
+      // a point whose proximal length would be negative keeps a negative key and never matches
       memo_clear(1);
       const double xs[7] = {left, right, start, left, right, start, v};
-      const int first[4] = {0, 1, 2, 6};
       double cut = dist_bl + prox_bl, px[7];
 #pragma unroll
       for (int i = 0; i < 7; ++i) {
@@ -274,60 +403,291 @@ struct TTWarp : TTDriver<TTWarp<R>> {
         px[i] = prox;
         if (prox >= 0.0) cut = xs[i] + prox;
       }
-      double bls[8], o[4];
+      const double bx[4] = {xs[0], xs[1], xs[2], xs[6]}, bp[4] = {px[0], px[1], px[2], px[6]};
+      __syncwarp();
+      if (lane_id() == 0) {
 #pragma unroll
-      for (int b = 0; b < 4; ++b) { bls[2 * b] = xs[first[b]]; bls[2 * b + 1] = px[first[b]]; }
-      build_P_n<8>(sw + OFF_PB, PM, bls);
-      dist_batch4(o);
-#pragma unroll
-      for (int b = 0; b < 4; ++b)
-        if (px[first[b]] >= 0.0) memo_put(xs[first[b]], px[first[b]], o[b]);
+        for (int b = 0; b < 4; ++b) { s[OFF_BL + 2 * b] = bx[b]; s[OFF_BL + 2 * b + 1] = bp[b]; s[OFF_MX + b] = bx[b]; s[OFF_MA + b] = bp[b]; }
+      }
+      memo_pending = 4;
+      build_P(OFF_PB, PM, 8, false);
     } else {
       memo_clear(0);
-      const double bls[4] = {left, right, start, v};
-      double o[4];
-      build_P_n<4>(sw + OFF_PB, PM, bls);
-      pend_batch4(o);
+      const double mid = 0.5 * (left + right);
+      const double ee = (start < mid) ? right - start : -(start - left);
+      const double u1 = start + 0.3819660 * ee;
+      const double bls[5] = {left, right, start, v, u1};
+      __syncwarp();
+      if (lane_id() == 0) {
 #pragma unroll
-      for (int b = 0; b < 4; ++b) memo_put(bls[b], 0.0, o[b]);
+        for (int b = 0; b < NBP; ++b) { s[OFF_BL + b] = bls[b < 5 ? b : 4]; if (b < 5) { s[OFF_MX + b] = bls[b]; s[OFF_MA + b] = 0.0; } }
+      }
+      memo_pending = 5;
+      build_P(OFF_PB, PQS, NBP, true);
     }
+  }
+  __device__ void hint_commit() {
+    double *s = SW();
+    __syncwarp();
+    if (lane_id() < memo_pending) s[OFF_MF + lane_id()] = s[OFF_OUT + lane_id()];
+    __syncwarp();
+    memo_n = memo_pending;
+    memo_pending = 0;
+  }
+  __device__ void hint_brent(int kind, double left, double right, double start, double v) {  // TTDriver path (--pp)
+    hint_prepare(kind, left, right, start, v);
+    if (kind == OBJ_DIST) dist_batch(); else pend_batch();
+    hint_commit();
   }
   __device__ void hint_begin() { memo_clear(0); }
   __device__ void hint_add(double x) {
     const int at = memo_n + memo_pending;
     if (at >= MEMO) return;
+    double *s = SW();
     __syncwarp();
-    if (lane == 0) { sw[OFF_MX + at] = x; sw[OFF_MA + at] = 0.0; }
+    if (lane_id() == 0) { s[OFF_MX + at] = x; s[OFF_MA + at] = 0.0; }
     __syncwarp();
     ++memo_pending;
   }
   __device__ __noinline__ void hint_flush() {
+    double *s = SW();
     while (memo_pending > 0) {
       const int n = memo_pending < NBP ? memo_pending : NBP;
-      double bls[NBP], o[NBP];
-#pragma unroll
-      for (int b = 0; b < NBP; ++b) bls[b] = sw[OFF_MX + memo_n + (b < n ? b : n - 1)];
-      build_P_n<NBP>(sw + OFF_PB, PM, bls);
-      pend_batch8(o);
       __syncwarp();
-#pragma unroll
-      for (int b = 0; b < NBP; ++b)
-        if (b < n && lane == 0) sw[OFF_MF + memo_n + b] = o[b];
+      if (lane_id() < NBP) s[OFF_BL + lane_id()] = s[OFF_MX + memo_n + (lane_id() < n ? lane_id() : n - 1)];
+      build_P(OFF_PB, PQS, NBP, true);
+      pend_batch();
+      if (lane_id() < n) s[OFF_MF + memo_n + lane_id()] = s[OFF_OUT + lane_id()];
       __syncwarp();
       memo_n += n;
       memo_pending -= n;
     }
   }
 
+
+  // ---------------------------------------------------------------------------------------------
+  // Three_tax.optimize as a RESUMABLE state machine: the same statements as TTDriver::brent /
+  // ::optimize (threetax.cuh; minimization.ml:83-101, three_tax.ml:70-83, GSL min/brent.c), cut at
+  // every objective call, so that the kernel has ONE evaluation site and the optimiser's variables
+  // sit in this (shared-memory) object instead of being spilled around nine call sites.
+  //   opt_advance(0, -)  starts;  opt_advance(1, f) feeds the value of the requested call.
+  //   returns 1: evaluate objective(b_kind, req_x) next;  0: finished, status in o_status.
+  // ---------------------------------------------------------------------------------------------
+  enum : int { B_LEFT, B_RIGHT, B_START, B_LOWER, B_UPPER, B_MIN, B_V, B_ITER };
+  enum : int { O_PEND, O_DIST };
+  double b_left, b_right, b_tol, b_lefty, b_righty, b_smaller, b_miny, b_prev;
+  double b_xmin, b_xlo, b_xup, b_flo, b_fup, b_fmin, b_v, b_w, b_d, b_e, b_fv, b_fw, b_out, req_x;
+  int b_ph, b_kind, b_iter, b_step, b_max, b_status;
+  double o_prev_pend, o_prev_dist, o_curr_pend, o_curr_dist, o_tol, o_max_pend;
+  int o_ph, o_step, o_max_iter, o_status;
+
+  __device__ int brent_begin(int kind, double raw_start, double left, double right, double tolerance, int max_iters) {
+    b_kind = kind; b_left = left; b_right = right; b_tol = tolerance; b_max = max_iters;
+    if (left >= raw_start || raw_start >= right) { b_status = ST_INVALID_START; return 0; }
+    hint_prepare(kind, left, right, raw_start, left + 0.3819660 * (right - left));
+    b_prev = raw_start;
+    return 2;  // run the batched pass, then opt_advance(2, -)
+  }
+  __device__ int brent_done(int st) { b_status = st; return 0; }
+  __device__ int brent_feed(double fv) {
+    const double golden = 0.3819660;
+    switch (b_ph) {
+      case B_LEFT: b_lefty = fv; b_ph = B_RIGHT; req_x = b_right; return 1;
+      case B_RIGHT: {
+        b_righty = fv;
+        b_smaller = (b_lefty < b_righty) ? b_left : b_right;
+        double miny = fmin(b_lefty, b_righty);
+        if (b_lefty != b_lefty || b_righty != b_righty) miny = __longlong_as_double(0x7ff8000000000000LL);
+        b_miny = miny; b_iter = 1; b_ph = B_START; req_x = b_prev;
+        return 1;
+      }
+      case B_START: {
+        if (fv < b_miny) { b_xmin = b_prev; b_xlo = b_left; b_xup = b_right; b_ph = B_LOWER; req_x = b_xlo; return 1; }
+        if (fabs(b_prev - b_smaller) < b_tol) { b_out = b_smaller; return brent_done(ST_OK); }  // FoundMin
+        if (b_iter > b_max) return brent_done(ST_FIND_START_FAILURE);
+        b_prev = (b_prev + b_smaller) / 2.0; ++b_iter; req_x = b_prev;
+        return 1;
+      }
+      case B_LOWER: b_flo = fv; if (!isfinite(fv)) return brent_done(ST_GSL_EBADFUNC); b_ph = B_UPPER; req_x = b_xup; return 1;
+      case B_UPPER: b_fup = fv; if (!isfinite(fv)) return brent_done(ST_GSL_EBADFUNC); b_ph = B_MIN; req_x = b_xmin; return 1;
+      case B_MIN: {
+        b_fmin = fv;
+        if (!isfinite(fv)) return brent_done(ST_GSL_EBADFUNC);
+        if (b_xlo > b_xup) return brent_done(ST_GSL_EINVAL);
+        if (b_xmin >= b_xup || b_xmin <= b_xlo) return brent_done(ST_GSL_EINVAL);
+        if (b_fmin >= b_flo || b_fmin >= b_fup) return brent_done(ST_GSL_EINVAL);
+        b_v = b_xlo + golden * (b_xup - b_xlo); b_w = b_v; b_d = 0.0; b_e = 0.0;
+        b_ph = B_V; req_x = b_v;
+        return 1;
+      }
+      case B_V: {
+        if (!isfinite(fv)) return brent_done(ST_GSL_EBADFUNC);
+        b_fv = fv; b_fw = fv; b_step = 1;
+        break;
+      }
+      default: {  // B_ITER: the value at u
+        const double u = req_x, f_u = fv, z = b_xmin, f_z = b_fmin;
+        if (!isfinite(f_u)) return brent_done(ST_GSL_EBADFUNC);
+        if (f_u <= f_z) {
+          if (u < z) { b_xup = z; b_fup = f_z; } else { b_xlo = z; b_flo = f_z; }
+          b_v = b_w; b_fv = b_fw; b_w = z; b_fw = f_z; b_xmin = u; b_fmin = f_u;
+        } else {
+          if (u < z) { b_xlo = u; b_flo = f_u; } else { b_xup = u; b_fup = f_u; }
+          if (f_u <= b_fw || b_w == z) { b_v = b_w; b_fv = b_fw; b_w = u; b_fw = f_u; }
+          else if (f_u <= b_fv || b_v == z || b_v == b_w) { b_v = u; b_fv = f_u; }
+        }
+        if (b_xup - b_xlo < b_tol) { b_out = b_xmin; return brent_done(ST_OK); }
+        ++b_step;
+      }
+    }
+    // next iterate (GSL brent_iterate up to the function evaluation)
+    if (b_step > b_max) return brent_done(ST_EXCEEDED_MAX_ITER);
+    {
+      const double x_left = b_xlo, x_right = b_xup, z = b_xmin, f_z = b_fmin, v = b_v, wv = b_w, f_v = b_fv, f_w = b_fw;
+      double dd = b_e, ee = b_d;  // GSL: d = state->e; e = state->d
+      double u;
+      const double w_lower = z - x_left, w_upper = x_right - z;
+      const double tol = kSqrtDblEps * fabs(z);
+      double p = 0.0, q = 0.0, r = 0.0;
+      const double midpoint = 0.5 * (x_left + x_right);
+      if (fabs(ee) > tol) {
+        r = (z - wv) * (f_z - f_v);
+        q = (z - v) * (f_z - f_w);
+        p = (z - v) * q - (z - wv) * r;
+        q = 2.0 * (q - r);
+        if (q > 0.0) p = -p; else q = -q;
+        r = ee;
+        ee = dd;
+      }
+      if (fabs(p) < fabs(0.5 * q * r) && p < q * w_lower && p < q * w_upper) {
+        const double t2 = 2.0 * tol;
+        dd = p / q;
+        u = z + dd;
+        if ((u - x_left) < t2 || (x_right - u) < t2) dd = (z < midpoint) ? tol : -tol;
+      } else {
+        ee = (z < midpoint) ? x_right - z : -(z - x_left);
+        dd = golden * ee;
+      }
+      if (fabs(dd) >= tol) u = z + dd; else u = z + ((dd > 0.0) ? tol : -tol);
+      b_e = ee;
+      b_d = dd;
+      b_ph = B_ITER; req_x = u;
+    }
+    return 1;
+  }
+
+  __device__ void opt_init(double tolerance, double max_pend, int max_iter) {
+    o_tol = tolerance; o_max_pend = max_pend; o_max_iter = max_iter;
+    o_prev_pend = pend_bl; o_prev_dist = dist_bl; o_step = 1;
+  }
+  __device__ __forceinline__ int opt_advance(int feed, double fv) {
+    if (feed == 1) {
+      if (brent_feed(fv)) return 1;
+      goto after_brent;
+    }
+    if (feed == 2) { hint_commit(); b_ph = B_LEFT; req_x = b_left; return 1; }
+  round:
+    if (o_step > o_max_iter) { o_status = ST_EXCEEDED_MAX_ITER; return 0; }
+    o_curr_pend = pend_bl; o_curr_dist = dist_bl;
+    if (1e-8 != o_max_pend) {
+      o_ph = O_PEND;
+      if (brent_begin(OBJ_PEND, pend_bl, 1e-8, o_max_pend, o_tol, 100)) return 2;
+      goto after_brent;
+    }
+  start_dist:
+    {
+      const double cut = dist_bl + prox_bl;
+      if (0.0 != cut) {
+        o_ph = O_DIST;
+        if (brent_begin(OBJ_DIST, dist_bl, 0.0, cut, o_tol, 100)) return 2;
+        goto after_brent;
+      }
+    }
+    goto check;
+  after_brent:
+    if (b_status != ST_OK) { o_status = b_status; return 0; }
+    if (o_ph == O_PEND) { o_curr_pend = b_out; goto start_dist; }
+    o_curr_dist = b_out;
+  check:
+    if (fabs(o_prev_pend - o_curr_pend) > o_tol || fabs(o_prev_dist - o_curr_dist) > o_tol) {
+      o_prev_pend = o_curr_pend;
+      o_prev_dist = o_curr_dist;
+      ++o_step;
+      goto round;
+    }
+    o_status = ST_OK;
+    return 0;
+  }
+  // One (query, edge) candidate in TT_MODE_OPTIMIZE / TT_MODE_LOGLIKE: Three_tax.optimize through the
+  // state machine, the retry from the default branch lengths after a GSL error (core.ml:254-279,
+  // tt_edges_default :240-245), then Three_tax.get_results (three_tax.ml:85).  Every likelihood pass
+  // is inlined exactly once, here.
+  enum : int { OBJ_FINAL = 3 };
+  __device__ __forceinline__ int run_candidate(bool optimise, double cut_bl, const TTParams &prm, double *ll_out) {
+    int st = ST_OK, feed = 0, attempt = 0;
+    double f = 0.0;
+    if (optimise) opt_init(prm.tol, prm.max_pend, prm.max_iter);
+    for (;;) {
+      const int more = optimise ? opt_advance(feed, f) : 0;
+      if (more == 2) {  // Brent's predictable calls, several per pass
+        if (memo_kind == 1) pass_dist<NBD>(OFF_PB);
+        else if (w_stale) { pass_pend<NBP, true>(OFF_PB); w_stale = false; }
+        else pass_pend<NBP, false>(OFF_PB);
+        feed = 2;
+        continue;
+      }
+      int kind = OBJ_FINAL;
+      if (more == 1) kind = b_kind;
+      else if (optimise) {
+        st = o_status;
+        if (st_is_gsl(st) && attempt == 0) {
+          attempt = 1;
+          set_tt_edges(cut_bl, prm.start_pend, cut_bl / 2.0);
+          opt_init(prm.tol, prm.max_pend, prm.max_iter);
+          feed = 0;
+          continue;
+        }
+        if (st == ST_EXCEEDED_MAX_ITER) st = ST_OK;
+      }
+      // ---- the evaluation site: TTDriver::objective with f_pend / f_dist inlined ----
+      const double x = req_x;
+      double val = 0.0;
+      bool have = false, nan_out = false;
+      if (kind == OBJ_PEND) {
+        calls++;
+        set_pend(x);
+        have = memo_get(0, x, 0.0, &val);
+        if (!have) {
+          if (w_stale) { pass_pend<1, true>(OFF_PQ); w_stale = false; } else pass_pend<1, false>(OFF_PQ);
+        }
+      } else {
+        if (kind == OBJ_DIST) {
+          calls++;
+          const double prox = (dist_bl + prox_bl) - x;
+          if (!(prox >= 0.0)) nan_out = true;
+          else {
+            have = memo_get(1, x, prox, &val);
+            set_dist_prox(x, prox);
+          }
+        }
+        if (!have && !nan_out) pass_dist<1>(OFF_PD);
+      }
+      if (!have) val = SW()[OFF_OUT];
+      if (more == 0) { *ll_out = val; return st; }
+      f = nan_out ? __longlong_as_double(0x7ff8000000000000LL) : -val;
+      feed = 1;
+    }
+  }
+
   // core.ml:225-239 set_tt_edges (no gather): fix the candidate and its three branch lengths
-  __device__ void set_tt_edges(double cut_bl, double pendant, double distal) {
+  __device__ __noinline__ void set_tt_edges(double cut_bl, double pendant, double distal) {
     long long es = 0;
-    for (int i = lane; i < nq; i += 32) {
-      const int site = qsite[i];
+    for (int i = lane_id(); i < nq; i += 32) {
+      const int site = qsite[i] & kSiteMask;
       es += (long long)ebase_d[site] + (long long)ebase_p[site];
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(0xffffffffu, es, o);
+    for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(FULL, es, o);
     e_tot_ln2 = kLn2 * (double)es;  // gstar_support.ml:43-49
     rate_term = (double)((float)nq) * log((double)((float)R));  // linear_c.c:421
     memo_clear(-1);
@@ -344,27 +704,25 @@ tt_warp_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__rest
                const int32_t *__restrict__ order, CandOut *__restrict__ out, int n, TTParams prm, double *__restrict__ wbuf,
                int *counter) {
   using TT = TTWarp<R>;
-  extern __shared__ double sm[];
+  double *sm = reinterpret_cast<double *>(ppb_ttw_smem);
   for (int i = threadIdx.x; i < 4; i += blockDim.x) { sm[TT::C_STATD + i] = m->statd[i]; sm[TT::C_LAM + i] = m->lam[i]; }
   for (int i = threadIdx.x; i < 16; i += blockDim.x) { sm[TT::C_X + i] = m->x[i]; sm[TT::C_XIT + i] = m->xit[i]; }
   for (int i = threadIdx.x; i < R; i += blockDim.x) sm[TT::C_RATES + i] = m->rates[i];
   __syncthreads();
-  const int warp = threadIdx.x >> 5;
-  TT tt;
-  tt.cst = sm;
-  tt.sw = sm + ((TT::C_TOTAL + 1) & ~1) + warp * TT::PER_WARP;
-  tt.lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  static_assert(sizeof(TT) <= TT::OBJ_DOUBLES * sizeof(double), "TTWarp object does not fit its shared slot");
+  TT &tt = *reinterpret_cast<TT *>(sm + TT::C_TOTAL + warp * TT::PER_WARP + TT::OFF_OBJ);
+  tt.sw_off = TT::C_TOTAL + warp * TT::PER_WARP;
   tt.Lp = g.Lp;
   tt.w = wbuf + (int64_t)(blockIdx.x * WARPS + warp) * TT::K * g.Lp;
   for (;;) {
     int idx = 0;
-    if (tt.lane == 0) idx = atomicAdd(counter, 1);
+    if (lane == 0) idx = atomicAdd(counter, 1);
     idx = __shfl_sync(0xffffffffu, idx, 0);
     if (idx >= n) break;
     const int ci = order ? order[idx] : idx;
     const CandIn c = in[ci];
     tt.qsite = qsite + (int64_t)c.q * g.Lp;
-    tt.qcode = codes + (int64_t)c.q * g.Lp;
     tt.nq = nq[c.q];
     tt.dbase = g.a[0] + (int64_t)c.loc * g.a_stride;
     tt.pbase = g.a[1] + (int64_t)c.loc * g.a_stride;
@@ -378,18 +736,10 @@ tt_warp_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__rest
     const double d0 = prm.use_defaults ? cut_bl / 2.0 : c.dist0;
     tt.set_tt_edges(cut_bl, p0, d0);
     int st = ST_OK;
-    if (prm.mode == TT_MODE_OPTIMIZE) {
-      // core.ml:254-279: ExceededMaxIter keeps the current state; a GSL error retries once from the
-      // default branch lengths (tt_edges_default, core.ml:240-245).
-      st = tt.optimize(prm.tol, prm.max_pend, prm.max_iter);
-      if (st_is_gsl(st)) {
-        tt.set_tt_edges(cut_bl, prm.start_pend, cut_bl / 2.0);
-        st = tt.optimize(prm.tol, prm.max_pend, prm.max_iter);
-      }
-      if (st == ST_EXCEEDED_MAX_ITER) st = ST_OK;
-      o.ll = tt.eval_full_plain();  // Three_tax.get_results (three_tax.ml:85)
-    } else if (prm.mode == TT_MODE_LOGLIKE) {
-      o.ll = tt.eval_full_plain();
+    if (prm.mode != TT_MODE_MARGINAL) {
+      double ll;
+      st = tt.run_candidate(prm.mode == TT_MODE_OPTIMIZE, cut_bl, prm, &ll);
+      o.ll = ll;
     } else {
       tt.prior.kind = prm.prior_kind;
       tt.prior.mean = prm.prior_kind == 2 ? prm.prior_means[c.loc] : prm.prior_mean;
@@ -402,7 +752,7 @@ tt_warp_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__rest
     o.dist = tt.dist_bl;
     o.status = st;
     o.calls = tt.calls;
-    if (tt.lane == 0) out[ci] = o;
+    if (lane == 0) out[ci] = o;
   }
 }
 
