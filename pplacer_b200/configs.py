@@ -71,8 +71,16 @@ def c2(Q: int = 10_000) -> Problem:
     return synth.make_problem(800, 1500, Q, seed=2, alpha=0.5)
 
 
+# C4 branch lengths: with the C2 mean (0.05) a 10k-taxon tree is ~1000 substitutions/site long and the
+# REFERENCE ITSELF degenerates under Gamma(0.5): the slowest rate category underflows to 0, after which
+# perhaps_pull_exponent never rescales that site again (frexp 0. = (0., 0), gmix_model.ml:172-176) and
+# whole sites decay to 0 => log-likelihood -inf at every edge.  Mean 0.002 (tree
+# length ~40, dense species-level sampling) keeps every site maximum above 1e-8.
+C4_MEAN_BL = 0.002
+
+
 def c4(Q: int, n_taxa: int = 10_000) -> Problem:
-    return synth.make_problem(n_taxa, 1500, Q, seed=4, alpha=0.5)
+    return synth.make_problem(n_taxa, 1500, Q, seed=4, alpha=0.5, mean_bl=C4_MEAN_BL)
 
 
 def ar53_available() -> bool:

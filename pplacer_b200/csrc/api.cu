@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include <cstdlib>
 #include <cub/device/device_segmented_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -108,6 +109,7 @@ struct pp_ctx {
   DevBuf<PlaceOut> place_out;
   DevBuf<int64_t> n_calls;
   DevBuf<int> counters;  // [0] queue head, [1] wave count, [2] active queries, [3] keep count
+  DevBuf<unsigned long long> tt_work;  // second-stage work done (warp engine): pendant calls, distal calls, each x sites
   int *h_counters = nullptr;  // pinned
   int64_t launches = 0;
   double phase_ms[4] = {0, 0, 0, 0};
@@ -124,6 +126,7 @@ struct pp_ctx {
 
 constexpr int kTTWarpsPerBlock = 8;
 constexpr int kTTWarpDefaultBlocks = 2;
+constexpr int kTTWarpDefaultFlags = 2;
 static bool ttw_supported(const pp_ctx *c) { return c->S == 4 && !c->gcat && c->R == 4; }
 static int tt_threads(const pp_ctx *c) { return c->S == 4 ? kTTThreadsDNA : kTTThreadsAA; }
 
@@ -180,7 +183,7 @@ extern "C" void pp_destroy(pp_ctx *c) {
   c->n_out.release(); c->Tq.release(); c->scores.release(); c->keys_in.release(); c->keys_out.release();
   c->ord_keys.release(); c->ord_vals.release(); c->ord_keys2.release(); c->ord_vals2.release(); c->ord_tmp.release();
   c->wbuf.release(); c->f64pool.release(); c->cand.release(); c->cand_out.release(); c->pp_out.release();
-  c->place_out.release(); c->n_calls.release(); c->counters.release();
+  c->place_out.release(); c->n_calls.release(); c->counters.release(); c->tt_work.release();
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->ev[0]) cudaEventDestroy(c->ev[0]);
   if (c->ev[1]) cudaEventDestroy(c->ev[1]);
@@ -294,7 +297,8 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
   c->t.child_ptr = c->d_child_ptr; c->t.child_idx = c->d_child_idx; c->t.parent = c->d_parent; c->t.leaf_row = c->d_leaf_row;
   c->t.ref_codes = c->d_ref_codes; c->t.site_cat = c->d_site_cat;
   CK(cudaMallocHost(&c->h_counters, 8 * sizeof(int)));
-  if ((rc = c->counters.ensure(8)) != PP_OK) { pp_destroy(c); return rc; }
+  if ((rc = c->counters.ensure(8)) != PP_OK || (rc = c->tt_work.ensure(4)) != PP_OK) { pp_destroy(c); return rc; }
+  CK(cudaMemsetAsync(c->tt_work.p, 0, 4 * sizeof(unsigned long long), c->stream));
   // QNG tables -> constant memory
   cudaMemcpyToSymbol(c_qng_x1, ppb_qng_x1, sizeof ppb_qng_x1); cudaMemcpyToSymbol(c_qng_w10, ppb_qng_w10, sizeof ppb_qng_w10);
   cudaMemcpyToSymbol(c_qng_x2, ppb_qng_x2, sizeof ppb_qng_x2); cudaMemcpyToSymbol(c_qng_w21a, ppb_qng_w21a, sizeof ppb_qng_w21a);
@@ -316,11 +320,11 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
   });
   size_t w_slots = (size_t)c->tt_blocks;
   if (ttw_supported(c)) {
-    const size_t smw = TTWarp<4>::smem_bytes(kTTWarpsPerBlock);
-    CK(cudaFuncSetAttribute(tt_warp_kernel<4, kTTWarpsPerBlock, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
-    CK(cudaFuncSetAttribute(tt_warp_kernel<4, kTTWarpsPerBlock, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
+    const size_t smw = TTWarp<4, 1>::smem_bytes(kTTWarpsPerBlock);
+    CK(cudaFuncSetAttribute(tt_warp_kernel<4, kTTWarpsPerBlock, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
+    CK(cudaFuncSetAttribute(tt_warp_kernel<4, kTTWarpsPerBlock, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tt_warp_kernel<4, kTTWarpsPerBlock, 3>, kTTWarpsPerBlock * 32, smw));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tt_warp_kernel<4, kTTWarpsPerBlock, 3, 1>, kTTWarpsPerBlock * 32, smw));
     c->ttw_max_blocks = std::max(per_sm, 2) * c->sm_count;
     w_slots = std::max(w_slots, (size_t)c->ttw_max_blocks * kTTWarpsPerBlock);
   }
@@ -623,13 +627,13 @@ static int launch_three_tax_warp(pp_ctx *c, const CandIn *in, CandOut *out, int 
   const int per_sm = c->ttw_blocks_per_sm > 0 ? std::min(c->ttw_blocks_per_sm, 3) : kTTWarpDefaultBlocks;
   int blocks = std::min(c->ttw_max_blocks, per_sm * c->sm_count);
   blocks = std::min(blocks, (n + kTTWarpsPerBlock - 1) / kTTWarpsPerBlock);
-  const size_t smw = TTWarp<4>::smem_bytes(kTTWarpsPerBlock);
+  const size_t smw = TTWarp<4, 1>::smem_bytes(kTTWarpsPerBlock);
   if (per_sm >= 3)
-    tt_warp_kernel<4, kTTWarpsPerBlock, 3><<<blocks, kTTWarpsPerBlock * 32, smw, c->stream>>>(
-        c->dm, c->g, c->d_bl, c->codes.p, c->qsite.p, c->nq.p, in, order, out, n, prm, c->wbuf.p, c->counters.p);
+    tt_warp_kernel<4, kTTWarpsPerBlock, 3, 1><<<blocks, kTTWarpsPerBlock * 32, smw, c->stream>>>(
+        c->dm, c->g, c->d_bl, c->codes.p, c->qsite.p, c->nq.p, in, order, out, n, prm, c->wbuf.p, c->counters.p, c->tt_work.p);
   else
-    tt_warp_kernel<4, kTTWarpsPerBlock, 2><<<blocks, kTTWarpsPerBlock * 32, smw, c->stream>>>(
-        c->dm, c->g, c->d_bl, c->codes.p, c->qsite.p, c->nq.p, in, order, out, n, prm, c->wbuf.p, c->counters.p);
+    tt_warp_kernel<4, kTTWarpsPerBlock, 2, 2><<<blocks, kTTWarpsPerBlock * 32, smw, c->stream>>>(
+        c->dm, c->g, c->d_bl, c->codes.p, c->qsite.p, c->nq.p, in, order, out, n, prm, c->wbuf.p, c->counters.p, c->tt_work.p);
   LAUNCH_CHECK(c);
   return PP_OK;
 }
@@ -654,6 +658,8 @@ static TTParams make_params(const pp_prefs *pf, int mode, double tol, int use_de
   p.start_pend = pf->start_pend; p.max_pend = pf->max_pend; p.tol = tol; p.pp_rel_err = pf->pp_rel_err;
   p.prior_mean = pf->prior_mean; p.prior_means = nullptr; p.max_iter = pf->max_iter; p.mode = mode;
   p.prior_kind = pf->prior_kind; p.use_defaults = use_defaults;
+  static const int env_flags = [] { const char *e = std::getenv("PPB_TT_FLAGS"); return e ? std::atoi(e) : kTTWarpDefaultFlags; }();
+  p.flags = env_flags;
   return p;
 }
 
@@ -971,6 +977,16 @@ extern "C" int pp_phase_times_ms(pp_ctx *c, double *out4, int32_t reset) {
   if (!c || !out4) return fail(PP_EINVAL, "pp_phase_times_ms: bad arguments");
   std::memcpy(out4, c->phase_ms, sizeof c->phase_ms);
   if (reset) std::memset(c->phase_ms, 0, sizeof c->phase_ms);
+  return PP_OK;
+}
+extern "C" int pp_three_tax_work(pp_ctx *c, double *out4, int32_t reset) {
+  if (!c || !out4) return fail(PP_EINVAL, "pp_three_tax_work: bad arguments");
+  CK(cudaSetDevice(c->device));
+  unsigned long long h[4];
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(h, c->tt_work.p, sizeof h, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 4; ++i) out4[i] = (double)h[i];
+  if (reset) CK(cudaMemset(c->tt_work.p, 0, sizeof h));
   return PP_OK;
 }
 extern "C" int pp_measure_fp64_peak(pp_ctx *c, double *tflops_out) {

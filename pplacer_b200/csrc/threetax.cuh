@@ -55,6 +55,7 @@ struct TTParams {
   double start_pend, max_pend, tol, pp_rel_err, prior_mean;
   const double *prior_means;  // informative prior (per edge) or null
   int max_iter, mode, prior_kind, use_defaults;
+  int flags;  // warp engine: bit 0 = recompute w in every pendant pass instead of caching it, bit 1 = L2 prefetch
 };
 
 __constant__ double c_qng_x1[5], c_qng_w10[5], c_qng_x2[5], c_qng_w21a[5], c_qng_w21b[6], c_qng_x3[11],

@@ -50,12 +50,13 @@ struct WarpProd {
 
 extern __shared__ double2 ppb_ttw_smem[];
 
-template <int R>
-struct TTWarp : TTDriver<TTWarp<R>> {
-  using Base = TTDriver<TTWarp<R>>;
+// TS = sites per lane per iteration in the one-point passes of the optimiser
+template <int R, int TS>
+struct TTWarp : TTDriver<TTWarp<R, TS>> {
+  using Base = TTDriver<TTWarp<R, TS>>;
   using Base::pend_bl; using Base::dist_bl; using Base::prox_bl; using Base::calls;
   static constexpr int S = 4, K = 4 * R, PM = 16 * R;
-  static constexpr int PQS = PM + K;  // a pendant matrix set: P [R][4][4] then QN [R][4] (row sums, for 'N')
+  static constexpr int PQS = 5 * K;   // a pendant matrix set: rows [R*4][5] = P[rs][0..3] then QN[rs] (row sum, for 'N')
   static constexpr int NBP = 6;    // pendant points per pass
   static constexpr int NBD = 4;    // distal points per pass
   static constexpr int MEMO = 24;  // QNG's 21- and 22-point rule extensions (the 44-point one is batched in part)
@@ -92,6 +93,8 @@ struct TTWarp : TTDriver<TTWarp<R>> {
   int nq;
   double e_tot_ln2, rate_term;
   bool w_stale;
+  int flags;  // TTParams.flags
+  int calls_dist;  // distal-objective calls among `calls`
   int memo_n, memo_pending, memo_kind;  // memo_kind: -1 none, 0 pendant values, 1 distal values
 
   static __host__ __device__ constexpr size_t smem_bytes(int warps) { return sizeof(double) * (size_t)(C_TOTAL + warps * PER_WARP); }
@@ -100,6 +103,7 @@ struct TTWarp : TTDriver<TTWarp<R>> {
   __device__ __forceinline__ static const double *CST() { return reinterpret_cast<const double *>(ppb_ttw_smem); }
   __device__ __forceinline__ double *SW() const { return reinterpret_cast<double *>(ppb_ttw_smem) + sw_off; }
   __device__ __forceinline__ static int lane_id() { return threadIdx.x & 31; }
+  __device__ __forceinline__ static void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
   __device__ __forceinline__ static double warp_sum(double v) {
 #pragma unroll
@@ -127,14 +131,14 @@ struct TTWarp : TTDriver<TTWarp<R>> {
       double acc = 0.0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) acc = fma(ex[b * K + r * 4 + k] * c[C_X + i * 4 + k], c[C_XIT + j * 4 + k], acc);
-      dst[b * stride + e] = acc;
+      dst[b * stride + (qn ? (e >> 2) * 5 + (e & 3) : e)] = acc;
     }
     __syncwarp();
     if (qn) {
       for (int t = lane_id(); t < n * K; t += 32) {
         const int b = t / K, rs = t - b * K;
-        const double *row = dst + b * stride + rs * 4;
-        dst[b * stride + PM + rs] = (((0.0 + row[0]) + row[1]) + row[2]) + row[3];
+        double *row = dst + b * stride + rs * 5;
+        row[4] = (((0.0 + row[0]) + row[1]) + row[2]) + row[3];
       }
       __syncwarp();
     }
@@ -177,24 +181,23 @@ struct TTWarp : TTDriver<TTWarp<R>> {
 
   // Per-row (32 sites) query-character decode, uniform across the warp.  The evolved pendant GLV
   // entry for state row rs is P[rs][col] for a plain base, QN[rs] for 'N' (fast: one shared load at
-  // set[rs*qmul + qadd]); any other ambiguity code in the row sends the whole row down the slow path
+  // set[rs*5 + qcol]); any other ambiguity code in the row sends the whole row down the slow path
   // (sum of the selected columns in ascending order - exact for plain bases too, since 0 + x = x).
   struct RowCodes {
     uint32_t mask;
-    int qmul, qadd;
+    int qcol;
     bool fast;
   };
   __device__ __forceinline__ static RowCodes decode(int packed) {
     RowCodes c;
     c.mask = ((uint32_t)packed >> kSiteCodeShift) & 0x7f;
     const bool single = (c.mask & (c.mask - 1)) == 0;
-    c.qmul = single ? 4 : 1;
-    c.qadd = single ? __ffs(c.mask) - 1 : PM;
+    c.qcol = single ? __ffs(c.mask) - 1 : 4;
     c.fast = __all_sync(FULL, single || c.mask == 15u);
     return c;
   }
   __device__ __forceinline__ static double q_slow(const double *set, int rs, uint32_t mask) {
-    const double *row = set + rs * 4;
+    const double *row = set + rs * 5;
     double acc = 0.0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc = ((mask >> j) & 1u) ? acc + row[j] : acc;
@@ -208,18 +211,24 @@ struct TTWarp : TTDriver<TTWarp<R>> {
   }
 
   // de = P_d d, pe = P_p p, ww[s] = (statd_s * pe_s) * de_s   (log_like3's ((statd*x)*y), x = prox,
-  // y = dist: three_tax.ml:31-36, linear_c.c:367-424) for one rate category
-  __device__ __forceinline__ static void site_w(const double *Pd, const double *Pp, const double (&d)[4], const double (&p)[4],
-                                                const double *st, double (&ww)[4]) {
+  // y = dist: three_tax.ml:31-36, linear_c.c:367-424) for one rate category and T sites per lane:
+  // every matrix entry fetched from shared memory serves T sites.
+  template <int T>
+  __device__ __forceinline__ static void site_w(const double *Pd, const double *Pp, const double (&d)[T][4], const double (&p)[T][4],
+                                                const double *st, double (&ww)[T][4]) {
     const double2 *Pd2 = reinterpret_cast<const double2 *>(Pd), *Pp2 = reinterpret_cast<const double2 *>(Pp);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       const double2 a0 = Pd2[s * 2], a1 = Pd2[s * 2 + 1], b0 = Pp2[s * 2], b1 = Pp2[s * 2 + 1];
-      double de = fma(a0.x, d[0], 0.0), pe = fma(b0.x, p[0], 0.0);
-      de = fma(a0.y, d[1], de); pe = fma(b0.y, p[1], pe);
-      de = fma(a1.x, d[2], de); pe = fma(b1.x, p[2], pe);
-      de = fma(a1.y, d[3], de); pe = fma(b1.y, p[3], pe);
-      ww[s] = (st[s] * pe) * de;
+      const double sts = st[s];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        double de = fma(a0.x, d[t][0], 0.0), pe = fma(b0.x, p[t][0], 0.0);
+        de = fma(a0.y, d[t][1], de); pe = fma(b0.y, p[t][1], pe);
+        de = fma(a1.x, d[t][2], de); pe = fma(b1.x, p[t][2], pe);
+        de = fma(a1.y, d[t][3], de); pe = fma(b1.y, p[t][3], pe);
+        ww[t][s] = (sts * pe) * de;
+      }
     }
   }
 
@@ -229,11 +238,25 @@ struct TTWarp : TTDriver<TTWarp<R>> {
     if (lane_id() < 8) s[OFF_BAD + lane_id()] = 0.0;
     __syncwarp();
   }
+  template <int NB>
+  __device__ __forceinline__ void pass_end(const WarpProd (&lp)[NB]) {
+    double *s = SW();
+    __syncwarp();
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const double v = finish(lp[b].m, lp[b].e, b);
+      if (lane_id() == 0) s[OFF_OUT + b] = v;
+    }
+    __syncwarp();
+  }
 
+  // Row bookkeeping shared by the passes: each iteration handles T rows of 32 sites (lane l owns
+  // sites base + t*32 + l); the packed (site, code) words of the next iteration are loaded one
+  // iteration ahead, and the planes two iterations ahead are pulled towards L2 (flags bit 1).
   // Three_tax.log_like at NB (distal, proximal) pairs with the current pendant matrices: the set at
   // pm_off holds NB x {P(distal), P(proximal)}.  One pass over darr/parr planes at the query's sites;
   // results go to SW()[OFF_OUT + b].
-  template <int NB>
+  template <int NB, int T>
   __device__ __forceinline__ void pass_dist(int pm_off) {
     pass_begin();
     double *s = SW();
@@ -241,132 +264,197 @@ struct TTWarp : TTDriver<TTWarp<R>> {
     WarpProd lp[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) lp[b].init();
-    int packed_next = qsite[min(lane_id(), nq - 1)];
-    for (int base = 0; base < nq; base += 32) {
-      const int i = base + lane_id();
-      const bool act = i < nq;
-      const int packed = packed_next;
-      packed_next = qsite[min(i + 32, nq - 1)];  // next row's sites are in flight while this row computes
-      const int site = packed & kSiteMask;
-      const RowCodes c = decode(packed);
-      const double *dp = dbase + site, *pp = pbase + site;
-      double u[NB];
+    const int lane = lane_id();
+    int next[T];
 #pragma unroll
-      for (int b = 0; b < NB; ++b) u[b] = 0.0;
-#pragma unroll(NB == 1 ? R : 1)
+    for (int t = 0; t < T; ++t) next[t] = qsite[min(t * 32 + lane, nq - 1)];
+    const bool pf = (flags & 2) != 0;
+    const double *pfp = (lane < 16 ? dbase : pbase) + (int64_t)(lane & 15) * Lp;  // lane -> plane, for prefetch
+    const int pf_max = (int)Lp - 16;
+    for (int base = 0; base < nq; base += 32 * T) {
+      int packed[T];
+      bool act[T], fast = true;
+      const double *dp[T], *pp[T], *Pqc[T];
+      uint32_t mask[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int i = base + t * 32 + lane;
+        act[t] = i < nq;
+        packed[t] = next[t];
+        next[t] = qsite[min(i + 32 * T, nq - 1)];
+        const RowCodes c = decode(packed[t]);
+        fast = fast && c.fast;
+        mask[t] = c.mask;
+        Pqc[t] = Pq + c.qcol;
+        const int site = packed[t] & kSiteMask;
+        dp[t] = dbase + site; pp[t] = pbase + site;
+      }
+      if (pf) {
+        const int s0 = __shfl_sync(FULL, packed[0] & kSiteMask, 0) + 64 * T;
+#pragma unroll
+        for (int h = 0; h < 2 * T; ++h) prefetch_l2(pfp + min(s0 + 16 * h, pf_max));
+      }
+      double u[T][NB];
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) u[t][b] = 0.0;
+#pragma unroll 1
       for (int r = 0; r < R; ++r) {
-        double d[4], p[4], q[4];
+        double d[T][4], p[T][4], q[T][4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          d[k] = __ldg(dp + (int64_t)(r * 4 + k) * Lp);
-          p[k] = __ldg(pp + (int64_t)(r * 4 + k) * Lp);
-        }
-        if (c.fast) {
+        for (int t = 0; t < T; ++t)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) q[k] = Pq[(r * 4 + k) * c.qmul + c.qadd];
+          for (int k = 0; k < 4; ++k) {
+            d[t][k] = __ldg(dp[t] + (int64_t)(r * 4 + k) * Lp);
+            p[t][k] = __ldg(pp[t] + (int64_t)(r * 4 + k) * Lp);
+          }
+        if (fast) {
+#pragma unroll
+          for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[t][k] = Pqc[t][(r * 4 + k) * 5];
         } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) q[k] = q_slow(Pq, r * 4 + k, c.mask);
+          for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[t][k] = q_slow(Pq, r * 4 + k, mask[t]);
         }
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-          double ww[4];
-          site_w(Pm + b * 2 * PM + r * 16, Pm + b * 2 * PM + PM + r * 16, d, p, st, ww);
+          double ww[T][4];
+          site_w<T>(Pm + b * 2 * PM + r * 16, Pm + b * 2 * PM + PM + r * 16, d, p, st, ww);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) u[b] = fma(ww[k], q[k], u[b]);
+          for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) u[t][b] = fma(ww[t][k], q[t][k], u[t][b]);
         }
       }
-      if (act) {
 #pragma unroll
-        for (int b = 0; b < NB; ++b) lp[b].mul(u[b], s + OFF_BAD + b);
-      }
-    }
-    __syncwarp();
+      for (int t = 0; t < T; ++t)
+        if (act[t]) {
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const double v = finish(lp[b].m, lp[b].e, b);
-      if (lane_id() == 0) s[OFF_OUT + b] = v;
+          for (int b = 0; b < NB; ++b) lp[b].mul(u[t][b], s + OFF_BAD + b);
+        }
     }
-    __syncwarp();
+    pass_end<NB>(lp);
   }
 
   // log_like at NB pendant lengths (sets at pq_off + b*PQS) with the current distal / proximal
-  // matrices.  FUSED: recompute w from darr/parr and store it; otherwise read the cached w.  w is
-  // streamed (evict-first) so that it does not push the shared darr/parr planes out of L2.
-  template <int NB, bool FUSED>
+  // matrices.  MODE 0: read the cached w; 1: recompute w from darr/parr and store it; 2: recompute,
+  // no store.  w is streamed (evict-first) so that it does not push the shared darr/parr planes out of L2.
+  template <int NB, int MODE, int T>
   __device__ __forceinline__ void pass_pend(int pq_off) {
+    constexpr bool FUSED = MODE != 0;
     pass_begin();
     double *s = SW();
     const double *Pqm = s + pq_off, *Pd0 = s + OFF_PD, *st = CST() + C_STATD;
     WarpProd lp[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) lp[b].init();
-    int packed_next = qsite[min(lane_id(), nq - 1)];
-    for (int base = 0; base < nq; base += 32) {
-      const int i = base + lane_id();
-      const bool act = i < nq;
-      const int ic = act ? i : nq - 1;
-      const int packed = packed_next;
-      packed_next = qsite[min(i + 32, nq - 1)];
-      const int site = packed & kSiteMask;
-      const RowCodes c = decode(packed);
-      const double *dp = dbase + site, *pp = pbase + site;
-      double *wp = w + ic;
-      double u[NB];
+    const int lane = lane_id();
+    int next[T];
 #pragma unroll
-      for (int b = 0; b < NB; ++b) u[b] = 0.0;
-#pragma unroll(NB == 1 ? R : 1)
-      for (int r = 0; r < R; ++r) {
-        double ww[4];
+    for (int t = 0; t < T; ++t) next[t] = qsite[min(t * 32 + lane, nq - 1)];
+    const bool pf = (flags & 2) != 0;
+    const double *pfp = FUSED ? (lane < 16 ? dbase : pbase) + (int64_t)(lane & 15) * Lp
+                              : w + (int64_t)(lane & 15) * Lp + (lane >> 4) * 16;
+    const int pf_max = (int)Lp - 16;
+    for (int base = 0; base < nq; base += 32 * T) {
+      int packed[T];
+      bool act[T], fast = true;
+      const double *dp[T], *pp[T], *Pqc[T];
+      double *wp[T];
+      uint32_t mask[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int i = base + t * 32 + lane;
+        act[t] = i < nq;
+        packed[t] = next[t];
+        next[t] = qsite[min(i + 32 * T, nq - 1)];
+        const RowCodes c = decode(packed[t]);
+        fast = fast && c.fast;
+        mask[t] = c.mask;
+        Pqc[t] = Pqm + c.qcol;
+        const int site = packed[t] & kSiteMask;
+        dp[t] = dbase + site; pp[t] = pbase + site;
+        wp[t] = w + (act[t] ? i : nq - 1);
+      }
+      if (pf) {
         if (FUSED) {
-          double d[4], p[4];
+          const int s0 = __shfl_sync(FULL, packed[0] & kSiteMask, 0) + 64 * T;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            d[k] = __ldg(dp + (int64_t)(r * 4 + k) * Lp);
-            p[k] = __ldg(pp + (int64_t)(r * 4 + k) * Lp);
-          }
-          site_w(Pd0 + r * 16, Pd0 + PM + r * 16, d, p, st, ww);
-          if (act) {
+          for (int h = 0; h < 2 * T; ++h) prefetch_l2(pfp + min(s0 + 16 * h, pf_max));
+        } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) __stcs(wp + (int64_t)(r * 4 + k) * Lp, ww[k]);
+          for (int h = 0; h < T; ++h) prefetch_l2(pfp + min(base + 64 * T + 32 * h, pf_max));
+        }
+      }
+      double u[T][NB];
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) u[t][b] = 0.0;
+#pragma unroll 1
+      for (int r = 0; r < R; ++r) {
+        double ww[T][4];
+        if (FUSED) {
+          double d[T][4], p[T][4];
+#pragma unroll
+          for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              d[t][k] = __ldg(dp[t] + (int64_t)(r * 4 + k) * Lp);
+              p[t][k] = __ldg(pp[t] + (int64_t)(r * 4 + k) * Lp);
+            }
+          site_w<T>(Pd0 + r * 16, Pd0 + PM + r * 16, d, p, st, ww);
+          if (MODE == 1) {
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+              if (act[t]) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) __stcs(wp[t] + (int64_t)(r * 4 + k) * Lp, ww[t][k]);
+              }
           }
         } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ww[k] = __ldcs(wp + (int64_t)(r * 4 + k) * Lp);
+          for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ww[t][k] = __ldcs(wp[t] + (int64_t)(r * 4 + k) * Lp);
         }
-        if (c.fast) {
+        if (fast) {
 #pragma unroll
           for (int b = 0; b < NB; ++b)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) u[b] = fma(ww[k], Pqm[b * PQS + (r * 4 + k) * c.qmul + c.qadd], u[b]);
+            for (int t = 0; t < T; ++t)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) u[t][b] = fma(ww[t][k], Pqc[t][b * PQS + (r * 4 + k) * 5], u[t][b]);
         } else {
 #pragma unroll
           for (int b = 0; b < NB; ++b)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) u[b] = fma(ww[k], q_slow(Pqm + b * PQS, r * 4 + k, c.mask), u[b]);
+            for (int t = 0; t < T; ++t)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) u[t][b] = fma(ww[t][k], q_slow(Pqm + b * PQS, r * 4 + k, mask[t]), u[t][b]);
         }
       }
-      if (act) {
 #pragma unroll
-        for (int b = 0; b < NB; ++b) lp[b].mul(u[b], s + OFF_BAD + b);
-      }
-    }
-    __syncwarp();
+      for (int t = 0; t < T; ++t)
+        if (act[t]) {
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const double v = finish(lp[b].m, lp[b].e, b);
-      if (lane_id() == 0) s[OFF_OUT + b] = v;
+          for (int b = 0; b < NB; ++b) lp[b].mul(u[t][b], s + OFF_BAD + b);
+        }
     }
-    __syncwarp();
+    pass_end<NB>(lp);
   }
 
-  __device__ __noinline__ double pend_single_cached() { pass_pend<1, false>(OFF_PQ); return SW()[OFF_OUT]; }
-  __device__ __noinline__ double pend_single_fused() { pass_pend<1, true>(OFF_PQ); w_stale = false; return SW()[OFF_OUT]; }
-  __device__ __noinline__ double dist_single() { pass_dist<1>(OFF_PD); return SW()[OFF_OUT]; }
-  __device__ __noinline__ void pend_batch_cached() { pass_pend<NBP, false>(OFF_PB); }
-  __device__ __noinline__ void pend_batch_fused() { pass_pend<NBP, true>(OFF_PB); w_stale = false; }
+  __device__ __noinline__ double pend_single_cached() { pass_pend<1, 0, 1>(OFF_PQ); return SW()[OFF_OUT]; }
+  __device__ __noinline__ double pend_single_fused() { pass_pend<1, 1, 1>(OFF_PQ); w_stale = false; return SW()[OFF_OUT]; }
+  __device__ __noinline__ double dist_single() { pass_dist<1, 1>(OFF_PD); return SW()[OFF_OUT]; }
+  __device__ __noinline__ void pend_batch_cached() { pass_pend<NBP, 0, 1>(OFF_PB); }
+  __device__ __noinline__ void pend_batch_fused() { pass_pend<NBP, 1, 1>(OFF_PB); w_stale = false; }
   __device__ void pend_batch() { if (w_stale) pend_batch_fused(); else pend_batch_cached(); }
-  __device__ __noinline__ void dist_batch() { pass_dist<NBD>(OFF_PB); }
+  __device__ __noinline__ void dist_batch() { pass_dist<NBD, 1>(OFF_PB); }
 
   // ---- TTDriver engine interface ----
   __device__ double f_pend(double v) {
@@ -630,9 +718,10 @@ struct TTWarp : TTDriver<TTWarp<R>> {
     for (;;) {
       const int more = optimise ? opt_advance(feed, f) : 0;
       if (more == 2) {  // Brent's predictable calls, several per pass
-        if (memo_kind == 1) pass_dist<NBD>(OFF_PB);
-        else if (w_stale) { pass_pend<NBP, true>(OFF_PB); w_stale = false; }
-        else pass_pend<NBP, false>(OFF_PB);
+        if (memo_kind == 1) pass_dist<NBD, 1>(OFF_PB);
+        else if (flags & 1) pass_pend<NBP, 2, 1>(OFF_PB);
+        else if (w_stale) { pass_pend<NBP, 1, 1>(OFF_PB); w_stale = false; }
+        else pass_pend<NBP, 0, 1>(OFF_PB);
         feed = 2;
         continue;
       }
@@ -658,11 +747,14 @@ struct TTWarp : TTDriver<TTWarp<R>> {
         set_pend(x);
         have = memo_get(0, x, 0.0, &val);
         if (!have) {
-          if (w_stale) { pass_pend<1, true>(OFF_PQ); w_stale = false; } else pass_pend<1, false>(OFF_PQ);
+          if (flags & 1) pass_pend<1, 2, TS>(OFF_PQ);
+          else if (w_stale) { pass_pend<1, 1, TS>(OFF_PQ); w_stale = false; }
+          else pass_pend<1, 0, TS>(OFF_PQ);
         }
       } else {
         if (kind == OBJ_DIST) {
           calls++;
+          calls_dist++;
           const double prox = (dist_bl + prox_bl) - x;
           if (!(prox >= 0.0)) nan_out = true;
           else {
@@ -670,7 +762,7 @@ struct TTWarp : TTDriver<TTWarp<R>> {
             set_dist_prox(x, prox);
           }
         }
-        if (!have && !nan_out) pass_dist<1>(OFF_PD);
+        if (!have && !nan_out) pass_dist<1, TS>(OFF_PD);
       }
       if (!have) val = SW()[OFF_OUT];
       if (more == 0) { *ll_out = val; return st; }
@@ -697,13 +789,13 @@ struct TTWarp : TTDriver<TTWarp<R>> {
 };
 
 // Persistent kernel: every warp pulls candidates (in `order`, sorted by edge) until n are done.
-template <int R, int WARPS, int MINB>
+template <int R, int WARPS, int MINB, int TS>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 tt_warp_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__restrict__ bl, const uint8_t *__restrict__ codes,
                const int32_t *__restrict__ qsite, const int32_t *__restrict__ nq, const CandIn *__restrict__ in,
                const int32_t *__restrict__ order, CandOut *__restrict__ out, int n, TTParams prm, double *__restrict__ wbuf,
-               int *counter) {
-  using TT = TTWarp<R>;
+               int *counter, unsigned long long *__restrict__ work) {
+  using TT = TTWarp<R, TS>;
   double *sm = reinterpret_cast<double *>(ppb_ttw_smem);
   for (int i = threadIdx.x; i < 4; i += blockDim.x) { sm[TT::C_STATD + i] = m->statd[i]; sm[TT::C_LAM + i] = m->lam[i]; }
   for (int i = threadIdx.x; i < 16; i += blockDim.x) { sm[TT::C_X + i] = m->x[i]; sm[TT::C_XIT + i] = m->xit[i]; }
@@ -714,6 +806,7 @@ tt_warp_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__rest
   TT &tt = *reinterpret_cast<TT *>(sm + TT::C_TOTAL + warp * TT::PER_WARP + TT::OFF_OBJ);
   tt.sw_off = TT::C_TOTAL + warp * TT::PER_WARP;
   tt.Lp = g.Lp;
+  tt.flags = prm.flags;
   tt.w = wbuf + (int64_t)(blockIdx.x * WARPS + warp) * TT::K * g.Lp;
   for (;;) {
     int idx = 0;
@@ -729,6 +822,7 @@ tt_warp_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__rest
     tt.ebase_d = g.e[0] + (int64_t)c.loc * g.Lp;
     tt.ebase_p = g.e[1] + (int64_t)c.loc * g.Lp;
     tt.calls = 0;
+    tt.calls_dist = 0;
     const double cut_bl = bl[c.loc];
     CandOut o;
     o.marg = __longlong_as_double(0x7ff8000000000000LL);
@@ -752,7 +846,11 @@ tt_warp_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__rest
     o.dist = tt.dist_bl;
     o.status = st;
     o.calls = tt.calls;
-    if (lane == 0) out[ci] = o;
+    if (lane == 0) {
+      out[ci] = o;
+      const unsigned long long nd = tt.calls_dist, np = tt.calls - tt.calls_dist, ns = tt.nq;
+      atomicAdd(work + 0, np); atomicAdd(work + 1, nd); atomicAdd(work + 2, np * ns); atomicAdd(work + 3, nd * ns);
+    }
   }
 }
 

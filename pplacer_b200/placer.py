@@ -201,6 +201,12 @@ class Placer:
         _lib.check(_lib.load().pp_phase_times_ms(self.ctx, _lib.dp(out), 1 if reset else 0))
         return out
 
+    def three_tax_work(self, reset: bool = False) -> np.ndarray:
+        """[pendant calls, distal calls, pendant call-sites, distal call-sites] of the warp engine."""
+        out = np.zeros(4)
+        _lib.check(_lib.load().pp_three_tax_work(self.ctx, _lib.dp(out), 1 if reset else 0))
+        return out
+
     def measure_fp64_peak(self) -> float:
         v = C.c_double(0)
         _lib.check(_lib.load().pp_measure_fp64_peak(self.ctx, C.byref(v)))

@@ -95,9 +95,9 @@ class Synth:
 
 
 def simulate_reference(n_taxa: int, L: int, seed: int, alpha: float = 0.5, n_cats: int = 4,
-                       gap_frac: float = 0.10) -> Synth:
+                       gap_frac: float = 0.10, mean_bl: float = 0.05) -> Synth:
     rng = np.random.default_rng(seed)
-    tree = random_tree(n_taxa, rng)
+    tree = random_tree(n_taxa, rng, mean_bl=mean_bl)
     exch = gtr_exch(**HIV_GTR)
     pi = HIV_PI / HIV_PI.sum()
     x, lam, xit = _lib.diagd(exch, pi)
@@ -158,7 +158,7 @@ def simulate_queries(s: Synth, Q: int, seed: int, min_len: int = 250, max_len: i
 
 
 def make_problem(n_taxa: int, L: int, Q: int, seed: int, **kw) -> Problem:
-    s = simulate_reference(n_taxa, L, seed, **{k: v for k, v in kw.items() if k in ("alpha", "n_cats", "gap_frac")})
+    s = simulate_reference(n_taxa, L, seed, **{k: v for k, v in kw.items() if k in ("alpha", "n_cats", "gap_frac", "mean_bl")})
     queries = simulate_queries(s, Q, seed, **{k: v for k, v in kw.items() if k in ("min_len", "max_len", "pend_mean")})
     return build_problem(s.tree, s.model, s.ref_align, queries)
 

@@ -21,6 +21,11 @@ PROBLEMS = {
     "gcat_dna": lambda: configs.gcat_variant("gtr"),
     "gcat_aa": lambda: configs.gcat_variant("wag"),
     "synth": lambda: configs.synthetic(60, 300, 64, seed=7, min_len=40),
+    # a long tree under Gamma(0.5): the slowest rate category underflows to exactly 0 at many sites, and
+    # the reference's exponent pull then stops for good (frexp 0. = (0., 0) is the maximum over the
+    # rates, gmix_model.ml:172-176) - 12 % of the (edge, site, rate) maxima are 0.  The device must
+    # reproduce that, including the prefilter's exact fallback for values outside its fast range.
+    "zero_cat": lambda: configs.synthetic(1500, 48, 6, seed=9, alpha=0.5, mean_bl=0.12, min_len=30),
 }
 _cache = {}
 
@@ -70,7 +75,7 @@ def test_phyml_tree_likelihood_at_every_edge(name):
 # ---------------------------------------------------------------------------------------------
 # stage by stage against the oracle
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["c1_gtr", "wag", "gcat_dna", "gcat_aa"])
+@pytest.mark.parametrize("name", ["c1_gtr", "wag", "gcat_dna", "gcat_aa", "zero_cat"])
 def test_precompute_glvs_match_oracle(oracle_binding, name):
     prob, o, p = setup(name, oracle_binding)
     exp_equal = exp_total = 0
@@ -92,7 +97,7 @@ def test_precompute_glvs_match_oracle(oracle_binding, name):
     assert exp_equal == exp_total
 
 
-@pytest.mark.parametrize("name", ["c1_gtr", "wag", "gcat_dna", "gcat_aa", "synth"])
+@pytest.mark.parametrize("name", ["c1_gtr", "wag", "gcat_dna", "gcat_aa", "synth", "zero_cat"])
 def test_prefilter_scores_and_ranking_match_oracle(oracle_binding, name):
     prob, o, p = setup(name, oracle_binding)
     _, _, st, info = o.place(prob.query_chars, oracle_prefs(oracle_binding, prob), n_threads=4, debug=True)
@@ -177,7 +182,7 @@ def test_evolve_matches_oracle(oracle_binding, name):
 # ---------------------------------------------------------------------------------------------
 # the path end to end
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["c1_gtr", "wag", "gcat_dna", "gcat_aa", "synth"])
+@pytest.mark.parametrize("name", ["c1_gtr", "wag", "gcat_dna", "gcat_aa", "synth", "zero_cat"])
 def test_place_matches_oracle(oracle_binding, name):
     prob, o, p = setup(name, oracle_binding)
     exp, n_exp, st_exp, oinfo = o.place(prob.query_chars, oracle_prefs(oracle_binding, prob), n_threads=4, debug=True)
@@ -389,3 +394,39 @@ def test_ar53_golden_placements():
         assert abs(r["pendant"] - g["pendant_length"]) <= 1e-4
         assert abs(r["distal"] - g["distal_length"]) <= 1e-4
         assert abs(r["ml_ratio"] - g["like_weight_ratio"]) <= 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# C1 end to end: refpkg + query FASTA -> jplace (run_file), compared with the oracle under the
+# north_star tolerances through the jplace comparator
+# ---------------------------------------------------------------------------------------------
+def test_c1_refpkg_to_jplace_matches_oracle(oracle_binding, tmp_path):
+    import shutil
+    from pplacer_b200 import jplace, run, synth, models
+    src = os.path.join(configs.GOLDEN, "like", "gtr")
+    rp = tmp_path / "hiv.refpkg"
+    rp.mkdir()
+    for f in ("hiv.fasta", "hiv.phy_phyml_tree.txt", "phylo_model.jplace"):
+        shutil.copyfile(os.path.join(src, f), rp / f)
+    (rp / "CONTENTS.json").write_text(json.dumps({"files": {"aln_fasta": "hiv.fasta", "tree": "hiv.phy_phyml_tree.txt",
+                                                             "phylo_model": "phylo_model.jplace"}}))
+    tree, aln, model = configs.like_inputs("gtr")
+    queries = synth.perturbed_queries(aln, models.NUC_CODE, 1)
+    queries.append(("dup_of_first", queries[0][1].lower()))          # de-duplicated and upper-cased
+    qf = tmp_path / "q.fasta"
+    qf.write_text("".join(">%s\n%s\n" % (n, s) for n, s in queries))
+    for pp in (False, True):
+        out_path = str(tmp_path / ("out_pp.jplace" if pp else "out.jplace"))
+        path, prob, (res, n_out, st) = run.run_file(str(rp), str(qf), out_path, pp=pp)
+        assert (st == 0).all()
+        tree_str, fields, got = jplace.read_jplace(path)
+        assert tree_str == prob.tree.to_newick(with_node_numbers=True)
+        assert fields == (jplace.PP_FIELDS if pp else jplace.BASE_FIELDS)
+        assert ["q_%s_0" % aln[0][0], "dup_of_first"] in [pq.names for pq in got]
+        o = oracle_binding.Oracle(prob)
+        kw = dict(calc_pp=1, keep_at_most=20, keep_factor=0.001, max_strikes=20) if pp else {}
+        exp, n_exp, st_exp, _ = o.place(prob.query_chars, oracle_prefs(oracle_binding, prob, **kw), n_threads=4)
+        want = jplace.pqueries_from_results(prob.query_names, exp, n_exp, st_exp, pp=pp)
+        rep = jplace.compare(got, want, keep_factor=0.001 if pp else 0.01)
+        assert rep.ok and rep.n_queries == len(prob.query_names), rep.summary() + " " + "; ".join(rep.failures[:5])
+        o.close()

@@ -1,24 +1,19 @@
 #!/bin/bash
-# one GPU visit: parity tests, bench lines, ncu launch list and full captures (outputs under gpurun_out/)
+# one GPU visit: parity tests, bench lines (C2 default, C5, C4), ncu launch list and full captures (outputs under gpurun_out/)
 set -u
-TAG=${1:-r1c}
+TAG=${1:-r1j}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${TAG}_pytest.log
-tail -15 gpurun_out/${TAG}_pytest.log
+timeout 1800 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${TAG}_pytest.log
+tail -6 gpurun_out/${TAG}_pytest.log
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 cat gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
-for B in 1 3; do
-timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --tt-blocks-per-sm $B > gpurun_out/${TAG}_bench_b$B.json 2> gpurun_out/${TAG}_bench_b$B.err; echo "bench b$B rc=$?"
-python - <<PY
-import json
-try:
-    j=json.load(open("gpurun_out/${TAG}_bench_b$B.json")); print("blocks/SM $B:", j["value"], j["roofline"]["share_of_step_ms"])
-except Exception as e: print("parse failed", e)
-PY
-done
-timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --tt-engine block > gpurun_out/${TAG}_bench_block.json 2> gpurun_out/${TAG}_bench_block.err; echo "bench block rc=$?"
-cat gpurun_out/${TAG}_bench_block.json
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launch.log 2>&1; echo "ncu launches rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tt_warp_kernel' -c 2 -o gpurun_out/${TAG}_full_ttwarp -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --queries 4096 > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
-ls -la gpurun_out
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err; echo "bench reference rc=$?"
+cat gpurun_out/${TAG}_bench_reference.json
+timeout 900 python bench.py --workload c5 --steps 2 --warmup 3 --cpu-seconds 8 > gpurun_out/${TAG}_bench_c5.json 2> gpurun_out/${TAG}_bench_c5.err; echo "bench c5 rc=$?"
+cat gpurun_out/${TAG}_bench_c5.json; tail -3 gpurun_out/${TAG}_bench_c5.err
+timeout 900 python bench.py --workload c4 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_c4.json 2> gpurun_out/${TAG}_bench_c4.err; echo "bench c4 rc=$?"
+cat gpurun_out/${TAG}_bench_c4.json; tail -3 gpurun_out/${TAG}_bench_c4.err
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launch.log 2>&1; echo "ncu launches rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tt_warp_kernel|prefilter_table_kernel' -c 3 -o gpurun_out/${TAG}_full -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+ls -la gpurun_out | tail -20
