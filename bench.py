@@ -231,7 +231,7 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     p.set_stream(stream.cuda_stream)
     p.set_prefilter_kernel({"default": 0, "direct": 1, "table": 2}[args.prefilter])
-    p.set_three_tax_engine({"default": 0, "block": 1, "warp": 2}[args.tt_engine], args.tt_blocks_per_sm)
+    p.set_three_tax_engine({"default": 0, "block": 1, "warp": 2, "group": 3}[args.tt_engine], args.tt_blocks_per_sm)
     fp64_peak = p.measure_fp64_peak()
 
     # ---- device-resident arm -------------------------------------------------------------------
@@ -323,7 +323,7 @@ def run_ours(args):
     tt_tflops = tt_flops / (opt_ms * 1e-3) / 1e12 if opt_ms > 0 else 0.0
     engine = p.three_tax_engine_used()
     roofline_tt = {
-        "kernel": "tt_warp_kernel" if engine == 2 else "three_tax_kernel", "bound": "fp64", "achieved": tt_tflops, "peak": fp64_peak,
+        "kernel": {2: "tt_warp_kernel", 3: "tt_group_kernel"}.get(engine, "three_tax_kernel"), "bound": "fp64", "achieved": tt_tflops, "peak": fp64_peak,
         "unit": "TFLOP/s", "frac": tt_tflops / fp64_peak if fp64_peak else None,
         "peak_source": "DFMA micro-benchmark in this run (pp_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
         "algorithmic_flops_per_step": tt_flops, "ms_per_step": opt_ms,
@@ -335,7 +335,7 @@ def run_ours(args):
         "traffic": None,
         "note": "all second-stage launches of a step (baseball waves + refinement), timed together with their bookkeeping kernels",
     }
-    if engine != 2 or tt_work[:2].sum() == 0:
+    if engine == 1 or tt_work[:2].sum() == 0:
         roofline_tt["note"] += "; work counters exist for the warp engine only"
     dominant_tt = opt_ms >= pre_ms
     roofline = dict(roofline_tt if dominant_tt else roofline_prefilter)
@@ -383,8 +383,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prefilter", default="default", choices=["default", "direct", "table"],
                     help="prefilter kernel: library default, the FMA form, or the four-base table form")
-    ap.add_argument("--tt-engine", default="default", choices=["default", "block", "warp"],
-                    help="second-stage engine: library default, block-per-candidate, warp-per-candidate")
+    ap.add_argument("--tt-engine", default="default", choices=["default", "block", "warp", "group"],
+                    help="second-stage engine: library default (group), block-per-candidate, warp-per-candidate, block + shared-memory w")
     ap.add_argument("--tt-blocks-per-sm", type=int, default=0, help="cap on resident blocks of the warp engine (0 = max)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -179,9 +179,10 @@ int pp_set_prefilter_kernel(pp_ctx *, int32_t kernel);
 int pp_prefilter_kernel_used(pp_ctx *);
 
 /* Which engine runs the second stage (Three_tax.optimize / calc_marg_prob, three_tax.ml:70-83,169-215):
- * 0 = default (warp-per-candidate for the DNA Gamma-4 model, block-per-candidate otherwise),
- * 1 = block-per-candidate, 2 = warp-per-candidate.  blocks_per_sm > 0 caps the resident thread blocks
- * of the warp engine (8 candidates each); 0 = as many as fit.  pp_three_tax_engine_used: 1 or 2. */
+ * 0 = default (engine 3 for the DNA Gamma-4 model with the --pp integrals on engine 2; engine 1 otherwise),
+ * 1 = block-per-candidate (every model), 2 = warp-per-candidate, 3 = block-per-candidate with the cached
+ * (statd*prox*dist) product in shared memory.  blocks_per_sm > 0 caps the resident thread blocks of engine
+ * 2 (8 candidates each); 0 = default.  pp_three_tax_engine_used: 1, 2 or 3. */
 int pp_set_three_tax_engine(pp_ctx *, int32_t engine, int32_t blocks_per_sm);
 int pp_three_tax_engine_used(pp_ctx *);
 

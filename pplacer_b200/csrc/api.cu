@@ -23,6 +23,7 @@
 #include "query.cuh"
 #include "threetax.cuh"
 #include "threetax_warp.cuh"
+#include "threetax_group.cuh"
 
 using namespace ppb;
 
@@ -117,7 +118,8 @@ struct pp_ctx {
   int tt_blocks = 0;
   size_t tt_smem = 0;
   // warp-per-candidate engine (threetax_warp.cuh): DNA Gamma-4 only
-  int tt_engine = 0;          // pp_set_three_tax_engine: 0 default, 1 block-per-candidate, 2 warp-per-candidate
+  int tt_engine = 0;          // pp_set_three_tax_engine: 0 default, 1 block-per-candidate, 2 warp-per-candidate, 3 block + shared-memory w
+  int ttg_blocks = 0, ttg_ws = 0, ttg_variant = 0;
   int ttw_blocks_per_sm = 0;  // 0 = occupancy maximum
   int ttw_max_blocks = 0;
   DevBuf<int32_t> ord_keys, ord_vals, ord_keys2, ord_vals2;
@@ -125,6 +127,9 @@ struct pp_ctx {
 };
 
 constexpr int kTTWarpsPerBlock = 8;
+constexpr int kTTGroupWarps = 8;
+constexpr int kTTGroupDefaultVariant = 1;  // 0: 8 warps x 2 blocks/SM, 768 sites of w in shared memory; 1: 4 warps x 4 blocks/SM, 352 sites
+constexpr int kTTGroupSites = 768;   // sites of w kept in shared memory per candidate (the rest goes to the global overflow)
 constexpr int kTTWarpDefaultBlocks = 2;
 constexpr int kTTWarpDefaultFlags = 2;
 static bool ttw_supported(const pp_ctx *c) { return c->S == 4 && !c->gcat && c->R == 4; }
@@ -327,6 +332,11 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tt_warp_kernel<4, kTTWarpsPerBlock, 3, 1>, kTTWarpsPerBlock * 32, smw));
     c->ttw_max_blocks = std::max(per_sm, 2) * c->sm_count;
     w_slots = std::max(w_slots, (size_t)c->ttw_max_blocks * kTTWarpsPerBlock);
+    static const int variant = [] { const char *e = std::getenv("PPB_TTG_VARIANT"); return e ? std::atoi(e) : kTTGroupDefaultVariant; }();
+    c->ttg_variant = variant;
+    c->ttg_ws = std::min(variant == 1 ? 352 : kTTGroupSites, c->Lp);
+    c->ttg_blocks = (variant == 1 ? 4 : 2) * c->sm_count;
+    w_slots = std::max(w_slots, (size_t)c->ttg_blocks);
   }
   if ((rc = c->wbuf.ensure(w_slots * c->K * c->Lp)) != PP_OK) { pp_destroy(c); return rc; }
   CK(cudaStreamSynchronize(c->stream));
@@ -612,9 +622,10 @@ static int launch_three_tax_warp(pp_ctx *c, const CandIn *in, CandOut *out, int 
   const int32_t *order = nullptr;
   if (n > 1) {
     if ((rc = c->ord_keys.ensure(n)) || (rc = c->ord_vals.ensure(n)) || (rc = c->ord_keys2.ensure(n)) || (rc = c->ord_vals2.ensure(n))) return rc;
-    cand_keys_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(in, n, c->ord_keys.p, c->ord_vals.p); LAUNCH_CHECK(c);
-    int end_bit = 1;
-    while ((1 << end_bit) < c->n_nodes && end_bit < 31) ++end_bit;
+    int loc_bits = 1;
+    while ((1 << loc_bits) < c->n_nodes && loc_bits < 28) ++loc_bits;
+    const int end_bit = loc_bits + 2;
+    cand_keys_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(in, c->nq.p, n, c->L, loc_bits, c->ord_keys.p, c->ord_vals.p); LAUNCH_CHECK(c);
     size_t tmp = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->ord_keys.p, c->ord_keys2.p, c->ord_vals.p, c->ord_vals2.p, n, 0, end_bit, c->stream));
     if ((rc = c->ord_tmp.ensure(tmp))) return rc;
@@ -625,6 +636,23 @@ static int launch_three_tax_warp(pp_ctx *c, const CandIn *in, CandOut *out, int 
   // two builds of the kernel: <=128 registers (two blocks = 16 candidates per SM) and <=80 registers
   // (three blocks = 24 candidates per SM); ttw_blocks_per_sm picks (default kTTWarpDefaultBlocks)
   const int per_sm = c->ttw_blocks_per_sm > 0 ? std::min(c->ttw_blocks_per_sm, 3) : kTTWarpDefaultBlocks;
+  if (c->tt_engine != 2 && prm.mode != TT_MODE_MARGINAL) {  // block per candidate, w in shared memory
+    const int gblocks = std::min(c->ttg_blocks, n);
+    // the shared-memory attribute is per function, not per context: set it at every launch
+    if (c->ttg_variant == 1) {
+      const size_t smg = TTGroup<4, 4, 1>::smem_bytes(c->ttg_ws);
+      CK(cudaFuncSetAttribute(tt_group_kernel<4, 4, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smg));
+      tt_group_kernel<4, 4, 4, 1><<<gblocks, 128, smg, c->stream>>>(c->dm, c->g, c->d_bl, c->qsite.p, c->nq.p, in, order, out, n, prm,
+                                                                    c->wbuf.p, c->ttg_ws, c->counters.p, c->tt_work.p);
+    } else {
+      const size_t smg = TTGroup<4, kTTGroupWarps, 2>::smem_bytes(c->ttg_ws);
+      CK(cudaFuncSetAttribute(tt_group_kernel<4, kTTGroupWarps, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smg));
+      tt_group_kernel<4, kTTGroupWarps, 2, 2><<<gblocks, kTTGroupWarps * 32, smg, c->stream>>>(
+          c->dm, c->g, c->d_bl, c->qsite.p, c->nq.p, in, order, out, n, prm, c->wbuf.p, c->ttg_ws, c->counters.p, c->tt_work.p);
+    }
+    LAUNCH_CHECK(c);
+    return PP_OK;
+  }
   int blocks = std::min(c->ttw_max_blocks, per_sm * c->sm_count);
   blocks = std::min(blocks, (n + kTTWarpsPerBlock - 1) / kTTWarpsPerBlock);
   const size_t smw = TTWarp<4, 1>::smem_bytes(kTTWarpsPerBlock);
@@ -959,13 +987,13 @@ extern "C" int pp_set_prefilter_kernel(pp_ctx *c, int32_t kernel) {
 extern "C" int pp_prefilter_kernel_used(pp_ctx *c) { return c ? c->prefilter_kernel_used : -1; }
 
 extern "C" int pp_set_three_tax_engine(pp_ctx *c, int32_t engine, int32_t blocks_per_sm) {
-  if (!c || engine < 0 || engine > 2 || blocks_per_sm < 0) return fail(PP_EINVAL, "pp_set_three_tax_engine: engine must be 0, 1 or 2");
-  if (engine == 2 && !ttw_supported(c)) return fail(PP_EINVAL, "pp_set_three_tax_engine: the warp engine exists for the DNA Gamma-4 model only");
+  if (!c || engine < 0 || engine > 3 || blocks_per_sm < 0) return fail(PP_EINVAL, "pp_set_three_tax_engine: engine must be 0, 1, 2 or 3");
+  if (engine >= 2 && !ttw_supported(c)) return fail(PP_EINVAL, "pp_set_three_tax_engine: the warp engine exists for the DNA Gamma-4 model only");
   c->tt_engine = engine;
   c->ttw_blocks_per_sm = blocks_per_sm;
   return PP_OK;
 }
-extern "C" int pp_three_tax_engine_used(pp_ctx *c) { return !c ? -1 : (ttw_supported(c) && c->tt_engine != 1) ? 2 : 1; }
+extern "C" int pp_three_tax_engine_used(pp_ctx *c) { return !c ? -1 : !(ttw_supported(c) && c->tt_engine != 1) ? 1 : (c->tt_engine == 2 ? 2 : 3); }
 
 extern "C" int64_t pp_kernel_launches(pp_ctx *c, int32_t reset) {
   if (!c) return -1;

@@ -1,0 +1,583 @@
+// Second stage, block-per-candidate engine with the cached product IN SHARED MEMORY, for the
+// four-state Gamma-mixture model (Three_tax.optimize / log_like only; --pp stays on the warp engine).
+//   Three_tax.log_like / optimize   pplacer_src/three_tax.ml:30-83
+//   Model.log_like3    gmix_model.ml:298-304 -> ten_log_like3_c (linear_c.c:367-424)
+//   Model.evolve_into  gmix_model.ml:308-315 ; Diagd.multi_exp diagd.ml:79-98
+//
+// Why: three out of four objective calls move only the pendant length and need nothing but
+// w = (statd*prox_ev)*dist_ev (16 doubles per site).  With one warp per candidate (threetax_warp.cuh)
+// thousands of candidates are in flight, their w copies (250 MB) miss L2 and every pendant call
+// streams 128 B/site from HBM - measured 2.9 TB/s, the bound of that engine.  Here ONE THREAD BLOCK
+// (8 warps) owns a candidate: a thread owns the sites tid, tid+256, ..., w for those sites sits in
+// the block's shared memory (each thread reads back only what it wrote itself), and a pendant call
+// touches no global memory at all.  Only ~300 candidates are in flight, so the darr/parr planes they
+// gather (queue ordered by edge) stay in L2.
+//
+// Division of labour inside the block, per objective call:
+//   warp 0      runs the scalar optimiser (TTMachine, threetax.cuh) up to the next call that needs
+//               a pass over the sites - calls answered by the memo of batched values cost no barrier
+//               at all - and posts a COMMAND: which pass, and which rate-matrix sets to (re)build
+//   all warps   build the posted matrix sets cooperatively (one thread per entry), run the pass,
+//               and leave one partial sum per warp; warp 0 adds them in a fixed order.
+// Four block barriers per pass: command, exponentials, matrices, partial sums.
+#pragma once
+#include "threetax_warp.cuh"
+
+namespace ppb {
+
+struct GCand {  // per-candidate constants every thread keeps in registers
+  const double *dbase, *pbase;
+  const int32_t *qsite;
+  double *wg;  // global overflow of w for sites >= ws
+  int64_t Lp;
+  int nq, ws;
+};
+
+template <int R, int G, int TS>
+struct TTGroup : TTMachine<TTGroup<R, G, TS>> {
+  using Mach = TTMachine<TTGroup<R, G, TS>>;
+  using Mach::opt_init; using Mach::opt_advance; using Mach::b_kind; using Mach::req_x; using Mach::o_status;
+  static constexpr int S = 4, K = 4 * R, PM = 16 * R, NT = 32 * G;
+  static constexpr int PQS = 5 * K;  // pendant matrix set: rows [R*4][5] = P[rs][0..3], QN[rs] (row sum, for 'N')
+  static constexpr int NBP = 6, NBD = 4, MEMO = 8, MAXJOBS = 12;
+  static constexpr unsigned FULL = 0xffffffffu;
+  enum : int { CMD_DONE = 0, CMD_DIST1, CMD_PEND1_FUSED, CMD_PEND1_CACHED, CMD_DIST_BATCH, CMD_PEND_BATCH_FUSED, CMD_PEND_BATCH_CACHED };
+  // block-shared layout (doubles)
+  static constexpr int C_STATD = 0, C_LAM = 4, C_X = 8, C_XIT = 24, C_RATES = 40, C_TOTAL = (40 + R + 1) & ~1;
+  static constexpr int OFF_EX = C_TOTAL;                 // [MAXJOBS][K] exponentials of the posted builds
+  static constexpr int OFF_JBL = OFF_EX + MAXJOBS * K;   // [MAXJOBS] branch length of each build job
+  static constexpr int OFF_JOB = OFF_JBL + MAXJOBS;      // ints: [0] pass, [1] n_jobs, [2] queue slot, [4..] dst[MAXJOBS], qn[MAXJOBS]
+  static constexpr int OFF_OUT = OFF_JOB + 2 + MAXJOBS;  // [8] pass results
+  static constexpr int OFF_BAD = OFF_OUT + 8;            // [8] non-finite log terms per point
+  static constexpr int OFF_PART = OFF_BAD + 8;           // [G][8] per-warp partial sums
+  static constexpr int OFF_ESUM = OFF_PART + G * 8;      // [G] per-warp exponent sums
+  static constexpr int OFF_PQ = OFF_ESUM + G;            // current pendant set
+  static constexpr int OFF_PD = OFF_PQ + PQS;            // current distal P, then proximal P
+  static constexpr int OFF_PB = OFF_PD + 2 * PM;         // batch: pendant [NBP][PQS] | distal [NBD][2][PM]
+  static constexpr int PB_SIZE = NBP * PQS > NBD * 2 * PM ? NBP * PQS : NBD * 2 * PM;
+  static constexpr int OFF_MX = OFF_PB + PB_SIZE;        // memo: argument, proximal length, value
+  static constexpr int OFF_MA = OFF_MX + MEMO;
+  static constexpr int OFF_MF = OFF_MA + MEMO;
+  static constexpr int OFF_OBJ = OFF_MF + MEMO;          // warp 0's scalar state (this object)
+  static constexpr int OBJ_DOUBLES = 64;
+  static constexpr int OFF_W = OFF_OBJ + OBJ_DOUBLES;    // w[K][ws] for the first ws sites of the query
+  static_assert((PQS % 2) == 0 && (PM % 2) == 0 && (MEMO % 2) == 0 && (G % 2) == 0 && (MAXJOBS % 2) == 0 && (OFF_PD % 2) == 0 &&
+                (OFF_PB % 2) == 0, "double2 alignment of the matrix sets");
+
+  static __host__ __device__ constexpr size_t smem_bytes(int ws) { return sizeof(double) * ((size_t)OFF_W + (size_t)K * ws); }
+
+  // ---- scalar state: read and written by warp 0 only (all lanes store identical values) ----
+  double pend_bl, dist_bl, prox_bl;
+  double e_tot_ln2, rate_term, fval, cut_bl, start_pend, tol, max_pend;
+  int calls, calls_dist, max_iter;
+  int feed, attempt, status, optimise, final_pending;
+  bool w_stale, pq_dirty, pd_dirty;
+  int memo_n, memo_pending, memo_kind;  // memo_kind: -1 none, 0 pendant values, 1 distal values
+  int n_jobs;
+
+  __device__ __forceinline__ static double *SM() { return reinterpret_cast<double *>(ppb_ttw_smem); }
+  __device__ __forceinline__ static int *JOB() { return reinterpret_cast<int *>(SM() + OFF_JOB); }
+  __device__ __forceinline__ static int lane_id() { return threadIdx.x & 31; }
+  __device__ __forceinline__ static int warp_id() { return threadIdx.x >> 5; }
+
+  __device__ __forceinline__ static double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+  }
+
+  // ---- warp 0: build jobs and the memo ----
+  __device__ void add_job(double bl, int dst_off, int qn) {
+    __syncwarp();
+    if (lane_id() == 0) { SM()[OFF_JBL + n_jobs] = bl; JOB()[4 + n_jobs] = dst_off; JOB()[4 + MAXJOBS + n_jobs] = qn; }
+    __syncwarp();
+    ++n_jobs;
+  }
+  __device__ void memo_clear(int kind) { memo_n = 0; memo_pending = 0; memo_kind = kind; }
+  __device__ bool memo_get(int kind, double x, double aux, double *f) const {
+    if (memo_kind != kind) return false;
+    const double *s = SM();
+    for (int i = 0; i < memo_n; ++i)
+      if (s[OFF_MX + i] == x && s[OFF_MA + i] == aux) { *f = s[OFF_MF + i]; return true; }
+    return false;
+  }
+  // Brent's predictable first calls, several per pass (TTWarp::hint_prepare): posts the batch's build jobs
+  __device__ void hint_prepare(int kind, double left, double right, double start, double v) {
+    double *s = SM();
+    if (kind == OBJ_DIST) {
+      // replay the drift of cut = dist + prox over the seven calls (set_dist_bl, three_tax.ml:41-45)
+      memo_clear(1);
+      const double xs[7] = {left, right, start, left, right, start, v};
+      double cut = dist_bl + prox_bl, px[7];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        const double prox = cut - xs[i];
+        px[i] = prox;
+        if (prox >= 0.0) cut = xs[i] + prox;
+      }
+      const double bx[4] = {xs[0], xs[1], xs[2], xs[6]}, bp[4] = {px[0], px[1], px[2], px[6]};
+      __syncwarp();
+      if (lane_id() == 0) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { s[OFF_MX + b] = bx[b]; s[OFF_MA + b] = bp[b]; }
+      }
+      memo_pending = 4;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) { add_job(bx[b], OFF_PB + 2 * b * PM, 0); add_job(bp[b], OFF_PB + (2 * b + 1) * PM, 0); }
+    } else {
+      memo_clear(0);
+      const double mid = 0.5 * (left + right);
+      const double ee = (start < mid) ? right - start : -(start - left);
+      const double u1 = start + 0.3819660 * ee;  // Brent's first golden-section step (GSL min/brent.c)
+      const double bls[5] = {left, right, start, v, u1};
+      __syncwarp();
+      if (lane_id() == 0) {
+#pragma unroll
+        for (int b = 0; b < 5; ++b) { s[OFF_MX + b] = bls[b]; s[OFF_MA + b] = 0.0; }
+      }
+      memo_pending = 5;
+#pragma unroll
+      for (int b = 0; b < NBP; ++b) add_job(bls[b < 5 ? b : 4], OFF_PB + b * PQS, 1);
+    }
+  }
+  __device__ void hint_commit() {
+    double *s = SM();
+    __syncwarp();
+    if (lane_id() < memo_pending) s[OFF_MF + lane_id()] = s[OFF_OUT + lane_id()];
+    __syncwarp();
+    memo_n = memo_pending;
+    memo_pending = 0;
+  }
+
+  // core.ml:225-239 set_tt_edges / :240-245 tt_edges_default: branch lengths only (the sites are
+  // never gathered); the matrices are rebuilt lazily by the next pass that needs them
+  __device__ void reset_edges(double pendant, double distal) {
+    pend_bl = pendant; dist_bl = distal; prox_bl = cut_bl - distal;
+    pq_dirty = true; pd_dirty = true; w_stale = true;
+    memo_clear(-1);
+  }
+  __device__ void post(int pass, bool need_pq, bool need_pd) {
+    if (need_pq && pq_dirty) { add_job(pend_bl, OFF_PQ, 1); pq_dirty = false; }
+    if (need_pd && pd_dirty) { add_job(dist_bl, OFF_PD, 0); add_job(prox_bl, OFF_PD + PM, 0); pd_dirty = false; }
+    __syncwarp();
+    if (lane_id() == 0) { JOB()[0] = pass; JOB()[1] = n_jobs; }
+    __syncwarp();
+  }
+
+  // warp 0: advance the optimiser to the next call that needs a pass; returns false when the candidate is done
+  __device__ __forceinline__ bool scalar_step(bool first, double *ll_out) {
+    double *s = SM();
+    if (!first) {
+      // consume the pass just finished
+      if (final_pending) { *ll_out = s[OFF_OUT]; return false; }
+      if (feed != 2) { fval = -s[OFF_OUT]; feed = 1; }
+    }
+    n_jobs = 0;
+    for (;;) {
+      const int more = optimise ? opt_advance(feed, fval) : 0;
+      if (more == 2) {  // Brent's predictable calls: hint_prepare posted the batch's matrices
+        feed = 2;
+        if (memo_kind == 1) post(CMD_DIST_BATCH, true, false);
+        else if (w_stale) { post(CMD_PEND_BATCH_FUSED, false, true); w_stale = false; }
+        else post(CMD_PEND_BATCH_CACHED, false, false);
+        return true;
+      }
+      if (more == 0) {
+        if (optimise) {
+          status = o_status;
+          if (st_is_gsl(status) && attempt == 0) {  // core.ml:254-279: retry once from the default branch lengths
+            attempt = 1;
+            reset_edges(start_pend, cut_bl / 2.0);
+            opt_init(tol, max_pend, max_iter);
+            feed = 0;
+            n_jobs = 0;
+            continue;
+          }
+          if (status == ST_EXCEEDED_MAX_ITER) status = ST_OK;
+        }
+        final_pending = 1;  // Three_tax.get_results (three_tax.ml:85): log_like at the state left by the last call
+        post(CMD_DIST1, true, true);
+        return true;
+      }
+      // ---- TTDriver::objective, with calls answered by the memo costing no pass ----
+      const double x = req_x;
+      double val;
+      if (b_kind == OBJ_PEND) {
+        calls++;
+        pend_bl = x; pq_dirty = true;
+        if (memo_kind == 1) memo_kind = -1;
+        if (memo_get(0, x, 0.0, &val)) { fval = -val; feed = 1; continue; }
+        if (w_stale) { post(CMD_PEND1_FUSED, true, true); w_stale = false; } else post(CMD_PEND1_CACHED, true, false);
+        feed = 1;
+        return true;
+      }
+      calls++;
+      calls_dist++;
+      const double prox = (dist_bl + prox_bl) - x;
+      if (!(prox >= 0.0)) { fval = __longlong_as_double(0x7ff8000000000000LL); feed = 1; continue; }
+      const bool hit = memo_get(1, x, prox, &val);
+      dist_bl = x; prox_bl = prox; pd_dirty = true; w_stale = true;
+      if (memo_kind == 0) memo_kind = -1;
+      if (hit) { fval = -val; feed = 1; continue; }
+      post(CMD_DIST1, true, true);
+      feed = 1;
+      return true;
+    }
+  }
+
+  // ---- all threads: Diagd.multi_exp (diagd.ml:79-98; linear_c.c:92-146) for the posted jobs ----
+  __device__ __forceinline__ static void build_jobs(int n) {
+    double *s = SM();
+    const int *job = JOB();
+    const int tid = threadIdx.x;
+    for (int t = tid; t < n * K; t += NT) {
+      const int j = t / K, kk = t - j * K;
+      s[OFF_EX + t] = exp(s[C_RATES + (kk >> 2)] * s[OFF_JBL + j] * s[C_LAM + (kk & 3)]);
+    }
+    __syncthreads();
+    for (int t0 = 0; t0 < n * PM; t0 += NT) {  // uniform trip count: the shuffles below need whole warps
+      const int t = t0 + tid;
+      const bool on = t < n * PM;
+      const int j = on ? t / PM : 0, e = on ? t - j * PM : 0;
+      const int r = e >> 4, i = (e >> 2) & 3, c = e & 3;
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc = fma(s[OFF_EX + j * K + r * 4 + k] * s[C_X + i * 4 + k], s[C_XIT + c * 4 + k], acc);
+      const int qn = job[4 + MAXJOBS + j];
+      double *dst = s + job[4 + j];
+      if (on) dst[qn ? (e >> 2) * 5 + c : e] = acc;
+      // row sum ((0+P0)+P1)+P2)+P3 for the all-ones character (lanes 4m..4m+3 hold row m)
+      const double p1 = __shfl_down_sync(FULL, acc, 1), p2 = __shfl_down_sync(FULL, acc, 2), p3 = __shfl_down_sync(FULL, acc, 3);
+      if (on && qn && c == 0) dst[(e >> 2) * 5 + 4] = (((0.0 + acc) + p1) + p2) + p3;
+    }
+    __syncthreads();
+  }
+
+  struct RowCodes {
+    uint32_t mask;
+    int qcol;
+    bool fast;
+  };
+  __device__ __forceinline__ static RowCodes decode(int packed) {
+    RowCodes c;
+    c.mask = ((uint32_t)packed >> kSiteCodeShift) & 0x7f;
+    const bool single = (c.mask & (c.mask - 1)) == 0;
+    c.qcol = single ? __ffs(c.mask) - 1 : 4;
+    c.fast = __all_sync(FULL, single || c.mask == 15u);
+    return c;
+  }
+  __device__ __noinline__ static double q_slow(const double *set, int rs, uint32_t mask) {
+    const double *row = set + rs * 5;
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc = ((mask >> j) & 1u) ? acc + row[j] : acc;
+    return acc;
+  }
+
+  template <int T>
+  __device__ __forceinline__ static void site_w(const double *Pd, const double *Pp, const double (&d)[T][4], const double (&p)[T][4],
+                                                const double *st, double (&ww)[T][4]) {
+    const double2 *Pd2 = reinterpret_cast<const double2 *>(Pd), *Pp2 = reinterpret_cast<const double2 *>(Pp);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const double2 a0 = Pd2[s * 2], a1 = Pd2[s * 2 + 1], b0 = Pp2[s * 2], b1 = Pp2[s * 2 + 1];
+      const double sts = st[s];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        double de = fma(a0.x, d[t][0], 0.0), pe = fma(b0.x, p[t][0], 0.0);
+        de = fma(a0.y, d[t][1], de); pe = fma(b0.y, p[t][1], pe);
+        de = fma(a1.x, d[t][2], de); pe = fma(b1.x, p[t][2], pe);
+        de = fma(a1.y, d[t][3], de); pe = fma(b1.y, p[t][3], pe);
+        ww[t][s] = (sts * pe) * de;  // ((statd*x)*y), x = prox, y = dist (three_tax.ml:31-36)
+      }
+    }
+  }
+
+  // per-warp partial sums of the NB running products; warp 0 adds them (fixed order) after the barrier
+  template <int NB>
+  __device__ __forceinline__ void pass_end(const WarpProd (&lp)[NB]) {
+    double *s = SM();
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const double v = warp_sum(log(lp[b].m) + (double)lp[b].e * kLn2);
+      if (lane_id() == 0) s[OFF_PART + warp_id() * 8 + b] = v;
+    }
+    __syncthreads();
+    if (warp_id() == 0) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        double tot = 0.0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) tot += s[OFF_PART + g * 8 + b];
+        const double v = (tot + s[OFF_BAD + b]) - rate_term + e_tot_ln2;
+        __syncwarp();
+        if (lane_id() == 0) { s[OFF_OUT + b] = v; s[OFF_BAD + b] = 0.0; }
+      }
+      __syncwarp();
+    }
+  }
+
+  // Three_tax.log_like at NB (distal, proximal) pairs with the current pendant matrices
+  template <int NB, int T>
+  __device__ __forceinline__ void pass_dist(const GCand &c, int pm_off) {
+    double *s = SM();
+    const double *Pm = s + pm_off, *Pq = s + OFF_PQ, *st = s + C_STATD;
+    double *bad = s + OFF_BAD;
+    WarpProd lp[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) lp[b].init();
+    const int tid = threadIdx.x;
+    for (int base = 0; base < c.nq; base += NT * T) {
+      bool act[T], fast = true;
+      const double *dp[T], *pp[T], *Pqc[T];
+      uint32_t mask[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int i = base + t * NT + tid;
+        act[t] = i < c.nq;
+        const int packed = c.qsite[min(i, c.nq - 1)];
+        const RowCodes rc = decode(packed);
+        fast = fast && rc.fast;
+        mask[t] = rc.mask;
+        Pqc[t] = Pq + rc.qcol;
+        const int site = packed & kSiteMask;
+        dp[t] = c.dbase + site; pp[t] = c.pbase + site;
+      }
+      double u[T][NB];
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) u[t][b] = 0.0;
+#pragma unroll 1
+      for (int r = 0; r < R; ++r) {
+        double d[T][4], p[T][4], q[T][4];
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            d[t][k] = __ldg(dp[t] + (int64_t)(r * 4 + k) * c.Lp);
+            p[t][k] = __ldg(pp[t] + (int64_t)(r * 4 + k) * c.Lp);
+          }
+        if (fast) {
+#pragma unroll
+          for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[t][k] = Pqc[t][(r * 4 + k) * 5];
+        } else {
+#pragma unroll
+          for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[t][k] = q_slow(Pq, r * 4 + k, mask[t]);
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          double ww[T][4];
+          site_w<T>(Pm + b * 2 * PM + r * 16, Pm + b * 2 * PM + PM + r * 16, d, p, st, ww);
+#pragma unroll
+          for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) u[t][b] = fma(ww[t][k], q[t][k], u[t][b]);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+        if (act[t]) {
+#pragma unroll
+          for (int b = 0; b < NB; ++b) lp[b].mul(u[t][b], bad + b);
+        }
+    }
+    pass_end<NB>(lp);
+  }
+
+  // log_like at NB pendant lengths.  FUSED: recompute w from darr/parr and keep it (shared memory,
+  // global beyond ws sites); otherwise read it back.
+  template <int NB, bool FUSED, int T>
+  __device__ __forceinline__ void pass_pend(const GCand &c, int pq_off) {
+    double *s = SM();
+    const double *Pqm = s + pq_off, *Pd0 = s + OFF_PD, *st = s + C_STATD;
+    double *bad = s + OFF_BAD;
+    WarpProd lp[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) lp[b].init();
+    const int tid = threadIdx.x;
+    for (int base = 0; base < c.nq; base += NT * T) {
+      bool act[T], fast = true;
+      int iw[T];
+      const double *dp[T], *pp[T], *Pqc[T];
+      uint32_t mask[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int i = base + t * NT + tid;
+        act[t] = i < c.nq;
+        iw[t] = min(i, c.nq - 1);
+        const int packed = c.qsite[iw[t]];
+        const RowCodes rc = decode(packed);
+        fast = fast && rc.fast;
+        mask[t] = rc.mask;
+        Pqc[t] = Pqm + rc.qcol;
+        const int site = packed & kSiteMask;
+        dp[t] = c.dbase + site; pp[t] = c.pbase + site;
+      }
+      double u[T][NB];
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) u[t][b] = 0.0;
+#pragma unroll 1
+      for (int r = 0; r < R; ++r) {
+        double ww[T][4];
+        if (FUSED) {
+          double d[T][4], p[T][4];
+#pragma unroll
+          for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              d[t][k] = __ldg(dp[t] + (int64_t)(r * 4 + k) * c.Lp);
+              p[t][k] = __ldg(pp[t] + (int64_t)(r * 4 + k) * c.Lp);
+            }
+          site_w<T>(Pd0 + r * 16, Pd0 + PM + r * 16, d, p, st, ww);
+#pragma unroll
+          for (int t = 0; t < T; ++t)
+            if (act[t]) {
+              if (iw[t] < c.ws) {  // one branch per site, not per value
+                double *wp = SM() + OFF_W + (r * 4) * c.ws + iw[t];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) wp[k * c.ws] = ww[t][k];
+              } else {
+                double *wp = c.wg + (int64_t)(r * 4) * c.Lp + iw[t];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) __stcs(wp + (int64_t)k * c.Lp, ww[t][k]);
+              }
+            }
+        } else {
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            if (iw[t] < c.ws) {
+              const double *wp = SM() + OFF_W + (r * 4) * c.ws + iw[t];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) ww[t][k] = wp[k * c.ws];
+            } else {
+              const double *wp = c.wg + (int64_t)(r * 4) * c.Lp + iw[t];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) ww[t][k] = __ldcs(wp + (int64_t)k * c.Lp);
+            }
+          }
+        }
+        if (fast) {
+#pragma unroll
+          for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) u[t][b] = fma(ww[t][k], Pqc[t][b * PQS + (r * 4 + k) * 5], u[t][b]);
+        } else {
+#pragma unroll
+          for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) u[t][b] = fma(ww[t][k], q_slow(Pqm + b * PQS, r * 4 + k, mask[t]), u[t][b]);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+        if (act[t]) {
+#pragma unroll
+          for (int b = 0; b < NB; ++b) lp[b].mul(u[t][b], bad + b);
+        }
+    }
+    pass_end<NB>(lp);
+  }
+};
+
+// Persistent kernel: every BLOCK pulls candidates (in `order`: length class, then edge) until n are done.
+template <int R, int G, int MINB, int TS>
+__global__ void __launch_bounds__(G * 32, MINB)
+tt_group_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__restrict__ bl, const int32_t *__restrict__ qsite,
+                const int32_t *__restrict__ nq, const CandIn *__restrict__ in, const int32_t *__restrict__ order,
+                CandOut *__restrict__ out, int n, TTParams prm, double *__restrict__ wbuf, int ws, int *counter,
+                unsigned long long *__restrict__ work) {
+  using TT = TTGroup<R, G, TS>;
+  double *sm = reinterpret_cast<double *>(ppb_ttw_smem);
+  for (int i = threadIdx.x; i < 4; i += blockDim.x) { sm[TT::C_STATD + i] = m->statd[i]; sm[TT::C_LAM + i] = m->lam[i]; }
+  for (int i = threadIdx.x; i < 16; i += blockDim.x) { sm[TT::C_X + i] = m->x[i]; sm[TT::C_XIT + i] = m->xit[i]; }
+  for (int i = threadIdx.x; i < R; i += blockDim.x) sm[TT::C_RATES + i] = m->rates[i];
+  for (int i = threadIdx.x; i < 8; i += blockDim.x) sm[TT::OFF_BAD + i] = 0.0;
+  static_assert(sizeof(TT) <= TT::OBJ_DOUBLES * sizeof(double), "TTGroup object does not fit its shared slot");
+  TT &tt = *reinterpret_cast<TT *>(sm + TT::OFF_OBJ);  // warp 0 only
+  int *job = TT::JOB();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) job[2] = atomicAdd(counter, 1);
+    __syncthreads();
+    const int idx = job[2];
+    if (idx >= n) break;
+    const int ci = order ? order[idx] : idx;
+    const CandIn cin = in[ci];
+    GCand c;
+    c.qsite = qsite + (int64_t)cin.q * g.Lp;
+    c.nq = nq[cin.q];
+    c.dbase = g.a[0] + (int64_t)cin.loc * g.a_stride;
+    c.pbase = g.a[1] + (int64_t)cin.loc * g.a_stride;
+    c.Lp = g.Lp;
+    c.ws = ws;
+    c.wg = wbuf + (int64_t)blockIdx.x * TT::K * g.Lp;
+    {  // total_twoexp of the distal and proximal GLVs over the query's sites (gstar_support.ml:43-49)
+      const int32_t *ed = g.e[0] + (int64_t)cin.loc * g.Lp, *ep = g.e[1] + (int64_t)cin.loc * g.Lp;
+      long long es = 0;
+      for (int i = threadIdx.x; i < c.nq; i += TT::NT) {
+        const int site = c.qsite[i] & kSiteMask;
+        es += (long long)ed[site] + (long long)ep[site];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(0xffffffffu, es, o);
+      if (lane == 0) sm[TT::OFF_ESUM + warp] = (double)es;  // exact: |es| < 2^53
+    }
+    __syncthreads();
+    double ll = 0.0;
+    if (warp == 0) {
+      double tot = 0.0;
+#pragma unroll
+      for (int w = 0; w < G; ++w) tot += sm[TT::OFF_ESUM + w];
+      tt.e_tot_ln2 = kLn2 * tot;
+      tt.rate_term = (double)((float)c.nq) * log((double)((float)R));  // linear_c.c:421
+      tt.cut_bl = bl[cin.loc];
+      tt.start_pend = prm.start_pend; tt.tol = prm.tol; tt.max_pend = prm.max_pend; tt.max_iter = prm.max_iter;
+      tt.calls = 0; tt.calls_dist = 0; tt.feed = 0; tt.attempt = 0; tt.status = ST_OK; tt.final_pending = 0; tt.fval = 0.0;
+      tt.optimise = prm.mode == TT_MODE_OPTIMIZE;
+      tt.reset_edges(prm.use_defaults ? prm.start_pend : cin.pend0, prm.use_defaults ? tt.cut_bl / 2.0 : cin.dist0);
+      if (tt.optimise) tt.opt_init(prm.tol, prm.max_pend, prm.max_iter);
+    }
+    for (bool first = true;; first = false) {
+      if (warp == 0) {
+        if (!tt.scalar_step(first, &ll)) {
+          __syncwarp();
+          if (lane == 0) { job[0] = TT::CMD_DONE; job[1] = 0; }
+        }
+      }
+      __syncthreads();  // the command is posted
+      const int cmd = job[0], nj = job[1];
+      if (cmd == TT::CMD_DONE) break;
+      if (nj > 0) TT::build_jobs(nj);
+      switch (cmd) {
+        case TT::CMD_DIST1: tt.template pass_dist<1, TS>(c, TT::OFF_PD); break;
+        case TT::CMD_PEND1_FUSED: tt.template pass_pend<1, true, TS>(c, TT::OFF_PQ); break;
+        case TT::CMD_PEND1_CACHED: tt.template pass_pend<1, false, TS>(c, TT::OFF_PQ); break;
+        case TT::CMD_DIST_BATCH: tt.template pass_dist<TT::NBD, 1>(c, TT::OFF_PB); break;
+        case TT::CMD_PEND_BATCH_FUSED: tt.template pass_pend<TT::NBP, true, 1>(c, TT::OFF_PB); break;
+        default: tt.template pass_pend<TT::NBP, false, 1>(c, TT::OFF_PB); break;
+      }
+    }
+    if (threadIdx.x == 0) {
+      CandOut o;
+      o.marg = __longlong_as_double(0x7ff8000000000000LL);
+      o.ll = ll; o.pend = tt.pend_bl; o.dist = tt.dist_bl; o.status = tt.status; o.calls = tt.calls;
+      out[ci] = o;
+      const unsigned long long nd = tt.calls_dist, np = tt.calls - tt.calls_dist, ns = c.nq;
+      atomicAdd(work + 0, np); atomicAdd(work + 1, nd); atomicAdd(work + 2, np * ns); atomicAdd(work + 3, nd * ns);
+    }
+  }
+}
+
+}  // namespace ppb

@@ -30,16 +30,22 @@ struct WarpProd {
   double m;
   int e;
   __device__ __forceinline__ void init() { m = 1.0; e = 0; }
+  // zero / negative / NaN / inf / subnormal factor (rare): subnormals are rescaled exactly, the
+  // rest add log(u) = -inf / NaN / +inf to the point's shared slot and leave the product alone
+  __device__ __noinline__ static double special(double u, double *bad_slot, int *eadj) {
+    if (u > 0.0 && u < 2.2250738585072014e-308) { *eadj = -600; return u * 0x1p600; }
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    atomicAdd(bad_slot, u == 0.0 ? -inf : (u == inf ? inf : __longlong_as_double(0x7ff8000000000000LL)));  // linear_c.c:418 sums log(util)
+    *eadj = 0;
+    return 1.0;
+  }
   __device__ __forceinline__ void mul(double u, double *bad_slot) {
-    int hi = __double2hiint(u);
+    const int hi = __double2hiint(u);
     const int ef = (hi >> 20) & 0x7ff;
     if (hi < 0 || ef == 0 || ef == 0x7ff) {
-      if (u > 0.0 && ef == 0) { u *= 0x1p600; e -= 600; }   // subnormal: exact rescale
-      else {  // log(0) = -inf, log(negative) = log(NaN) = NaN, log(+inf) = +inf (linear_c.c:418 sums log(util))
-        const double inf = __longlong_as_double(0x7ff0000000000000LL);
-        atomicAdd(bad_slot, u == 0.0 ? -inf : (u == inf ? inf : __longlong_as_double(0x7ff8000000000000LL)));
-        return;
-      }
+      int adj;
+      u = special(u, bad_slot, &adj);
+      e += adj;
     }
     const double p = m * u;  // m in [1,2), u normal  =>  p normal, no overflow
     const int phi = __double2hiint(p);
@@ -52,9 +58,11 @@ extern __shared__ double2 ppb_ttw_smem[];
 
 // TS = sites per lane per iteration in the one-point passes of the optimiser
 template <int R, int TS>
-struct TTWarp : TTDriver<TTWarp<R, TS>> {
+struct TTWarp : TTDriver<TTWarp<R, TS>>, TTMachine<TTWarp<R, TS>> {
   using Base = TTDriver<TTWarp<R, TS>>;
+  using Mach = TTMachine<TTWarp<R, TS>>;
   using Base::pend_bl; using Base::dist_bl; using Base::prox_bl; using Base::calls;
+  using Mach::opt_init; using Mach::opt_advance; using Mach::b_kind; using Mach::req_x; using Mach::o_status;
   static constexpr int S = 4, K = 4 * R, PM = 16 * R;
   static constexpr int PQS = 5 * K;   // a pendant matrix set: rows [R*4][5] = P[rs][0..3] then QN[rs] (row sum, for 'N')
   static constexpr int NBP = 6;    // pendant points per pass
@@ -196,7 +204,7 @@ struct TTWarp : TTDriver<TTWarp<R, TS>> {
     c.fast = __all_sync(FULL, single || c.mask == 15u);
     return c;
   }
-  __device__ __forceinline__ static double q_slow(const double *set, int rs, uint32_t mask) {
+  __device__ __noinline__ static double q_slow(const double *set, int rs, uint32_t mask) {
     const double *row = set + rs * 5;
     double acc = 0.0;
 #pragma unroll
@@ -553,159 +561,6 @@ struct TTWarp : TTDriver<TTWarp<R, TS>> {
   }
 
 
-  // ---------------------------------------------------------------------------------------------
-  // Three_tax.optimize as a RESUMABLE state machine: the same statements as TTDriver::brent /
-  // ::optimize (threetax.cuh; minimization.ml:83-101, three_tax.ml:70-83, GSL min/brent.c), cut at
-  // every objective call, so that the kernel has ONE evaluation site and the optimiser's variables
-  // sit in this (shared-memory) object instead of being spilled around nine call sites.
-  //   opt_advance(0, -)  starts;  opt_advance(1, f) feeds the value of the requested call.
-  //   returns 1: evaluate objective(b_kind, req_x) next;  0: finished, status in o_status.
-  // ---------------------------------------------------------------------------------------------
-  enum : int { B_LEFT, B_RIGHT, B_START, B_LOWER, B_UPPER, B_MIN, B_V, B_ITER };
-  enum : int { O_PEND, O_DIST };
-  double b_left, b_right, b_tol, b_lefty, b_righty, b_smaller, b_miny, b_prev;
-  double b_xmin, b_xlo, b_xup, b_flo, b_fup, b_fmin, b_v, b_w, b_d, b_e, b_fv, b_fw, b_out, req_x;
-  int b_ph, b_kind, b_iter, b_step, b_max, b_status;
-  double o_prev_pend, o_prev_dist, o_curr_pend, o_curr_dist, o_tol, o_max_pend;
-  int o_ph, o_step, o_max_iter, o_status;
-
-  __device__ int brent_begin(int kind, double raw_start, double left, double right, double tolerance, int max_iters) {
-    b_kind = kind; b_left = left; b_right = right; b_tol = tolerance; b_max = max_iters;
-    if (left >= raw_start || raw_start >= right) { b_status = ST_INVALID_START; return 0; }
-    hint_prepare(kind, left, right, raw_start, left + 0.3819660 * (right - left));
-    b_prev = raw_start;
-    return 2;  // run the batched pass, then opt_advance(2, -)
-  }
-  __device__ int brent_done(int st) { b_status = st; return 0; }
-  __device__ int brent_feed(double fv) {
-    const double golden = 0.3819660;
-    switch (b_ph) {
-      case B_LEFT: b_lefty = fv; b_ph = B_RIGHT; req_x = b_right; return 1;
-      case B_RIGHT: {
-        b_righty = fv;
-        b_smaller = (b_lefty < b_righty) ? b_left : b_right;
-        double miny = fmin(b_lefty, b_righty);
-        if (b_lefty != b_lefty || b_righty != b_righty) miny = __longlong_as_double(0x7ff8000000000000LL);
-        b_miny = miny; b_iter = 1; b_ph = B_START; req_x = b_prev;
-        return 1;
-      }
-      case B_START: {
-        if (fv < b_miny) { b_xmin = b_prev; b_xlo = b_left; b_xup = b_right; b_ph = B_LOWER; req_x = b_xlo; return 1; }
-        if (fabs(b_prev - b_smaller) < b_tol) { b_out = b_smaller; return brent_done(ST_OK); }  // FoundMin
-        if (b_iter > b_max) return brent_done(ST_FIND_START_FAILURE);
-        b_prev = (b_prev + b_smaller) / 2.0; ++b_iter; req_x = b_prev;
-        return 1;
-      }
-      case B_LOWER: b_flo = fv; if (!isfinite(fv)) return brent_done(ST_GSL_EBADFUNC); b_ph = B_UPPER; req_x = b_xup; return 1;
-      case B_UPPER: b_fup = fv; if (!isfinite(fv)) return brent_done(ST_GSL_EBADFUNC); b_ph = B_MIN; req_x = b_xmin; return 1;
-      case B_MIN: {
-        b_fmin = fv;
-        if (!isfinite(fv)) return brent_done(ST_GSL_EBADFUNC);
-        if (b_xlo > b_xup) return brent_done(ST_GSL_EINVAL);
-        if (b_xmin >= b_xup || b_xmin <= b_xlo) return brent_done(ST_GSL_EINVAL);
-        if (b_fmin >= b_flo || b_fmin >= b_fup) return brent_done(ST_GSL_EINVAL);
-        b_v = b_xlo + golden * (b_xup - b_xlo); b_w = b_v; b_d = 0.0; b_e = 0.0;
-        b_ph = B_V; req_x = b_v;
-        return 1;
-      }
-      case B_V: {
-        if (!isfinite(fv)) return brent_done(ST_GSL_EBADFUNC);
-        b_fv = fv; b_fw = fv; b_step = 1;
-        break;
-      }
-      default: {  // B_ITER: the value at u
-        const double u = req_x, f_u = fv, z = b_xmin, f_z = b_fmin;
-        if (!isfinite(f_u)) return brent_done(ST_GSL_EBADFUNC);
-        if (f_u <= f_z) {
-          if (u < z) { b_xup = z; b_fup = f_z; } else { b_xlo = z; b_flo = f_z; }
-          b_v = b_w; b_fv = b_fw; b_w = z; b_fw = f_z; b_xmin = u; b_fmin = f_u;
-        } else {
-          if (u < z) { b_xlo = u; b_flo = f_u; } else { b_xup = u; b_fup = f_u; }
-          if (f_u <= b_fw || b_w == z) { b_v = b_w; b_fv = b_fw; b_w = u; b_fw = f_u; }
-          else if (f_u <= b_fv || b_v == z || b_v == b_w) { b_v = u; b_fv = f_u; }
-        }
-        if (b_xup - b_xlo < b_tol) { b_out = b_xmin; return brent_done(ST_OK); }
-        ++b_step;
-      }
-    }
-    // next iterate (GSL brent_iterate up to the function evaluation)
-    if (b_step > b_max) return brent_done(ST_EXCEEDED_MAX_ITER);
-    {
-      const double x_left = b_xlo, x_right = b_xup, z = b_xmin, f_z = b_fmin, v = b_v, wv = b_w, f_v = b_fv, f_w = b_fw;
-      double dd = b_e, ee = b_d;  // GSL: d = state->e; e = state->d
-      double u;
-      const double w_lower = z - x_left, w_upper = x_right - z;
-      const double tol = kSqrtDblEps * fabs(z);
-      double p = 0.0, q = 0.0, r = 0.0;
-      const double midpoint = 0.5 * (x_left + x_right);
-      if (fabs(ee) > tol) {
-        r = (z - wv) * (f_z - f_v);
-        q = (z - v) * (f_z - f_w);
-        p = (z - v) * q - (z - wv) * r;
-        q = 2.0 * (q - r);
-        if (q > 0.0) p = -p; else q = -q;
-        r = ee;
-        ee = dd;
-      }
-      if (fabs(p) < fabs(0.5 * q * r) && p < q * w_lower && p < q * w_upper) {
-        const double t2 = 2.0 * tol;
-        dd = p / q;
-        u = z + dd;
-        if ((u - x_left) < t2 || (x_right - u) < t2) dd = (z < midpoint) ? tol : -tol;
-      } else {
-        ee = (z < midpoint) ? x_right - z : -(z - x_left);
-        dd = golden * ee;
-      }
-      if (fabs(dd) >= tol) u = z + dd; else u = z + ((dd > 0.0) ? tol : -tol);
-      b_e = ee;
-      b_d = dd;
-      b_ph = B_ITER; req_x = u;
-    }
-    return 1;
-  }
-
-  __device__ void opt_init(double tolerance, double max_pend, int max_iter) {
-    o_tol = tolerance; o_max_pend = max_pend; o_max_iter = max_iter;
-    o_prev_pend = pend_bl; o_prev_dist = dist_bl; o_step = 1;
-  }
-  __device__ __forceinline__ int opt_advance(int feed, double fv) {
-    if (feed == 1) {
-      if (brent_feed(fv)) return 1;
-      goto after_brent;
-    }
-    if (feed == 2) { hint_commit(); b_ph = B_LEFT; req_x = b_left; return 1; }
-  round:
-    if (o_step > o_max_iter) { o_status = ST_EXCEEDED_MAX_ITER; return 0; }
-    o_curr_pend = pend_bl; o_curr_dist = dist_bl;
-    if (1e-8 != o_max_pend) {
-      o_ph = O_PEND;
-      if (brent_begin(OBJ_PEND, pend_bl, 1e-8, o_max_pend, o_tol, 100)) return 2;
-      goto after_brent;
-    }
-  start_dist:
-    {
-      const double cut = dist_bl + prox_bl;
-      if (0.0 != cut) {
-        o_ph = O_DIST;
-        if (brent_begin(OBJ_DIST, dist_bl, 0.0, cut, o_tol, 100)) return 2;
-        goto after_brent;
-      }
-    }
-    goto check;
-  after_brent:
-    if (b_status != ST_OK) { o_status = b_status; return 0; }
-    if (o_ph == O_PEND) { o_curr_pend = b_out; goto start_dist; }
-    o_curr_dist = b_out;
-  check:
-    if (fabs(o_prev_pend - o_curr_pend) > o_tol || fabs(o_prev_dist - o_curr_dist) > o_tol) {
-      o_prev_pend = o_curr_pend;
-      o_prev_dist = o_curr_dist;
-      ++o_step;
-      goto round;
-    }
-    o_status = ST_OK;
-    return 0;
-  }
   // One (query, edge) candidate in TT_MODE_OPTIMIZE / TT_MODE_LOGLIKE: Three_tax.optimize through the
   // state machine, the retry from the default branch lengths after a GSL error (core.ml:254-279,
   // tt_edges_default :240-245), then Three_tax.get_results (three_tax.ml:85).  Every likelihood pass
@@ -719,7 +574,6 @@ struct TTWarp : TTDriver<TTWarp<R, TS>> {
       const int more = optimise ? opt_advance(feed, f) : 0;
       if (more == 2) {  // Brent's predictable calls, several per pass
         if (memo_kind == 1) pass_dist<NBD, 1>(OFF_PB);
-        else if (flags & 1) pass_pend<NBP, 2, 1>(OFF_PB);
         else if (w_stale) { pass_pend<NBP, 1, 1>(OFF_PB); w_stale = false; }
         else pass_pend<NBP, 0, 1>(OFF_PB);
         feed = 2;
@@ -747,8 +601,7 @@ struct TTWarp : TTDriver<TTWarp<R, TS>> {
         set_pend(x);
         have = memo_get(0, x, 0.0, &val);
         if (!have) {
-          if (flags & 1) pass_pend<1, 2, TS>(OFF_PQ);
-          else if (w_stale) { pass_pend<1, 1, TS>(OFF_PQ); w_stale = false; }
+          if (w_stale) { pass_pend<1, 1, TS>(OFF_PQ); w_stale = false; }
           else pass_pend<1, 0, TS>(OFF_PQ);
         }
       } else {
@@ -854,10 +707,17 @@ tt_warp_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__rest
   }
 }
 
-// queue order: candidate indices sorted by edge (stable), so neighbours share GLV planes
-__global__ void cand_keys_kernel(const CandIn *__restrict__ in, int n, int32_t *__restrict__ keys, int32_t *__restrict__ vals) {
+// queue order: longest queries first (four length classes - a persistent warp that draws a long
+// candidate last would otherwise set the launch time), and by edge within a class (stable), so
+// that candidates running at the same time share darr/parr planes in L2
+__global__ void cand_keys_kernel(const CandIn *__restrict__ in, const int32_t *__restrict__ nq, int n, int L, int loc_bits,
+                                 int32_t *__restrict__ keys, int32_t *__restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { keys[i] = in[i].loc; vals[i] = i; }
+  if (i >= n) return;
+  const CandIn c = in[i];
+  const int cls = 3 - min(3, (4 * nq[c.q]) / (L + 1));
+  keys[i] = (cls << loc_bits) | c.loc;
+  vals[i] = i;
 }
 
 }  // namespace ppb

@@ -186,7 +186,7 @@ class Placer:
         return int(_lib.load().pp_prefilter_kernel_used(self.ctx))
 
     def set_three_tax_engine(self, engine: int, blocks_per_sm: int = 0):
-        """0 default, 1 block-per-candidate, 2 warp-per-candidate (DNA Gamma-4 only)."""
+        """0 default, 1 block-per-candidate, 2 warp-per-candidate, 3 block + shared-memory w (2, 3: DNA Gamma-4)."""
         _lib.check(_lib.load().pp_set_three_tax_engine(self.ctx, int(engine), int(blocks_per_sm)))
 
     def three_tax_engine_used(self) -> int:

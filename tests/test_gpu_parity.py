@@ -200,17 +200,20 @@ def test_place_matches_oracle(oracle_binding, name):
 
 @pytest.mark.parametrize("name,pp", [("c1_gtr", False), ("synth", False), ("c1_gtr", True)])
 def test_three_tax_engines_agree_and_match_oracle(oracle_binding, name, pp):
-    """The DNA Gamma-4 second stage has two engines: block-per-candidate (one objective value per
-    pass) and warp-per-candidate (values at points known in advance computed several per pass and
-    memoised).  Both restate the same Brent / QNG call sequence, so they must give the same
-    placements, the same number of objective calls, and both must match the oracle."""
+    """The DNA Gamma-4 second stage has three engines: 1 block-per-candidate (one objective value per
+    pass), 2 warp-per-candidate (values at points known in advance computed several per pass and
+    memoised; resumable Brent state machine), 3 block-per-candidate with the cached product in
+    shared memory (the default; --pp integrals run on engine 2).  All restate the same Brent / QNG
+    call sequence, so they must give the same placements, the same number of objective calls, and
+    each must match the oracle."""
     prob, o, p = setup(name, oracle_binding)
     sub = prob.query_chars[:12] if pp else prob.query_chars
     kw = dict(calc_pp=1, keep_at_most=20, keep_factor=0.001, max_strikes=20) if pp else {}
     exp, n_exp, st_exp, oinfo = o.place(sub, oracle_prefs(oracle_binding, prob, **kw), n_threads=4, debug=True)
     res = {}
     try:
-        for eng in (1, 2):
+        assert p.three_tax_engine_used() == 3
+        for eng in (1, 2, 3):
             p.set_three_tax_engine(eng)
             assert p.three_tax_engine_used() == eng
             got, n_got, st_got, info = p.place(sub, p.prefs(pp=pp), debug=True)
@@ -219,12 +222,14 @@ def test_three_tax_engines_agree_and_match_oracle(oracle_binding, name, pp):
             res[eng] = (got, n_got, st_got, info)
     finally:
         p.set_three_tax_engine(0)
-    (g1, n1, s1, i1), (g2, n2, s2, i2) = res[1], res[2]
-    assert np.array_equal(n1, n2) and np.array_equal(s1, s2)
-    assert_placements_match(g2, n2, s2, g1, n1, s1, pp=pp)
-    assert np.array_equal(i1["n_pitches"], i2["n_pitches"])
-    rel = np.abs(i1["n_like_calls"] - i2["n_like_calls"]) / np.maximum(i1["n_like_calls"], 1)
-    assert np.median(rel) <= 0.02 and rel.max() <= 0.25, (i1["n_like_calls"][:8], i2["n_like_calls"][:8])
+    g1, n1, s1, i1 = res[1]
+    for eng in (2, 3):
+        g2, n2, s2, i2 = res[eng]
+        assert np.array_equal(n1, n2) and np.array_equal(s1, s2)
+        assert_placements_match(g2, n2, s2, g1, n1, s1, pp=pp)
+        assert np.array_equal(i1["n_pitches"], i2["n_pitches"])
+        rel = np.abs(i1["n_like_calls"] - i2["n_like_calls"]) / np.maximum(i1["n_like_calls"], 1)
+        assert np.median(rel) <= 0.02 and rel.max() <= 0.25, (eng, i1["n_like_calls"][:8], i2["n_like_calls"][:8])
 
 
 @pytest.mark.parametrize("name", ["c1_gtr", "gcat_aa"])
