@@ -43,6 +43,10 @@ WORKLOADS = {
            "pplacer defaults (keep_at_most 7, max_strikes 6, max_pitches 40)", False, {}),
     "c4": (10_000, 4, "C4: 10k-taxon synthetic 16S tree (E=19997, mean branch length 0.002), 1500 columns, GTR+G4, synthetic reads 250-1500 columns",
            "pplacer defaults (keep_at_most 7, max_strikes 6, max_pitches 40)", False, {}),
+    # robustness check, not a BASELINE config: C4 with C2's branch lengths - the reference itself degenerates
+    # here; shows what the prefilter does when most site maxima sit far below 1
+    "c4_long": (10_000, 4, "C4 with mean branch length 0.05 (tree length ~1000: the reference's exponent pull stops, DESIGN.md 5b)",
+                "pplacer defaults", False, {}),
     "c5": (800, 2, "C5: C2 shape in posterior-probability mode",
            "-p --keep-at-most 40 (calc_pp, keep_factor 0.001, max_strikes 20)", True, {"keep_at_most": 40}),
 }

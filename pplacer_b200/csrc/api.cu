@@ -98,7 +98,7 @@ struct pp_ctx {
   TqPrimary tqp;
   DevBuf<uint8_t> qc;
   DevBuf<double> partial, MT;
-  DevBuf<int32_t> bad_edge;
+  DevBuf<int32_t> MTe;  // per (site, edge): (supernode exponent + table shift) << 1 | out-of-range flag
   int prefilter_choice = 0;       // pp_set_prefilter_kernel: 0 default, 1 direct, 2 table
   int prefilter_kernel_used = 0;  // 1 direct, 2 table (last run_prefilter)
   // workspace
@@ -119,7 +119,7 @@ struct pp_ctx {
   size_t tt_smem = 0;
   // warp-per-candidate engine (threetax_warp.cuh): DNA Gamma-4 only
   int tt_engine = 0;          // pp_set_three_tax_engine: 0 default, 1 block-per-candidate, 2 warp-per-candidate, 3 block + shared-memory w
-  int ttg_blocks = 0, ttg_ws = 0, ttg_variant = 0;
+  int ttg_blocks = 0, ttg_variant = 0;
   int ttw_blocks_per_sm = 0;  // 0 = occupancy maximum
   int ttw_max_blocks = 0;
   DevBuf<int32_t> ord_keys, ord_vals, ord_keys2, ord_vals2;
@@ -128,8 +128,7 @@ struct pp_ctx {
 
 constexpr int kTTWarpsPerBlock = 8;
 constexpr int kTTGroupWarps = 8;
-constexpr int kTTGroupDefaultVariant = 1;  // 0: 8 warps x 2 blocks/SM, 768 sites of w in shared memory; 1: 4 warps x 4 blocks/SM, 352 sites
-constexpr int kTTGroupSites = 768;   // sites of w kept in shared memory per candidate (the rest goes to the global overflow)
+constexpr int kTTGroupDefaultVariant = 1;  // 0: 8 warps x 2 blocks/SM, 768 sites of w in shared memory; 1: 4 warps x 4 blocks/SM, 256 sites; 2: 4 warps x 3 blocks/SM, 512 sites
 constexpr int kTTWarpDefaultBlocks = 2;
 constexpr int kTTWarpDefaultFlags = 2;
 static bool ttw_supported(const pp_ctx *c) { return c->S == 4 && !c->gcat && c->R == 4; }
@@ -180,7 +179,7 @@ extern "C" void pp_destroy(pp_ctx *c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (int w = 0; w < 3; ++w) { if (c->g.a[w]) cudaFree(c->g.a[w]); if (c->g.e[w]) cudaFree(c->g.e[w]); }
-  c->qc.release(); c->partial.release(); c->MT.release(); c->bad_edge.release();
+  c->qc.release(); c->partial.release(); c->MT.release(); c->MTe.release();
   void *ptrs[] = {c->snT_a, c->snT_e, c->dm, c->d_bl, c->d_code_of_char, c->d_ref_codes, c->d_site_cat, c->d_child_ptr, c->d_child_idx, c->d_parent, c->d_leaf_row};
   for (void *p : ptrs) if (p) cudaFree(p);
   c->chars.release(); c->codes.release(); c->sort_tmp.release(); c->qsite.release(); c->nq.release();
@@ -334,8 +333,7 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
     w_slots = std::max(w_slots, (size_t)c->ttw_max_blocks * kTTWarpsPerBlock);
     static const int variant = [] { const char *e = std::getenv("PPB_TTG_VARIANT"); return e ? std::atoi(e) : kTTGroupDefaultVariant; }();
     c->ttg_variant = variant;
-    c->ttg_ws = std::min(variant == 1 ? 352 : kTTGroupSites, c->Lp);
-    c->ttg_blocks = (variant == 1 ? 4 : 2) * c->sm_count;
+    c->ttg_blocks = (variant == 0 ? 2 : variant == 2 ? 3 : 4) * c->sm_count;
     w_slots = std::max(w_slots, (size_t)c->ttg_blocks);
   }
   if ((rc = c->wbuf.ensure(w_slots * c->K * c->Lp)) != PP_OK) { pp_destroy(c); return rc; }
@@ -560,17 +558,15 @@ template <int TE, int QT, int W>
 static int launch_prefilter_table(pp_ctx *c, int64_t Q, double pend, int blocks_per_sm) {
   int rc;
   if (c->mt_pend != pend) {  // four-base table: once per (reference, pendant length)
-    if ((rc = c->MT.ensure((size_t)c->L * 4 * c->Np)) || (rc = c->bad_edge.ensure(c->Np))) return rc;
-    CK(cudaMemsetAsync(c->bad_edge.p, 0, sizeof(int32_t) * c->Np, c->stream));
+    if ((rc = c->MT.ensure((size_t)c->L * 4 * c->Np)) || (rc = c->MTe.ensure((size_t)c->L * c->Np))) return rc;
     SnT sn; sn.a = c->snT_a; sn.e = c->snT_e; sn.Np = c->Np; sn.L = c->L; sn.K = c->K; sn.n_nodes = c->n_nodes;
-    mtable_kernel<16><<<dim3((unsigned)((c->Np + 127) / 128), c->L), 128, 0, c->stream>>>(sn, c->tqp, c->MT.p, c->bad_edge.p); LAUNCH_CHECK(c);
+    mtable_kernel<16><<<dim3((unsigned)((c->Np + 127) / 128), c->L), 128, 0, c->stream>>>(sn, c->tqp, c->MT.p, c->MTe.p); LAUNCH_CHECK(c);
     c->mt_pend = pend;
   }
   const PreGeom g = prefilter_geometry(c, Q, QT, TE, W, blocks_per_sm);
   PreArgs A;
   if ((rc = pack_codes<QT>(c, Q, g.nqt)) || (rc = prefilter_args(c, Q, g, &A))) return rc;
-  A.bad_edge = c->bad_edge.p;
-  prefilter_table_kernel<TE, QT, W><<<dim3(g.gx, g.gy, g.zs), W * 32, 0, c->stream>>>(A, c->MT.p); LAUNCH_CHECK(c);
+  prefilter_table_kernel<TE, QT, W><<<dim3(g.gx, g.gy, g.zs), W * 32, 0, c->stream>>>(A, c->MT.p, c->MTe.p); LAUNCH_CHECK(c);
   c->prefilter_kernel_used = 2;
   return prefilter_finish(c, Q, g);
 }
@@ -639,17 +635,17 @@ static int launch_three_tax_warp(pp_ctx *c, const CandIn *in, CandOut *out, int 
   if (c->tt_engine != 2 && prm.mode != TT_MODE_MARGINAL) {  // block per candidate, w in shared memory
     const int gblocks = std::min(c->ttg_blocks, n);
     // the shared-memory attribute is per function, not per context: set it at every launch
-    if (c->ttg_variant == 1) {
-      const size_t smg = TTGroup<4, 4, 1>::smem_bytes(c->ttg_ws);
-      CK(cudaFuncSetAttribute(tt_group_kernel<4, 4, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smg));
-      tt_group_kernel<4, 4, 4, 1><<<gblocks, 128, smg, c->stream>>>(c->dm, c->g, c->d_bl, c->qsite.p, c->nq.p, in, order, out, n, prm,
-                                                                    c->wbuf.p, c->ttg_ws, c->counters.p, c->tt_work.p);
-    } else {
-      const size_t smg = TTGroup<4, kTTGroupWarps, 2>::smem_bytes(c->ttg_ws);
-      CK(cudaFuncSetAttribute(tt_group_kernel<4, kTTGroupWarps, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smg));
-      tt_group_kernel<4, kTTGroupWarps, 2, 2><<<gblocks, kTTGroupWarps * 32, smg, c->stream>>>(
-          c->dm, c->g, c->d_bl, c->qsite.p, c->nq.p, in, order, out, n, prm, c->wbuf.p, c->ttg_ws, c->counters.p, c->tt_work.p);
-    }
+#define PPB_LAUNCH_GROUP(G_, MINB_, TS_, WS_)                                                                                   \
+  do {                                                                                                                          \
+    const size_t smg = TTGroup<4, G_, TS_, WS_>::smem_bytes();                                                                  \
+    CK(cudaFuncSetAttribute(tt_group_kernel<4, G_, MINB_, TS_, WS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smg));   \
+    tt_group_kernel<4, G_, MINB_, TS_, WS_><<<gblocks, G_ * 32, smg, c->stream>>>(c->dm, c->g, c->d_bl, c->qsite.p, c->nq.p, in, order, out, n, \
+                                                                                 prm, c->wbuf.p, c->counters.p, c->tt_work.p);  \
+  } while (0)
+    if (c->ttg_variant == 0) PPB_LAUNCH_GROUP(8, 2, 2, 768);
+    else if (c->ttg_variant == 2) PPB_LAUNCH_GROUP(4, 3, 1, 512);
+    else PPB_LAUNCH_GROUP(4, 4, 1, 256);
+#undef PPB_LAUNCH_GROUP
     LAUNCH_CHECK(c);
     return PP_OK;
   }

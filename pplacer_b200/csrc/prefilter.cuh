@@ -338,7 +338,7 @@ __global__ void combine_partials_kernel(const double *__restrict__ partial, doub
 // leaves the safe range of the deferred renormalisation.
 template <int K>
 __global__ void __launch_bounds__(128)
-mtable_kernel(const SnT sn, const TqPrimary tp, double *__restrict__ MT, int32_t *__restrict__ bad_edge) {
+mtable_kernel(const SnT sn, const TqPrimary tp, double *__restrict__ MT, int32_t *__restrict__ MTe) {
   const int64_t Np = sn.Np;
   const int e = blockIdx.x * 128 + threadIdx.x;
   const int site = blockIdx.y;
@@ -347,23 +347,43 @@ mtable_kernel(const SnT sn, const TqPrimary tp, double *__restrict__ MT, int32_t
   double v[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) v[k] = __ldg(col + (int64_t)k * Np);
-  unsigned bad = 0;
+  double M[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     double lo = tp.v[j][0] * v[0], hi = tp.v[j][K / 2] * v[K / 2];
 #pragma unroll
     for (int k = 1; k < K / 2; ++k) { lo = fma(tp.v[j][k], v[k], lo); hi = fma(tp.v[j][K / 2 + k], v[K / 2 + k], hi); }
-    const double M = lo + hi;
-    bad = max(bad, range_key(M));
-    MT[((int64_t)site * 4 + j) * Np + e] = M;
+    M[j] = lo + hi;
   }
-  if (bad >= kSafeSpan && e < sn.n_nodes) bad_edge[e] = 1;
+  // Per-(site, edge) power-of-two rescaling: the largest of the four entries goes to [1,2) and its
+  // exponent joins the supernode's own (exact, so the scores keep their bits).  Long trees leave site
+  // maxima hundreds of binary orders below 1 (the reference stops rescaling a site once a rate category
+  // has underflowed, gmix_model.ml:172-176); without this every such edge would fall out of the fast
+  // range.  Bit 0 of the stored word flags a (site, edge) whose entries still leave [2^-120, 2^120).
+  const double mx = fmax(fmax(M[0], M[1]), fmax(M[2], M[3]));
+  const int hi = __double2hiint(mx);
+  const int ef = (hi >> 20) & 0x7ff;
+  int shift = 0;
+  unsigned flag = 0;
+  if (hi >= 0 && ef != 0 && ef != 0x7ff) {
+    shift = max(-1000, min(1000, ef - 1023));
+    const double sc = __hiloint2double((1023 - shift) << 20, 0);  // 2^-shift, exact
+#pragma unroll
+    for (int j = 0; j < 4; ++j) M[j] *= sc;
+  } else
+    flag = 1;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (range_key(M[j]) >= kSafeSpan) flag = 1;
+    MT[((int64_t)site * 4 + j) * Np + e] = M[j];
+  }
+  MTe[(int64_t)site * Np + e] = ((__ldg(sn.e + (int64_t)site * Np + e) + shift) << 1) | (int)flag;
 }
 
 // grid / block exactly as prefilter_direct_kernel; MT[L][4][Np].
 template <int TE, int QT, int W>
 __global__ void __launch_bounds__(W * 32)
-prefilter_table_kernel(const PreArgs A, const double *__restrict__ MT) {
+prefilter_table_kernel(const PreArgs A, const double *__restrict__ MT, const int32_t *__restrict__ MTe) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int qt = blockIdx.x * W + warp;
   if (qt >= A.nqt) return;
@@ -378,6 +398,9 @@ prefilter_table_kernel(const PreArgs A, const double *__restrict__ MT) {
 #pragma unroll
     for (int a = 0; a < TE; ++a) { mm[b][a] = 1.0; ex[b][a] = 0; }
   int nren = 0, cnt = 0;
+  unsigned dead = 0;       // bit b*TE+a: (query b, edge a) met a negative / NaN / inf / subnormal factor -> exact path
+  unsigned dead_zero = 0;  // ... met a factor that is exactly 0 -> log-likelihood -inf (linear_c.c:532: log 0), unless `dead` too
+  static_assert(QT * TE <= 32, "one dead bit per (query, edge) of the thread");
   const uint8_t *qcp = A.qc + ((int64_t)qt * L) * QT;
   for (int site = s0; site < s1; ++site) {
     const CodeWords<QT> cw = load_codes<QT>(qcp + (int64_t)site * QT);
@@ -395,48 +418,102 @@ prefilter_table_kernel(const PreArgs A, const double *__restrict__ MT) {
         for (int a = 0; a < TE; ++a) M[j][a] = __ldg(row + (int64_t)j * Np + a);
       }
     }
+    int flagged = 0;  // bit a: this (site, edge) has entries outside the deferred-renormalisation range
     if constexpr (TE == 2) {
-      const int2 v = __ldg(reinterpret_cast<const int2 *>(A.sn.e + (int64_t)site * Np + e0));
-      es[0] = v.x; es[1] = v.y;
+      const int2 v = __ldg(reinterpret_cast<const int2 *>(MTe + (int64_t)site * Np + e0));
+      es[0] = v.x >> 1; es[1] = v.y >> 1;
+      flagged = (v.x & 1) | ((v.y & 1) << 1);
     } else {
 #pragma unroll
-      for (int a = 0; a < TE; ++a) es[a] = __ldg(A.sn.e + (int64_t)site * Np + e0 + a);
-    }
-#pragma unroll
-    for (int b = 0; b < QT; ++b) {
-      const unsigned code = cw.code(b);
-      if (code & 0x80u) continue;
-      double u[TE];
-      switch (code) {  // the DNA code IS the state mask (A=1, C=2, G=4, T=8)
-        case 1:
-#pragma unroll
-          for (int a = 0; a < TE; ++a) u[a] = M[0][a];
-          break;
-        case 2:
-#pragma unroll
-          for (int a = 0; a < TE; ++a) u[a] = M[1][a];
-          break;
-        case 4:
-#pragma unroll
-          for (int a = 0; a < TE; ++a) u[a] = M[2][a];
-          break;
-        case 8:
-#pragma unroll
-          for (int a = 0; a < TE; ++a) u[a] = M[3][a];
-          break;
-        default:  // ambiguity code: sum of the compatible columns, state order (linear_c.c:29-90 on a 0/1 vector)
-#pragma unroll
-          for (int a = 0; a < TE; ++a) {
-            double s = 0.0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (code >> j & 1u) s += M[j][a];
-            u[a] = s;
-          }
-          break;
+      for (int a = 0; a < TE; ++a) {
+        const int v = __ldg(MTe + (int64_t)site * Np + e0 + a);
+        es[a] = v >> 1;
+        flagged |= (v & 1) << a;
       }
+    }
+    if (!flagged) {  // the common case: exactly the unguarded loop
 #pragma unroll
-      for (int a = 0; a < TE; ++a) { mm[b][a] *= u[a]; ex[b][a] += es[a]; }
+      for (int b = 0; b < QT; ++b) {
+        const unsigned code = cw.code(b);
+        if (code & 0x80u) continue;
+        double u[TE];
+        switch (code) {  // the DNA code IS the state mask (A=1, C=2, G=4, T=8)
+          case 1:
+#pragma unroll
+            for (int a = 0; a < TE; ++a) u[a] = M[0][a];
+            break;
+          case 2:
+#pragma unroll
+            for (int a = 0; a < TE; ++a) u[a] = M[1][a];
+            break;
+          case 4:
+#pragma unroll
+            for (int a = 0; a < TE; ++a) u[a] = M[2][a];
+            break;
+          case 8:
+#pragma unroll
+            for (int a = 0; a < TE; ++a) u[a] = M[3][a];
+            break;
+          default:  // ambiguity code: sum of the compatible columns, state order (linear_c.c:29-90 on a 0/1 vector)
+#pragma unroll
+            for (int a = 0; a < TE; ++a) {
+              double s = 0.0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (code >> j & 1u) s += M[j][a];
+              u[a] = s;
+            }
+            break;
+        }
+#pragma unroll
+        for (int a = 0; a < TE; ++a) { mm[b][a] *= u[a]; ex[b][a] += es[a]; }
+      }
+    } else {
+#pragma unroll
+      for (int b = 0; b < QT; ++b) {
+        const unsigned code = cw.code(b);
+        if (code & 0x80u) continue;
+        double u[TE];
+        switch (code) {  // the DNA code IS the state mask (A=1, C=2, G=4, T=8)
+          case 1:
+#pragma unroll
+            for (int a = 0; a < TE; ++a) u[a] = M[0][a];
+            break;
+          case 2:
+#pragma unroll
+            for (int a = 0; a < TE; ++a) u[a] = M[1][a];
+            break;
+          case 4:
+#pragma unroll
+            for (int a = 0; a < TE; ++a) u[a] = M[2][a];
+            break;
+          case 8:
+#pragma unroll
+            for (int a = 0; a < TE; ++a) u[a] = M[3][a];
+            break;
+          default:  // ambiguity code: sum of the compatible columns, state order (linear_c.c:29-90 on a 0/1 vector)
+#pragma unroll
+            for (int a = 0; a < TE; ++a) {
+              double s = 0.0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (code >> j & 1u) s += M[j][a];
+              u[a] = s;
+            }
+            break;
+        }
+#pragma unroll
+        for (int a = 0; a < TE; ++a)
+          if ((flagged >> a) & 1) {  // pull the factor's own exponent out at once; non-normal factors kill the pair
+            const int hi = __double2hiint(u[a]);
+            const int ef = (hi >> 20) & 0x7ff;
+            if (u[a] == 0.0) { dead_zero |= 1u << (b * TE + a); u[a] = 1.0; }
+            else if (hi < 0 || ef == 0 || ef == 0x7ff) { dead |= 1u << (b * TE + a); u[a] = 1.0; }
+            else { ex[b][a] += ef - 1023; u[a] = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(u[a])); }
+          }
+#pragma unroll
+        for (int a = 0; a < TE; ++a) { mm[b][a] *= u[a]; ex[b][a] += es[a]; }
+      }
     }
     if ((++cnt & (kRenormEvery - 1)) == 0) {
       ++nren;
@@ -459,7 +536,8 @@ prefilter_table_kernel(const PreArgs A, const double *__restrict__ MT) {
       if (e >= A.sn.n_nodes) continue;
       renorm(mm[b][a], ex[b][a]);
       double v = log(mm[b][a]) + kLn2 * (double)(ex[b][a] - 1023 * nren);
-      if (A.bad_edge[e]) v = exact_partial_score<4, false>(A, qt, QT, b, e, s0, s1);
+      if ((dead >> (b * TE + a)) & 1u) v = exact_partial_score<4, false>(A, qt, QT, b, e, s0, s1);  // -inf / NaN as linear_c.c:532
+      else if ((dead_zero >> (b * TE + a)) & 1u) v = -__longlong_as_double(0x7ff0000000000000LL);
       v -= rate_term;
       if (A.zs == 1 && e == A.root_id) v = __longlong_as_double(0x7ff8000000000000LL);
       outz[(int64_t)q * A.sn.n_nodes + e] = v;

@@ -28,14 +28,15 @@ namespace ppb {
 struct GCand {  // per-candidate constants every thread keeps in registers
   const double *dbase, *pbase;
   const int32_t *qsite;
-  double *wg;  // global overflow of w for sites >= ws
+  double *wg;  // global overflow of w for sites >= WS
   int64_t Lp;
-  int nq, ws;
+  int nq;
 };
 
-template <int R, int G, int TS>
-struct TTGroup : TTMachine<TTGroup<R, G, TS>> {
-  using Mach = TTMachine<TTGroup<R, G, TS>>;
+// G warps per candidate, TS sites per thread per iteration in the one-point passes, WS sites of w in shared memory
+template <int R, int G, int TS, int WS>
+struct TTGroup : TTMachine<TTGroup<R, G, TS, WS>> {
+  using Mach = TTMachine<TTGroup<R, G, TS, WS>>;
   using Mach::opt_init; using Mach::opt_advance; using Mach::b_kind; using Mach::req_x; using Mach::o_status;
   static constexpr int S = 4, K = 4 * R, PM = 16 * R, NT = 32 * G;
   static constexpr int PQS = 5 * K;  // pendant matrix set: rows [R*4][5] = P[rs][0..3], QN[rs] (row sum, for 'N')
@@ -60,11 +61,12 @@ struct TTGroup : TTMachine<TTGroup<R, G, TS>> {
   static constexpr int OFF_MF = OFF_MA + MEMO;
   static constexpr int OFF_OBJ = OFF_MF + MEMO;          // warp 0's scalar state (this object)
   static constexpr int OBJ_DOUBLES = 64;
-  static constexpr int OFF_W = OFF_OBJ + OBJ_DOUBLES;    // w[K][ws] for the first ws sites of the query
+  static constexpr int OFF_W = OFF_OBJ + OBJ_DOUBLES;    // w[K][WS] for the first WS sites of the query
+  static_assert(WS % NT == 0, "an iteration's sites are all in shared memory or all in the global overflow");
   static_assert((PQS % 2) == 0 && (PM % 2) == 0 && (MEMO % 2) == 0 && (G % 2) == 0 && (MAXJOBS % 2) == 0 && (OFF_PD % 2) == 0 &&
                 (OFF_PB % 2) == 0, "double2 alignment of the matrix sets");
 
-  static __host__ __device__ constexpr size_t smem_bytes(int ws) { return sizeof(double) * ((size_t)OFF_W + (size_t)K * ws); }
+  static __host__ __device__ constexpr size_t smem_bytes() { return sizeof(double) * ((size_t)OFF_W + (size_t)K * WS); }
 
   // ---- scalar state: read and written by warp 0 only (all lanes store identical values) ----
   double pend_bl, dist_bl, prox_bl;
@@ -423,7 +425,7 @@ struct TTGroup : TTMachine<TTGroup<R, G, TS>> {
       for (int t = 0; t < T; ++t)
 #pragma unroll
         for (int b = 0; b < NB; ++b) u[t][b] = 0.0;
-#pragma unroll 1
+#pragma unroll(!FUSED && NB == 1 ? R : 1)
       for (int r = 0; r < R; ++r) {
         double ww[T][4];
         if (FUSED) {
@@ -439,10 +441,10 @@ struct TTGroup : TTMachine<TTGroup<R, G, TS>> {
 #pragma unroll
           for (int t = 0; t < T; ++t)
             if (act[t]) {
-              if (iw[t] < c.ws) {  // one branch per site, not per value
-                double *wp = SM() + OFF_W + (r * 4) * c.ws + iw[t];
+              if (base + t * NT < WS) {  // block-uniform: WS is a multiple of the block size
+                double *wp = SM() + OFF_W + (r * 4) * WS + iw[t];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) wp[k * c.ws] = ww[t][k];
+                for (int k = 0; k < 4; ++k) wp[k * WS] = ww[t][k];
               } else {
                 double *wp = c.wg + (int64_t)(r * 4) * c.Lp + iw[t];
 #pragma unroll
@@ -452,10 +454,10 @@ struct TTGroup : TTMachine<TTGroup<R, G, TS>> {
         } else {
 #pragma unroll
           for (int t = 0; t < T; ++t) {
-            if (iw[t] < c.ws) {
-              const double *wp = SM() + OFF_W + (r * 4) * c.ws + iw[t];
+            if (base + t * NT < WS) {
+              const double *wp = SM() + OFF_W + (r * 4) * WS + iw[t];
 #pragma unroll
-              for (int k = 0; k < 4; ++k) ww[t][k] = wp[k * c.ws];
+              for (int k = 0; k < 4; ++k) ww[t][k] = wp[k * WS];
             } else {
               const double *wp = c.wg + (int64_t)(r * 4) * c.Lp + iw[t];
 #pragma unroll
@@ -491,13 +493,13 @@ struct TTGroup : TTMachine<TTGroup<R, G, TS>> {
 };
 
 // Persistent kernel: every BLOCK pulls candidates (in `order`: length class, then edge) until n are done.
-template <int R, int G, int MINB, int TS>
+template <int R, int G, int MINB, int TS, int WS>
 __global__ void __launch_bounds__(G * 32, MINB)
 tt_group_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__restrict__ bl, const int32_t *__restrict__ qsite,
                 const int32_t *__restrict__ nq, const CandIn *__restrict__ in, const int32_t *__restrict__ order,
-                CandOut *__restrict__ out, int n, TTParams prm, double *__restrict__ wbuf, int ws, int *counter,
+                CandOut *__restrict__ out, int n, TTParams prm, double *__restrict__ wbuf, int *counter,
                 unsigned long long *__restrict__ work) {
-  using TT = TTGroup<R, G, TS>;
+  using TT = TTGroup<R, G, TS, WS>;
   double *sm = reinterpret_cast<double *>(ppb_ttw_smem);
   for (int i = threadIdx.x; i < 4; i += blockDim.x) { sm[TT::C_STATD + i] = m->statd[i]; sm[TT::C_LAM + i] = m->lam[i]; }
   for (int i = threadIdx.x; i < 16; i += blockDim.x) { sm[TT::C_X + i] = m->x[i]; sm[TT::C_XIT + i] = m->xit[i]; }
@@ -521,7 +523,6 @@ tt_group_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__res
     c.dbase = g.a[0] + (int64_t)cin.loc * g.a_stride;
     c.pbase = g.a[1] + (int64_t)cin.loc * g.a_stride;
     c.Lp = g.Lp;
-    c.ws = ws;
     c.wg = wbuf + (int64_t)blockIdx.x * TT::K * g.Lp;
     {  // total_twoexp of the distal and proximal GLVs over the query's sites (gstar_support.ml:43-49)
       const int32_t *ed = g.e[0] + (int64_t)cin.loc * g.Lp, *ep = g.e[1] + (int64_t)cin.loc * g.Lp;

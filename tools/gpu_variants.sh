@@ -2,8 +2,8 @@
 set -u
 TAG=${1:-v}
 mkdir -p gpurun_out
-for V in 1 0; do
-PPB_TTG_VARIANT=$V timeout 150 python -m pytest tests -m gpu -x -q -k "engines_agree or c2_properties" > gpurun_out/${TAG}_pytest_v$V.log 2>&1; echo "variant $V pytest rc=$? $(tail -1 gpurun_out/${TAG}_pytest_v$V.log)"
+for V in 1 2 0; do
+PPB_TTG_VARIANT=$V timeout 150 python -m pytest tests -m gpu -x -q -k "engines_agree or c2_properties or edge_cases" > gpurun_out/${TAG}_pytest_v$V.log 2>&1; echo "variant $V pytest rc=$? $(tail -1 gpurun_out/${TAG}_pytest_v$V.log)"
 PPB_TTG_VARIANT=$V timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_v$V.json 2> gpurun_out/${TAG}_bench_v$V.err
 python - <<PY
 import json
@@ -13,4 +13,3 @@ except Exception as e: print("parse failed", e)
 PY
 tail -2 gpurun_out/${TAG}_bench_v$V.err
 done
-PPB_TTG_VARIANT=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:'tt_group_kernel' -c 1 -o gpurun_out/${TAG}_full_ttgroup -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
