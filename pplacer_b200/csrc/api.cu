@@ -120,6 +120,7 @@ struct pp_ctx {
   // warp-per-candidate engine (threetax_warp.cuh): DNA Gamma-4 only
   int tt_engine = 0;          // pp_set_three_tax_engine: 0 default, 1 block-per-candidate, 2 warp-per-candidate, 3 block + shared-memory w
   int ttg_blocks = 0, ttg_variant = 0;
+  bool ttg_pp = true;  // --pp integrals on the block engine (PPB_TTG_PP=0: on the warp engine)
   int ttw_blocks_per_sm = 0;  // 0 = occupancy maximum
   int ttw_max_blocks = 0;
   DevBuf<int32_t> ord_keys, ord_vals, ord_keys2, ord_vals2;
@@ -333,6 +334,9 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
     w_slots = std::max(w_slots, (size_t)c->ttw_max_blocks * kTTWarpsPerBlock);
     static const int variant = [] { const char *e = std::getenv("PPB_TTG_VARIANT"); return e ? std::atoi(e) : kTTGroupDefaultVariant; }();
     c->ttg_variant = variant;
+    static const bool pp_on_group = [] { const char *e = std::getenv("PPB_TTG_PP"); return e ? std::atoi(e) != 0 : true; }();
+    c->ttg_pp = pp_on_group;
+    w_slots = std::max(w_slots, (size_t)4 * c->sm_count);
     c->ttg_blocks = (variant == 0 ? 2 : variant == 2 ? 3 : 4) * c->sm_count;
     w_slots = std::max(w_slots, (size_t)c->ttg_blocks);
   }
@@ -632,6 +636,15 @@ static int launch_three_tax_warp(pp_ctx *c, const CandIn *in, CandOut *out, int 
   // two builds of the kernel: <=128 registers (two blocks = 16 candidates per SM) and <=80 registers
   // (three blocks = 24 candidates per SM); ttw_blocks_per_sm picks (default kTTWarpDefaultBlocks)
   const int per_sm = c->ttw_blocks_per_sm > 0 ? std::min(c->ttw_blocks_per_sm, 3) : kTTWarpDefaultBlocks;
+  if (c->tt_engine != 2 && prm.mode == TT_MODE_MARGINAL && c->ttg_pp) {  // --pp on the block engine
+    const int gblocks = std::min(4 * c->sm_count, n);
+    const size_t smg = TTGroup<4, 4, 1, 256>::smem_bytes();
+    CK(cudaFuncSetAttribute(tt_group_pp_kernel<4, 4, 4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smg));
+    tt_group_pp_kernel<4, 4, 4, 256><<<gblocks, 128, smg, c->stream>>>(c->dm, c->g, c->d_bl, c->qsite.p, c->nq.p, in, order, out, n, prm,
+                                                                       c->wbuf.p, c->counters.p);
+    LAUNCH_CHECK(c);
+    return PP_OK;
+  }
   if (c->tt_engine != 2 && prm.mode != TT_MODE_MARGINAL) {  // block per candidate, w in shared memory
     const int gblocks = std::min(c->ttg_blocks, n);
     // the shared-memory attribute is per function, not per context: set it at every launch

@@ -35,12 +35,14 @@ struct GCand {  // per-candidate constants every thread keeps in registers
 
 // G warps per candidate, TS sites per thread per iteration in the one-point passes, WS sites of w in shared memory
 template <int R, int G, int TS, int WS>
-struct TTGroup : TTMachine<TTGroup<R, G, TS, WS>> {
+struct TTGroup : TTDriver<TTGroup<R, G, TS, WS>>, TTMachine<TTGroup<R, G, TS, WS>> {
+  using Drv = TTDriver<TTGroup<R, G, TS, WS>>;
   using Mach = TTMachine<TTGroup<R, G, TS, WS>>;
+  using Drv::pend_bl; using Drv::dist_bl; using Drv::prox_bl; using Drv::calls;
   using Mach::opt_init; using Mach::opt_advance; using Mach::b_kind; using Mach::req_x; using Mach::o_status;
   static constexpr int S = 4, K = 4 * R, PM = 16 * R, NT = 32 * G;
   static constexpr int PQS = 5 * K;  // pendant matrix set: rows [R*4][5] = P[rs][0..3], QN[rs] (row sum, for 'N')
-  static constexpr int NBP = 6, NBD = 4, MEMO = 8, MAXJOBS = 12;
+  static constexpr int NBP = 6, NBD = 4, MEMO = 24, MAXJOBS = 12;
   static constexpr unsigned FULL = 0xffffffffu;
   enum : int { CMD_DONE = 0, CMD_DIST1, CMD_PEND1_FUSED, CMD_PEND1_CACHED, CMD_DIST_BATCH, CMD_PEND_BATCH_FUSED, CMD_PEND_BATCH_CACHED };
   // block-shared layout (doubles)
@@ -60,7 +62,7 @@ struct TTGroup : TTMachine<TTGroup<R, G, TS, WS>> {
   static constexpr int OFF_MA = OFF_MX + MEMO;
   static constexpr int OFF_MF = OFF_MA + MEMO;
   static constexpr int OFF_OBJ = OFF_MF + MEMO;          // warp 0's scalar state (this object)
-  static constexpr int OBJ_DOUBLES = 64;
+  static constexpr int OBJ_DOUBLES = 96;
   static constexpr int OFF_W = OFF_OBJ + OBJ_DOUBLES;    // w[K][WS] for the first WS sites of the query
   static_assert(WS % NT == 0, "an iteration's sites are all in shared memory or all in the global overflow");
   static_assert((PQS % 2) == 0 && (PM % 2) == 0 && (MEMO % 2) == 0 && (G % 2) == 0 && (MAXJOBS % 2) == 0 && (OFF_PD % 2) == 0 &&
@@ -69,9 +71,9 @@ struct TTGroup : TTMachine<TTGroup<R, G, TS, WS>> {
   static __host__ __device__ constexpr size_t smem_bytes() { return sizeof(double) * ((size_t)OFF_W + (size_t)K * WS); }
 
   // ---- scalar state: read and written by warp 0 only (all lanes store identical values) ----
-  double pend_bl, dist_bl, prox_bl;
   double e_tot_ln2, rate_term, fval, cut_bl, start_pend, tol, max_pend;
-  int calls, calls_dist, max_iter;
+  int calls_dist, max_iter;
+  GCand cand;  // warp 0's copy, for the nested --pp driver
   int feed, attempt, status, optimise, final_pending;
   bool w_stale, pq_dirty, pd_dirty;
   int memo_n, memo_pending, memo_kind;  // memo_kind: -1 none, 0 pendant values, 1 distal values
@@ -490,6 +492,96 @@ struct TTGroup : TTMachine<TTGroup<R, G, TS, WS>> {
     }
     pass_end<NB>(lp);
   }
+
+  // ---------------------------------------------------------------------------------------------
+  // --pp on this engine: warp 0 runs TTDriver::calc_marg_prob (nested Brent / QNG, ordinary calls)
+  // and every objective value it needs is a BLOCKING request: post the command, then execute it
+  // together with the other warps, which sit in a loop on run_command() until CMD_DONE.
+  // ---------------------------------------------------------------------------------------------
+  __device__ __noinline__ bool run_command(const GCand &c) {
+    __syncthreads();  // the command is posted
+    const int cmd = JOB()[0], nj = JOB()[1];
+    if (cmd == CMD_DONE) return false;
+    if (nj > 0) build_jobs(nj);
+    switch (cmd) {
+      case CMD_DIST1: pass_dist<1, 1>(c, OFF_PD); break;
+      case CMD_PEND1_FUSED: pass_pend<1, true, 1>(c, OFF_PQ); break;
+      case CMD_PEND1_CACHED: pass_pend<1, false, 1>(c, OFF_PQ); break;
+      case CMD_DIST_BATCH: pass_dist<NBD, 1>(c, OFF_PB); break;
+      case CMD_PEND_BATCH_FUSED: pass_pend<NBP, true, 1>(c, OFF_PB); break;
+      default: pass_pend<NBP, false, 1>(c, OFF_PB); break;
+    }
+    return true;
+  }
+  __device__ void post_done() {
+    __syncwarp();
+    if (lane_id() == 0) { JOB()[0] = CMD_DONE; JOB()[1] = 0; }
+    __syncwarp();
+  }
+  __device__ double pend_now() {  // log_like at the current branch lengths through a pendant pass
+    n_jobs = 0;
+    if (w_stale) { post(CMD_PEND1_FUSED, true, true); w_stale = false; } else post(CMD_PEND1_CACHED, true, false);
+    run_command(cand);
+    return SM()[OFF_OUT];
+  }
+  // TTDriver engine interface (warp 0 only)
+  __device__ double f_pend(double v) {
+    pend_bl = v; pq_dirty = true;
+    if (memo_kind == 1) memo_kind = -1;
+    double f;
+    if (memo_get(0, v, 0.0, &f)) return f;
+    return pend_now();
+  }
+  __device__ double f_dist(double d, double p) {
+    double f;
+    const bool hit = memo_get(1, d, p, &f);
+    set_dist_prox(d, p);
+    if (hit) return f;
+    n_jobs = 0;
+    post(CMD_DIST1, true, true);
+    run_command(cand);
+    return SM()[OFF_OUT];
+  }
+  __device__ void set_dist_prox(double d, double p) {
+    dist_bl = d; prox_bl = p; pd_dirty = true; w_stale = true;
+    if (memo_kind == 0) memo_kind = -1;
+  }
+  __device__ void cache_w() {}  // lazy: the next pendant pass after a distal move recomputes w (fused)
+  __device__ double eval_full_cache() { return pend_now(); }
+  __device__ void hint_brent(int kind, double left, double right, double start, double v) {
+    n_jobs = 0;
+    hint_prepare(kind, left, right, start, v);
+    if (memo_kind == 1) post(CMD_DIST_BATCH, true, false);
+    else if (w_stale) { post(CMD_PEND_BATCH_FUSED, false, true); w_stale = false; }
+    else post(CMD_PEND_BATCH_CACHED, false, false);
+    run_command(cand);
+    hint_commit();
+  }
+  // QNG announces each rule's abscissae before evaluating them: six per pass
+  __device__ void hint_begin() { memo_clear(0); }
+  __device__ void hint_add(double x) {
+    const int at = memo_n + memo_pending;
+    if (at >= MEMO) return;
+    __syncwarp();
+    if (lane_id() == 0) { SM()[OFF_MX + at] = x; SM()[OFF_MA + at] = 0.0; }
+    __syncwarp();
+    ++memo_pending;
+  }
+  __device__ void hint_flush() {
+    double *s = SM();
+    while (memo_pending > 0) {
+      const int n = memo_pending < NBP ? memo_pending : NBP;
+      n_jobs = 0;
+      for (int b = 0; b < NBP; ++b) add_job(s[OFF_MX + memo_n + (b < n ? b : n - 1)], OFF_PB + b * PQS, 1);
+      if (w_stale) { post(CMD_PEND_BATCH_FUSED, false, true); w_stale = false; } else post(CMD_PEND_BATCH_CACHED, false, false);
+      run_command(cand);
+      __syncwarp();
+      if (lane_id() < n) s[OFF_MF + memo_n + lane_id()] = s[OFF_OUT + lane_id()];
+      __syncwarp();
+      memo_n += n;
+      memo_pending -= n;
+    }
+  }
 };
 
 // Persistent kernel: every BLOCK pulls candidates (in `order`: length class, then edge) until n are done.
@@ -577,6 +669,76 @@ tt_group_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__res
       out[ci] = o;
       const unsigned long long nd = tt.calls_dist, np = tt.calls - tt.calls_dist, ns = c.nq;
       atomicAdd(work + 0, np); atomicAdd(work + 1, nd); atomicAdd(work + 2, np * ns); atomicAdd(work + 3, nd * ns);
+    }
+  }
+}
+
+
+// --pp (TT_MODE_MARGINAL): Three_tax.calc_marg_prob per kept placement, block per candidate
+template <int R, int G, int MINB, int WS>
+__global__ void __launch_bounds__(G * 32, MINB)
+tt_group_pp_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__restrict__ bl, const int32_t *__restrict__ qsite,
+                   const int32_t *__restrict__ nq, const CandIn *__restrict__ in, const int32_t *__restrict__ order,
+                   CandOut *__restrict__ out, int n, TTParams prm, double *__restrict__ wbuf, int *counter) {
+  using TT = TTGroup<R, G, 1, WS>;
+  double *sm = reinterpret_cast<double *>(ppb_ttw_smem);
+  for (int i = threadIdx.x; i < 4; i += blockDim.x) { sm[TT::C_STATD + i] = m->statd[i]; sm[TT::C_LAM + i] = m->lam[i]; }
+  for (int i = threadIdx.x; i < 16; i += blockDim.x) { sm[TT::C_X + i] = m->x[i]; sm[TT::C_XIT + i] = m->xit[i]; }
+  for (int i = threadIdx.x; i < R; i += blockDim.x) sm[TT::C_RATES + i] = m->rates[i];
+  for (int i = threadIdx.x; i < 8; i += blockDim.x) sm[TT::OFF_BAD + i] = 0.0;
+  TT &tt = *reinterpret_cast<TT *>(sm + TT::OFF_OBJ);  // warp 0 only
+  int *job = TT::JOB();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) job[2] = atomicAdd(counter, 1);
+    __syncthreads();
+    const int idx = job[2];
+    if (idx >= n) break;
+    const int ci = order ? order[idx] : idx;
+    const CandIn cin = in[ci];
+    GCand c;
+    c.qsite = qsite + (int64_t)cin.q * g.Lp;
+    c.nq = nq[cin.q];
+    c.dbase = g.a[0] + (int64_t)cin.loc * g.a_stride;
+    c.pbase = g.a[1] + (int64_t)cin.loc * g.a_stride;
+    c.Lp = g.Lp;
+    c.wg = wbuf + (int64_t)blockIdx.x * TT::K * g.Lp;
+    {
+      const int32_t *ed = g.e[0] + (int64_t)cin.loc * g.Lp, *ep = g.e[1] + (int64_t)cin.loc * g.Lp;
+      long long es = 0;
+      for (int i = threadIdx.x; i < c.nq; i += TT::NT) {
+        const int site = c.qsite[i] & kSiteMask;
+        es += (long long)ed[site] + (long long)ep[site];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(0xffffffffu, es, o);
+      if (lane == 0) sm[TT::OFF_ESUM + warp] = (double)es;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double tot = 0.0;
+#pragma unroll
+      for (int w = 0; w < G; ++w) tot += sm[TT::OFF_ESUM + w];
+      tt.e_tot_ln2 = kLn2 * tot;
+      tt.rate_term = (double)((float)c.nq) * log((double)((float)R));
+      tt.cut_bl = bl[cin.loc];
+      tt.cand = c;
+      tt.calls = 0; tt.calls_dist = 0;
+      tt.reset_edges(prm.use_defaults ? prm.start_pend : cin.pend0, prm.use_defaults ? tt.cut_bl / 2.0 : cin.dist0);
+      tt.prior.kind = prm.prior_kind;
+      tt.prior.mean = prm.prior_kind == 2 ? prm.prior_means[cin.loc] : prm.prior_mean;
+      double mp = __longlong_as_double(0x7ff8000000000000LL);
+      const int st = tt.calc_marg_prob(prm.pp_rel_err, prm.max_pend, &mp);
+      tt.post_done();
+      tt.run_command(c);
+      if (lane == 0) {
+        CandOut o;
+        o.marg = mp; o.ll = mp; o.pend = tt.pend_bl; o.dist = tt.dist_bl; o.status = st; o.calls = tt.calls;
+        out[ci] = o;
+      }
+    } else {
+      while (tt.run_command(c)) {}
     }
   }
 }
