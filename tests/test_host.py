@@ -69,3 +69,24 @@ def test_shard_ranges_cover_and_balance():
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         sizes = [b - a for a, b in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_refpkg_loader_and_error_messages(tmp_path):
+    """refpkg_parse.ml:86-104 / refpkg.ml:26-63: CONTENTS.json -> tree, aln_fasta, phylo_model."""
+    import json, os, shutil
+    from pplacer_b200 import refpkg
+    src = os.path.join(configs.GOLDEN, "like", "gtr")
+    rp = tmp_path / "hiv.refpkg"
+    rp.mkdir()
+    for f in ("hiv.fasta", "hiv.phy_phyml_tree.txt", "phylo_model.jplace"):
+        shutil.copyfile(os.path.join(src, f), rp / f)
+    files = {"aln_fasta": "hiv.fasta", "tree": "hiv.phy_phyml_tree.txt", "phylo_model": "phylo_model.jplace"}
+    (rp / "CONTENTS.json").write_text(json.dumps({"files": files}))
+    tree, aln, model = refpkg.load(str(rp))
+    assert tree.n_nodes == 38 and len(aln) == 20 and model.n_states == 4 and model.n_rates == 4
+    assert all(s == s.upper() for _, s in aln)                      # refpkg.ml:37 Alignment.uppercase
+    with pytest.raises(ValueError, match="not a reference package"):
+        refpkg.load(str(tmp_path))
+    (rp / "CONTENTS.json").write_text(json.dumps({"files": {k: v for k, v in files.items() if k != "phylo_model"}}))
+    with pytest.raises(ValueError, match="phylo_model"):
+        refpkg.load(str(rp))
