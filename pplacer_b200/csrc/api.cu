@@ -337,7 +337,7 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
     static const bool pp_on_group = [] { const char *e = std::getenv("PPB_TTG_PP"); return e ? std::atoi(e) != 0 : true; }();
     c->ttg_pp = pp_on_group;
     w_slots = std::max(w_slots, (size_t)4 * c->sm_count);
-    c->ttg_blocks = (variant == 0 ? 2 : variant == 2 ? 3 : 4) * c->sm_count;
+    c->ttg_blocks = (variant == 0 ? 2 : variant == 2 ? 3 : 4) * c->sm_count;  // variants 1, 3, 4: four blocks per SM
     w_slots = std::max(w_slots, (size_t)c->ttg_blocks);
   }
   if ((rc = c->wbuf.ensure(w_slots * c->K * c->Lp)) != PP_OK) { pp_destroy(c); return rc; }
@@ -648,16 +648,18 @@ static int launch_three_tax_warp(pp_ctx *c, const CandIn *in, CandOut *out, int 
   if (c->tt_engine != 2 && prm.mode != TT_MODE_MARGINAL) {  // block per candidate, w in shared memory
     const int gblocks = std::min(c->ttg_blocks, n);
     // the shared-memory attribute is per function, not per context: set it at every launch
-#define PPB_LAUNCH_GROUP(G_, MINB_, TS_, WS_)                                                                                   \
+#define PPB_LAUNCH_GROUP(G_, MINB_, TS_, WS_, RU_)                                                                              \
   do {                                                                                                                          \
-    const size_t smg = TTGroup<4, G_, TS_, WS_>::smem_bytes();                                                                  \
-    CK(cudaFuncSetAttribute(tt_group_kernel<4, G_, MINB_, TS_, WS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smg));   \
-    tt_group_kernel<4, G_, MINB_, TS_, WS_><<<gblocks, G_ * 32, smg, c->stream>>>(c->dm, c->g, c->d_bl, c->qsite.p, c->nq.p, in, order, out, n, \
-                                                                                 prm, c->wbuf.p, c->counters.p, c->tt_work.p);  \
+    const size_t smg = TTGroup<4, G_, TS_, WS_, RU_>::smem_bytes();                                                             \
+    CK(cudaFuncSetAttribute(tt_group_kernel<4, G_, MINB_, TS_, WS_, RU_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smg)); \
+    tt_group_kernel<4, G_, MINB_, TS_, WS_, RU_><<<gblocks, G_ * 32, smg, c->stream>>>(c->dm, c->g, c->d_bl, c->qsite.p, c->nq.p, in, order, out, \
+                                                                                      n, prm, c->wbuf.p, c->counters.p, c->tt_work.p); \
   } while (0)
-    if (c->ttg_variant == 0) PPB_LAUNCH_GROUP(8, 2, 2, 768);
-    else if (c->ttg_variant == 2) PPB_LAUNCH_GROUP(4, 3, 1, 512);
-    else PPB_LAUNCH_GROUP(4, 4, 1, 256);
+    if (c->ttg_variant == 0) PPB_LAUNCH_GROUP(8, 2, 2, 768, false);
+    else if (c->ttg_variant == 2) PPB_LAUNCH_GROUP(4, 3, 1, 512, false);
+    else if (c->ttg_variant == 3) PPB_LAUNCH_GROUP(4, 4, 2, 256, false);
+    else if (c->ttg_variant == 4) PPB_LAUNCH_GROUP(4, 4, 1, 256, true);
+    else PPB_LAUNCH_GROUP(4, 4, 1, 256, false);
 #undef PPB_LAUNCH_GROUP
     LAUNCH_CHECK(c);
     return PP_OK;

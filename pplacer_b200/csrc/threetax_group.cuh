@@ -34,10 +34,10 @@ struct GCand {  // per-candidate constants every thread keeps in registers
 };
 
 // G warps per candidate, TS sites per thread per iteration in the one-point passes, WS sites of w in shared memory
-template <int R, int G, int TS, int WS>
-struct TTGroup : TTDriver<TTGroup<R, G, TS, WS>>, TTMachine<TTGroup<R, G, TS, WS>> {
-  using Drv = TTDriver<TTGroup<R, G, TS, WS>>;
-  using Mach = TTMachine<TTGroup<R, G, TS, WS>>;
+template <int R, int G, int TS, int WS, bool RU = false>
+struct TTGroup : TTDriver<TTGroup<R, G, TS, WS, RU>>, TTMachine<TTGroup<R, G, TS, WS, RU>> {
+  using Drv = TTDriver<TTGroup<R, G, TS, WS, RU>>;
+  using Mach = TTMachine<TTGroup<R, G, TS, WS, RU>>;
   using Drv::pend_bl; using Drv::dist_bl; using Drv::prox_bl; using Drv::calls;
   using Mach::opt_init; using Mach::opt_advance; using Mach::b_kind; using Mach::req_x; using Mach::o_status;
   static constexpr int S = 4, K = 4 * R, PM = 16 * R, NT = 32 * G;
@@ -352,7 +352,7 @@ struct TTGroup : TTDriver<TTGroup<R, G, TS, WS>>, TTMachine<TTGroup<R, G, TS, WS
       for (int t = 0; t < T; ++t)
 #pragma unroll
         for (int b = 0; b < NB; ++b) u[t][b] = 0.0;
-#pragma unroll 1
+#pragma unroll(RU && NB == 1 ? R : 1)
       for (int r = 0; r < R; ++r) {
         double d[T][4], p[T][4], q[T][4];
 #pragma unroll
@@ -585,13 +585,13 @@ struct TTGroup : TTDriver<TTGroup<R, G, TS, WS>>, TTMachine<TTGroup<R, G, TS, WS
 };
 
 // Persistent kernel: every BLOCK pulls candidates (in `order`: length class, then edge) until n are done.
-template <int R, int G, int MINB, int TS, int WS>
+template <int R, int G, int MINB, int TS, int WS, bool RU = false>
 __global__ void __launch_bounds__(G * 32, MINB)
 tt_group_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__restrict__ bl, const int32_t *__restrict__ qsite,
                 const int32_t *__restrict__ nq, const CandIn *__restrict__ in, const int32_t *__restrict__ order,
                 CandOut *__restrict__ out, int n, TTParams prm, double *__restrict__ wbuf, int *counter,
                 unsigned long long *__restrict__ work) {
-  using TT = TTGroup<R, G, TS, WS>;
+  using TT = TTGroup<R, G, TS, WS, RU>;
   double *sm = reinterpret_cast<double *>(ppb_ttw_smem);
   for (int i = threadIdx.x; i < 4; i += blockDim.x) { sm[TT::C_STATD + i] = m->statd[i]; sm[TT::C_LAM + i] = m->lam[i]; }
   for (int i = threadIdx.x; i < 16; i += blockDim.x) { sm[TT::C_X + i] = m->x[i]; sm[TT::C_XIT + i] = m->xit[i]; }
