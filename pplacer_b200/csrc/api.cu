@@ -337,7 +337,7 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
     static const bool pp_on_group = [] { const char *e = std::getenv("PPB_TTG_PP"); return e ? std::atoi(e) != 0 : true; }();
     c->ttg_pp = pp_on_group;
     w_slots = std::max(w_slots, (size_t)4 * c->sm_count);
-    c->ttg_blocks = (variant == 0 ? 2 : variant == 2 ? 3 : 4) * c->sm_count;  // variants 1, 3, 4: four blocks per SM
+    c->ttg_blocks = (variant == 0 ? 2 : (variant == 2 || variant == 5) ? 3 : 4) * c->sm_count;  // variants 1, 3, 4: four blocks per SM
     w_slots = std::max(w_slots, (size_t)c->ttg_blocks);
   }
   if ((rc = c->wbuf.ensure(w_slots * c->K * c->Lp)) != PP_OK) { pp_destroy(c); return rc; }
@@ -659,6 +659,7 @@ static int launch_three_tax_warp(pp_ctx *c, const CandIn *in, CandOut *out, int 
     else if (c->ttg_variant == 2) PPB_LAUNCH_GROUP(4, 3, 1, 512, false);
     else if (c->ttg_variant == 3) PPB_LAUNCH_GROUP(4, 4, 2, 256, false);
     else if (c->ttg_variant == 4) PPB_LAUNCH_GROUP(4, 4, 1, 256, true);
+    else if (c->ttg_variant == 5) PPB_LAUNCH_GROUP(4, 3, 2, 512, false);
     else PPB_LAUNCH_GROUP(4, 4, 1, 256, false);
 #undef PPB_LAUNCH_GROUP
     LAUNCH_CHECK(c);

@@ -435,3 +435,16 @@ def test_c1_refpkg_to_jplace_matches_oracle(oracle_binding, tmp_path):
         rep = jplace.compare(got, want, keep_factor=0.001 if pp else 0.01)
         assert rep.ok and rep.n_queries == len(prob.query_names), rep.summary() + " " + "; ".join(rep.failures[:5])
         o.close()
+
+
+def test_second_stage_work_counters(c2_small):
+    """pp_three_tax_work: the objective calls the second stage made, split by kind - the unit of its
+    roofline in bench.py - must add up to the per-query call counts pp_place reports."""
+    prob, p = c2_small
+    q = prob.query_chars[:200]
+    p.three_tax_work(reset=True)
+    out, n_out, st, info = p.place(q, p.prefs(), debug=True)
+    w = p.three_tax_work()
+    assert w[0] > 0 and w[1] > 0 and w[0] + w[1] == info["n_like_calls"].sum()
+    nq = seqio.informative(q).sum(axis=1)
+    assert nq.min() * (w[0] + w[1]) <= w[2] + w[3] <= nq.max() * (w[0] + w[1])
