@@ -128,12 +128,10 @@ struct pp_ctx {
 };
 
 constexpr int kTTWarpsPerBlock = 8;
-constexpr int kTTGroupWarps = 8;
 constexpr int kTTGroupDefaultVariant = 3;  // 0: 8 warps x 2 blocks/SM, 768 sites of w in shared memory; 1: 4 warps x 4 blocks/SM, 256 sites, one site per thread per iteration; 2: 4 warps x 3 blocks/SM, 512 sites; 3: as 1, two sites per thread per iteration (default); 4: as 1, rate loop unrolled
 constexpr int kTTWarpDefaultBlocks = 2;
 constexpr int kTTWarpDefaultFlags = 2;
 static bool ttw_supported(const pp_ctx *c) { return c->S == 4 && !c->gcat && c->R == 4; }
-static int tt_threads(const pp_ctx *c) { return c->S == 4 ? kTTThreadsDNA : kTTThreadsAA; }
 
 template <int S, bool G>
 static size_t tt_smem_bytes(const pp_ctx *c) {
