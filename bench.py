@@ -353,6 +353,18 @@ def run_ours(args):
     }
     if engine == 1 or tt_work[:2].sum() == 0:
         roofline_tt["note"] += "; work counters exist for the warp engine only"
+    # measured DRAM traffic of the same kernels from a committed ncu capture (profiles/traffic.json), C2 only
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            tr = json.load(fh).get(args.workload, {})
+        if roofline_prefilter["kernel"] in tr:
+            roofline_prefilter["traffic"] = tr[roofline_prefilter["kernel"]]["dram_bytes"]
+            roofline_prefilter["traffic_note"] = "dram bytes per launch, ncu capture r2f (profiles/traffic.json)"
+        if roofline_tt["kernel"] in tr and Q == 10_000:
+            roofline_tt["traffic"] = tr[roofline_tt["kernel"]]["dram_bytes"]
+            roofline_tt["traffic_note"] = "dram bytes per step (all second-stage launches), ncu capture r2f (profiles/traffic.json)"
+    except Exception:
+        pass
     dominant_tt = opt_ms >= pre_ms
     roofline = dict(roofline_tt if dominant_tt else roofline_prefilter)
     roofline["share_of_step_ms"] = share

@@ -334,8 +334,8 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
     c->ttg_variant = variant;
     static const bool pp_on_group = [] { const char *e = std::getenv("PPB_TTG_PP"); return e ? std::atoi(e) != 0 : true; }();
     c->ttg_pp = pp_on_group;
-    w_slots = std::max(w_slots, (size_t)4 * c->sm_count);
-    c->ttg_blocks = (variant == 0 ? 2 : (variant == 2 || variant == 5) ? 3 : 4) * c->sm_count;  // variants 1, 3, 4: four blocks per SM
+    w_slots = std::max(w_slots, (size_t)6 * c->sm_count);
+    c->ttg_blocks = (variant == 0 ? 2 : (variant == 2 || variant == 5) ? 3 : variant == 6 ? 5 : variant == 7 ? 6 : 4) * c->sm_count;  // variants 1, 3, 4: four blocks per SM
     w_slots = std::max(w_slots, (size_t)c->ttg_blocks);
   }
   if ((rc = c->wbuf.ensure(w_slots * c->K * c->Lp)) != PP_OK) { pp_destroy(c); return rc; }
@@ -658,6 +658,8 @@ static int launch_three_tax_warp(pp_ctx *c, const CandIn *in, CandOut *out, int 
     else if (c->ttg_variant == 3) PPB_LAUNCH_GROUP(4, 4, 2, 256, false);
     else if (c->ttg_variant == 4) PPB_LAUNCH_GROUP(4, 4, 1, 256, true);
     else if (c->ttg_variant == 5) PPB_LAUNCH_GROUP(4, 3, 2, 512, false);
+    else if (c->ttg_variant == 6) PPB_LAUNCH_GROUP(4, 5, 1, 256, false);
+    else if (c->ttg_variant == 7) PPB_LAUNCH_GROUP(4, 6, 1, 128, false);
     else PPB_LAUNCH_GROUP(4, 4, 1, 256, false);
 #undef PPB_LAUNCH_GROUP
     LAUNCH_CHECK(c);
