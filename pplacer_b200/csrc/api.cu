@@ -656,7 +656,7 @@ static int launch_three_tax_warp(pp_ctx *c, const CandIn *in, CandOut *out, int 
     if (c->ttg_variant == 0) PPB_LAUNCH_GROUP(8, 2, 2, 768, false);
     else if (c->ttg_variant == 2) PPB_LAUNCH_GROUP(4, 3, 1, 512, false);
     else if (c->ttg_variant == 3) PPB_LAUNCH_GROUP(4, 4, 2, 256, false);
-    else if (c->ttg_variant == 4) PPB_LAUNCH_GROUP(4, 4, 1, 256, true);
+    else if (c->ttg_variant == 4) PPB_LAUNCH_GROUP(4, 4, 2, 256, true);
     else if (c->ttg_variant == 5) PPB_LAUNCH_GROUP(4, 3, 2, 512, false);
     else if (c->ttg_variant == 6) PPB_LAUNCH_GROUP(4, 5, 1, 256, false);
     else if (c->ttg_variant == 7) PPB_LAUNCH_GROUP(4, 6, 1, 128, false);

@@ -83,6 +83,18 @@ struct TTGroup : TTDriver<TTGroup<R, G, TS, WS, RU>>, TTMachine<TTGroup<R, G, TS
   __device__ __forceinline__ static int *JOB() { return reinterpret_cast<int *>(SM() + OFF_JOB); }
   __device__ __forceinline__ static int lane_id() { return threadIdx.x & 31; }
   __device__ __forceinline__ static int warp_id() { return threadIdx.x >> 5; }
+  // darr/parr gathers: read-only path; RU = keep them in L2 ahead of the streamed w overflow (evict_last)
+  __device__ __forceinline__ static unsigned long long glv_policy() {
+    unsigned long long pol = 0;
+    if (RU) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+  }
+  __device__ __forceinline__ static double ld_glv(const double *p, unsigned long long pol) {
+    if (!RU) return __ldg(p);
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+  }
 
   __device__ __forceinline__ static double warp_sum(double v) {
 #pragma unroll
@@ -331,6 +343,7 @@ struct TTGroup : TTDriver<TTGroup<R, G, TS, WS, RU>>, TTMachine<TTGroup<R, G, TS
 #pragma unroll
     for (int b = 0; b < NB; ++b) lp[b].init();
     const int tid = threadIdx.x;
+    const unsigned long long pol = glv_policy();
     for (int base = 0; base < c.nq; base += NT * T) {
       bool act[T], fast = true;
       const double *dp[T], *pp[T], *Pqc[T];
@@ -352,15 +365,15 @@ struct TTGroup : TTDriver<TTGroup<R, G, TS, WS, RU>>, TTMachine<TTGroup<R, G, TS
       for (int t = 0; t < T; ++t)
 #pragma unroll
         for (int b = 0; b < NB; ++b) u[t][b] = 0.0;
-#pragma unroll(RU && NB == 1 ? R : 1)
+#pragma unroll 1
       for (int r = 0; r < R; ++r) {
         double d[T][4], p[T][4], q[T][4];
 #pragma unroll
         for (int t = 0; t < T; ++t)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            d[t][k] = __ldg(dp[t] + (int64_t)(r * 4 + k) * c.Lp);
-            p[t][k] = __ldg(pp[t] + (int64_t)(r * 4 + k) * c.Lp);
+            d[t][k] = ld_glv(dp[t] + (int64_t)(r * 4 + k) * c.Lp, pol);
+            p[t][k] = ld_glv(pp[t] + (int64_t)(r * 4 + k) * c.Lp, pol);
           }
         if (fast) {
 #pragma unroll
@@ -404,6 +417,7 @@ struct TTGroup : TTDriver<TTGroup<R, G, TS, WS, RU>>, TTMachine<TTGroup<R, G, TS
 #pragma unroll
     for (int b = 0; b < NB; ++b) lp[b].init();
     const int tid = threadIdx.x;
+    const unsigned long long pol = glv_policy();
     for (int base = 0; base < c.nq; base += NT * T) {
       bool act[T], fast = true;
       int iw[T];
@@ -436,8 +450,8 @@ struct TTGroup : TTDriver<TTGroup<R, G, TS, WS, RU>>, TTMachine<TTGroup<R, G, TS
           for (int t = 0; t < T; ++t)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              d[t][k] = __ldg(dp[t] + (int64_t)(r * 4 + k) * c.Lp);
-              p[t][k] = __ldg(pp[t] + (int64_t)(r * 4 + k) * c.Lp);
+              d[t][k] = ld_glv(dp[t] + (int64_t)(r * 4 + k) * c.Lp, pol);
+              p[t][k] = ld_glv(pp[t] + (int64_t)(r * 4 + k) * c.Lp, pol);
             }
           site_w<T>(Pd0 + r * 16, Pd0 + PM + r * 16, d, p, st, ww);
 #pragma unroll
