@@ -556,7 +556,7 @@ static int launch_prefilter_direct(pp_ctx *c, int64_t Q, int blocks_per_sm) {
   return prefilter_finish(c, Q, g);
 }
 
-template <int TE, int QT, int W>
+template <int TE, int QT, int W, int MINB = 1>
 static int launch_prefilter_table(pp_ctx *c, int64_t Q, double pend, int blocks_per_sm) {
   int rc;
   if (c->mt_pend != pend) {  // four-base table: once per (reference, pendant length)
@@ -568,7 +568,7 @@ static int launch_prefilter_table(pp_ctx *c, int64_t Q, double pend, int blocks_
   const PreGeom g = prefilter_geometry(c, Q, QT, TE, W, blocks_per_sm);
   PreArgs A;
   if ((rc = pack_codes<QT>(c, Q, g.nqt)) || (rc = prefilter_args(c, Q, g, &A))) return rc;
-  prefilter_table_kernel<TE, QT, W><<<dim3(g.gx, g.gy, g.zs), W * 32, 0, c->stream>>>(A, c->MT.p, c->MTe.p); LAUNCH_CHECK(c);
+  prefilter_table_kernel<TE, QT, W, MINB><<<dim3(g.gx, g.gy, g.zs), W * 32, 0, c->stream>>>(A, c->MT.p, c->MTe.p); LAUNCH_CHECK(c);
   c->prefilter_kernel_used = 2;
   return prefilter_finish(c, Q, g);
 }
@@ -582,7 +582,14 @@ static int run_prefilter(pp_ctx *c, int64_t Q, int kernel_choice, double pend) {
   if (c->S == 4 && !c->gcat && c->K == 16) {
     if (kernel_choice == 1) return few ? launch_prefilter_direct<4, false, 4, 2, 8, 1, TQ_CONST>(c, Q, 8) : launch_prefilter_direct<4, false, 4, 2, 16, 8, TQ_CONST>(c, Q, 1);
     if (kernel_choice == 3) return launch_prefilter_direct<4, false, 4, 2, 16, 8, TQ_SMEM>(c, Q, 1);
-    return few ? launch_prefilter_table<2, 8, 1>(c, Q, pend, 12) : launch_prefilter_table<2, 16, 4>(c, Q, pend, 3);
+    // Geometry of the table form (measured, profiles/README.md r2k): the kernel is latency-bound, so FEW
+    // queries per warp and many resident warps win over register-level reuse of the table entries
+    // (16 queries per warp, 3 blocks/SM: 18.1 ms; 4 queries per warp, 8 blocks/SM: 13.3 ms for C2).
+    static const int geom = [] { const char *e = std::getenv("PPB_PF_GEOM"); return e ? std::atoi(e) : 0; }();
+    if (!few && geom == 1) return launch_prefilter_table<2, 16, 4, 3>(c, Q, pend, 3);
+    if (!few && geom == 2) return launch_prefilter_table<2, 8, 4, 6>(c, Q, pend, 6);
+    if (!few && geom == 3) return launch_prefilter_table<2, 4, 8, 4>(c, Q, pend, 4);
+    return few ? launch_prefilter_table<2, 8, 1, 1>(c, Q, pend, 12) : launch_prefilter_table<2, 4, 4, 8>(c, Q, pend, 8);
   }
   if (kernel_choice == 2) return fail(PP_EINVAL, "prefilter: the table form exists for the DNA Gamma-4 model only");
   if (c->gcat) {

@@ -381,8 +381,8 @@ mtable_kernel(const SnT sn, const TqPrimary tp, double *__restrict__ MT, int32_t
 }
 
 // grid / block exactly as prefilter_direct_kernel; MT[L][4][Np].
-template <int TE, int QT, int W>
-__global__ void __launch_bounds__(W * 32)
+template <int TE, int QT, int W, int MINB = 1>
+__global__ void __launch_bounds__(W * 32, MINB)
 prefilter_table_kernel(const PreArgs A, const double *__restrict__ MT, const int32_t *__restrict__ MTe) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int qt = blockIdx.x * W + warp;
