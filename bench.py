@@ -329,6 +329,11 @@ def run_ours(args):
                 "note": "compulsory bytes: one pass over the supernodes (or their four-base table) + query codes + scores"},
         "traffic": None,
     }
+    if used == 2:
+        roofline_prefilter["note"] = ("table form: the four-base table turns a (query, edge, site) unit into one select and one "
+                                      "multiply, so the ALGORITHMIC rate 2RS flops/unit can exceed what the FP64 pipe executes "
+                                      "(frac may pass 1); the kernel is bound by issue slots (ncu: 71 % issue-active, FP64 pipe 6 %); "
+                                      "--prefilter direct runs the FMA form the roofline was defined on")
     # second stage: unit = one objective evaluation on n_q sites.  A distal move re-evolves the
     # distal and proximal GLVs (2 x 2RS^2 flops per site) and takes log_like3 (4RS); a pendant move is a
     # P-column lookup plus log_like3.  Compulsory bytes: the d/p gathers 2*8*R*S per site of a distal
