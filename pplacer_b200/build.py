@@ -9,8 +9,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpplacer_b200.so")
 SOURCES = ["api.cu", "model_host.cpp"]
-HEADERS = ["baseball.cuh", "device_common.cuh", "model_host.hpp", "precompute.cuh", "prefilter.cuh", "query.cuh", "threetax.cuh", "threetax_warp.cuh",
-           "qng_tables.h", os.path.join("..", "..", "include", "pplacer_b200.h")]
+
+
+def _headers():
+    """every header the two translation units can include (stale check)"""
+    hs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".hpp", ".h"))]
+    hs.append(os.path.join(HERE, "..", "include", "pplacer_b200.h"))
+    return hs
 
 
 def nvcc_path() -> str:
@@ -24,7 +29,7 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    return any(os.path.getmtime(f) > t for f in [os.path.join(CSRC, x) for x in SOURCES] + _headers())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -20,6 +20,11 @@
 //   all warps   build the posted matrix sets cooperatively (one thread per entry), run the pass,
 //               and leave one partial sum per warp; warp 0 adds them in a fixed order.
 // Four block barriers per pass: command, exponentials, matrices, partial sums.
+//
+// Redundant execution: warp 0's scalar state lives in ONE shared-memory object that all 32 lanes read
+// and write with identical values while executing the same instruction converged (no lane-dependent
+// branch exists in that code; __syncwarp() at the seams).  compute-sanitizer racecheck reports exactly
+// these same-value write/write pairs (profiles/README.md, r2n); memcheck is clean.
 #pragma once
 #include "threetax_warp.cuh"
 
@@ -183,6 +188,7 @@ struct TTGroup : TTDriver<TTGroup<R, G, TS, WS, RU>>, TTMachine<TTGroup<R, G, TS
   // warp 0: advance the optimiser to the next call that needs a pass; returns false when the candidate is done
   __device__ __forceinline__ bool scalar_step(bool first, double *ll_out) {
     double *s = SM();
+    __syncwarp();  // the 32 lanes run this uniform code converged (see the note on redundant execution above)
     if (!first) {
       // consume the pass just finished
       if (final_pending) { *ll_out = s[OFF_OUT]; return false; }
@@ -191,6 +197,7 @@ struct TTGroup : TTDriver<TTGroup<R, G, TS, WS, RU>>, TTMachine<TTGroup<R, G, TS
     n_jobs = 0;
     for (;;) {
       const int more = optimise ? opt_advance(feed, fval) : 0;
+      __syncwarp();
       if (more == 2) {  // Brent's predictable calls: hint_prepare posted the batch's matrices
         feed = 2;
         if (memo_kind == 1) post(CMD_DIST_BATCH, true, false);
