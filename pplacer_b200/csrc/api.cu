@@ -580,7 +580,8 @@ static int run_prefilter(pp_ctx *c, int64_t Q, int kernel_choice, double pend) {
   const bool few = Q <= 64;  // one warp per block when there are too few query tiles to fill a block
   const bool const_ok = (size_t)c->al.n_codes * c->K <= (size_t)kConstTqDoubles;
   if (c->S == 4 && !c->gcat && c->K == 16) {
-    if (kernel_choice == 1) return few ? launch_prefilter_direct<4, false, 4, 2, 8, 1, TQ_CONST>(c, Q, 8) : launch_prefilter_direct<4, false, 4, 2, 16, 8, TQ_CONST>(c, Q, 1);
+    // direct form: 8 queries per warp x 4 warps (157 registers, 3 blocks/SM) measured 35.9 ms against 42.9 ms for 16 x 8 (r2q)
+    if (kernel_choice == 1) return few ? launch_prefilter_direct<4, false, 4, 2, 8, 1, TQ_CONST>(c, Q, 8) : launch_prefilter_direct<4, false, 4, 2, 8, 4, TQ_CONST>(c, Q, 3);
     if (kernel_choice == 3) return launch_prefilter_direct<4, false, 4, 2, 16, 8, TQ_SMEM>(c, Q, 1);
     // Geometry of the table form (measured, profiles/README.md r2k): the kernel is latency-bound, so FEW
     // queries per warp and many resident warps win over register-level reuse of the table entries
