@@ -178,6 +178,13 @@ int pp_set_stream(pp_ctx *, void *cuda_stream);
 int pp_set_prefilter_kernel(pp_ctx *, int32_t kernel);
 int pp_prefilter_kernel_used(pp_ctx *);
 
+/* Ranking (Fig.enum_by_score with fig_cutoff 0, fig.ml:143-148): 0 = on trees with more than 1024 nodes keep only
+ * the first 256 entries of the stable descending order (all baseball reads unless a query runs through more
+ * than 256 locations - then the batch is redone on the full order, counted by pp_rank_fallbacks), 1 = always
+ * the full segmented sort.  Results are identical either way. */
+int pp_set_rank_mode(pp_ctx *, int32_t mode);
+int pp_rank_fallbacks(pp_ctx *);
+
 /* Which engine runs the second stage (Three_tax.optimize / calc_marg_prob, three_tax.ml:70-83,169-215):
  * 0 = default (engine 3 for the DNA Gamma-4 model with the --pp integrals on engine 2; engine 1 otherwise),
  * 1 = block-per-candidate (every model), 2 = warp-per-candidate, 3 = block-per-candidate with the cached

@@ -120,6 +120,8 @@ struct pp_ctx {
   // warp-per-candidate engine (threetax_warp.cuh): DNA Gamma-4 only
   int tt_engine = 0;          // pp_set_three_tax_engine: 0 default, 1 block-per-candidate, 2 warp-per-candidate, 3 block + shared-memory w
   int ttg_blocks = 0, ttg_variant = 0;
+  int rank_mode = -1;  // pp_set_rank_mode: -1 = default (PPB_RANK_FULL), 0 truncated ranking when possible, 1 always the full sort
+  int rank_fallbacks = 0;  // batches that had to be redone on the full ranking
   bool ttg_pp = true;  // --pp integrals on the block engine (PPB_TTG_PP=0: on the warp engine)
   int ttw_blocks_per_sm = 0;  // 0 = occupancy maximum
   int ttw_max_blocks = 0;
@@ -765,11 +767,17 @@ static int place_batch(pp_ctx *c, const pp_prefs *pf, int64_t Q, const uint8_t *
     t.stop();
   }
   const int64_t total = Q * (int64_t)n_nodes;
-  {
-    PhaseTimer t(c, 1);
-    if ((rc = c->keys_in.ensure(total)) || (rc = c->keys_out.ensure(total)) || (rc = c->rank_in.ensure(total)) ||
-        (rc = c->rank_loc.ensure(total)) || (rc = c->seg_off.ensure(Q + 1)))
-      return rc;
+  // Ranking: baseball reads only the head of Fig.enum_by_score's order, so large trees get a truncated
+  // ranking (first kTopK entries, topk_rank_kernel); a query that runs through all of them sends the
+  // batch back through the full segmented sort (second attempt below).
+  static const bool rank_full_only = [] { const char *e = std::getenv("PPB_RANK_FULL"); return e && std::atoi(e) != 0; }();
+  const bool full_only = c->rank_mode < 0 ? rank_full_only : c->rank_mode == 1;
+  const bool can_truncate = !all_edges && !full_only && n_nodes > 4 * kTopK;
+  auto rank_full = [&]() -> int {
+    int rc2;
+    if ((rc2 = c->keys_in.ensure(total)) || (rc2 = c->keys_out.ensure(total)) || (rc2 = c->rank_in.ensure(total)) ||
+        (rc2 = c->rank_loc.ensure(total)) || (rc2 = c->seg_off.ensure(Q + 1)))
+      return rc2;
     rank_keys_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->scores.p, c->keys_in.p, n_nodes, c->root_id, total); LAUNCH_CHECK(c);
     iota_segments_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->rank_in.p, n_nodes, total); LAUNCH_CHECK(c);
     std::vector<int32_t> off(Q + 1);
@@ -779,13 +787,19 @@ static int place_batch(pp_ctx *c, const pp_prefs *pf, int64_t Q, const uint8_t *
     size_t tmp_bytes = 0;
     CK(cub::DeviceSegmentedSort::StableSortPairsDescending(nullptr, tmp_bytes, c->keys_in.p, c->keys_out.p, c->rank_in.p, c->rank_loc.p,
                                                            total, (int)Q, c->seg_off.p, c->seg_off.p + 1, c->stream));
-    if ((rc = c->sort_tmp.ensure(tmp_bytes))) return rc;
+    if ((rc2 = c->sort_tmp.ensure(tmp_bytes))) return rc2;
     CK(cub::DeviceSegmentedSort::StableSortPairsDescending(c->sort_tmp.p, tmp_bytes, c->keys_in.p, c->keys_out.p, c->rank_in.p, c->rank_loc.p,
                                                            total, (int)Q, c->seg_off.p, c->seg_off.p + 1, c->stream));
     c->launches += 3;
     CK(cudaStreamSynchronize(c->stream));  // `off` must outlive the async copy
-    t.stop();
-  }
+    return PP_OK;
+  };
+  auto rank_truncated = [&]() -> int {
+    int rc2;
+    if ((rc2 = c->rank_loc.ensure(total))) return rc2;
+    topk_rank_kernel<<<(unsigned)Q, 256, 0, c->stream>>>(c->scores.p, c->rank_loc.p, n_nodes, c->root_id); LAUNCH_CHECK(c);
+    return PP_OK;
+  };
   // ---- stage 2: baseball in waves (core.ml:283-318) ----
   const size_t per_q_i32 = 7, per_q_f64 = 1;
   if ((rc = c->i32pool.ensure((size_t)Q * (per_q_i32 + 2) + (size_t)Q * P)) || (rc = c->f64pool.ensure((size_t)Q * per_q_f64 + 3 * (size_t)Q * P)) ||
@@ -804,24 +818,42 @@ static int place_batch(pp_ctx *c, const pp_prefs *pf, int64_t Q, const uint8_t *
   }
   KeepState ks; ks.keep_begin = c->i32pool.p + 7 * Q; ks.n_keep = c->i32pool.p + 8 * Q;
   const int qb = (int)((Q + 255) / 256);
-  ball_init_kernel<<<qb, 256, 0, c->stream>>>(b, c->prep_status.p, (int)Q); LAUNCH_CHECK(c);
   const size_t max_wave = all_edges ? (size_t)Q * (n_nodes - 1) : (size_t)Q * std::max(std::min(pf->max_strikes, pf->max_pitches + 1), 1);
   if ((rc = c->cand.ensure(std::max(max_wave, (size_t)Q * pf->keep_at_most))) || (rc = c->cand_out.ensure(std::max(max_wave, (size_t)Q * pf->keep_at_most))))
     return rc;
   {
-    PhaseTimer t(c, 2);
     const TTParams prm = make_params(pf, TT_MODE_OPTIMIZE, pf->initial_tolerance, 1);
-    for (int wave = 0;; ++wave) {
-      CK(cudaMemsetAsync(c->counters.p + 1, 0, 2 * sizeof(int), c->stream));
-      ball_plan_kernel<<<qb, 256, 0, c->stream>>>(b, bp, c->rank_loc.p, n_nodes, c->root_id, (int)Q, c->cand.p, c->counters.p + 1); LAUNCH_CHECK(c);
-      CK(cudaMemcpyAsync(c->h_counters, c->counters.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    for (int attempt = 0;; ++attempt) {
+      const bool truncated = can_truncate && attempt == 0;
+      const int n_rank = truncated ? kTopK : n_nodes;
+      {
+        PhaseTimer tr(c, 1);
+        if ((rc = truncated ? rank_truncated() : rank_full())) return rc;
+        tr.stop();
+      }
+      PhaseTimer tw(c, 2);
+      ball_init_kernel<<<qb, 256, 0, c->stream>>>(b, c->prep_status.p, (int)Q); LAUNCH_CHECK(c);
+      CK(cudaMemsetAsync(c->counters.p + 5, 0, sizeof(int), c->stream));
+      for (int wave = 0;; ++wave) {
+        CK(cudaMemsetAsync(c->counters.p + 1, 0, 2 * sizeof(int), c->stream));
+        ball_plan_kernel<<<qb, 256, 0, c->stream>>>(b, bp, c->rank_loc.p, n_nodes, n_rank, c->root_id, (int)Q, c->cand.p, c->counters.p + 1,
+                                                    c->counters.p + 5); LAUNCH_CHECK(c);
+        CK(cudaMemcpyAsync(c->h_counters, c->counters.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        const int n_cand = c->h_counters[1];
+        if (n_cand == 0) break;
+        if ((rc = launch_three_tax(c, c->cand.p, c->cand_out.p, n_cand, prm))) return rc;
+        ball_update_kernel<<<qb, 256, 0, c->stream>>>(b, bp, c->cand.p, c->cand_out.p, n_rank, n_nodes, (int)Q, c->counters.p + 2,
+                                                      c->counters.p + 5); LAUNCH_CHECK(c);
+        if (wave > n_nodes + 64) return fail(PP_ECUDA, "place_batch: baseball did not terminate");
+      }
+      CK(cudaMemcpyAsync(c->h_counters, c->counters.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
-      const int n_cand = c->h_counters[1];
-      if (n_cand == 0) break;
-      if ((rc = launch_three_tax(c, c->cand.p, c->cand_out.p, n_cand, prm))) return rc;
-      ball_update_kernel<<<qb, 256, 0, c->stream>>>(b, bp, c->cand.p, c->cand_out.p, n_nodes, (int)Q, c->counters.p + 2); LAUNCH_CHECK(c);
-      if (wave > n_nodes + 64) return fail(PP_ECUDA, "place_batch: baseball did not terminate");
+      tw.stop();
+      if (!(truncated && c->h_counters[5] > 0)) break;  // else: some query used up the truncated ranking - redo on the full one
+      c->rank_fallbacks++;
     }
+    PhaseTimer t(c, 2);
     // ---- keep + refinement (core.ml:336-369) ----
     CK(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(int), c->stream));
     keep_select_kernel<<<qb, 256, 0, c->stream>>>(b, bp, ks, (int)Q, c->cand.p, c->counters.p + 3, PP_Q_EMPTY_RESULTS); LAUNCH_CHECK(c);
@@ -1005,6 +1037,13 @@ extern "C" int pp_set_prefilter_kernel(pp_ctx *c, int32_t kernel) {
   return PP_OK;
 }
 extern "C" int pp_prefilter_kernel_used(pp_ctx *c) { return c ? c->prefilter_kernel_used : -1; }
+
+extern "C" int pp_set_rank_mode(pp_ctx *c, int32_t mode) {
+  if (!c || mode < 0 || mode > 1) return fail(PP_EINVAL, "pp_set_rank_mode: mode must be 0 (truncated ranking when possible) or 1 (full sort)");
+  c->rank_mode = mode;
+  return PP_OK;
+}
+extern "C" int pp_rank_fallbacks(pp_ctx *c) { return c ? c->rank_fallbacks : -1; }
 
 extern "C" int pp_set_three_tax_engine(pp_ctx *c, int32_t engine, int32_t blocks_per_sm) {
   if (!c || engine < 0 || engine > 3 || blocks_per_sm < 0) return fail(PP_EINVAL, "pp_set_three_tax_engine: engine must be 0, 1, 2 or 3");

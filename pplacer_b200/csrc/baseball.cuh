@@ -45,8 +45,9 @@ __global__ void ball_init_kernel(BallState b, const int32_t *__restrict__ prep_s
 
 // ranking: rank_loc[q][n_nodes] = edge ids sorted by score descending (stable); entries equal to
 // root_id are skipped (the root is never scored: fig.ml:103, stree.ml:33-35).
-__global__ void ball_plan_kernel(BallState b, BallPrefs bp, const int32_t *__restrict__ rank_loc, int n_nodes,
-                                 int root_id, int Q, CandIn *__restrict__ cand, int *__restrict__ wave_count) {
+__global__ void ball_plan_kernel(BallState b, BallPrefs bp, const int32_t *__restrict__ rank_loc, int n_nodes, int n_rank,
+                                 int root_id, int Q, CandIn *__restrict__ cand, int *__restrict__ wave_count,
+                                 int *__restrict__ exhausted) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= Q || b.done[q]) { if (q < Q) b.wave_n[q] = 0; return; }
   long long need = (long long)bp.t_max_strikes - b.n_strikes[q];
@@ -56,8 +57,12 @@ __global__ void ball_plan_kernel(BallState b, BallPrefs bp, const int32_t *__res
   const int32_t *rk = rank_loc + (int64_t)q * n_nodes;
   // count how many non-root ranks remain, up to need
   int r = b.next_rank[q], cnt = 0;
-  for (int rr = r; rr < n_nodes && cnt < need; ++rr) cnt += (rk[rr] != root_id);
-  if (cnt == 0) { b.done[q] = 1; b.wave_n[q] = 0; return; }
+  for (int rr = r; rr < n_rank && cnt < need; ++rr) cnt += (rk[rr] != root_id);
+  if (cnt == 0) {  // ranking used up (with a truncated ranking the caller must redo the batch on the full one)
+    if (n_rank < n_nodes) atomicAdd(exhausted, 1);
+    b.done[q] = 1; b.wave_n[q] = 0;
+    return;
+  }
   const int base = atomicAdd(wave_count, cnt);
   b.wave_begin[q] = base; b.wave_n[q] = cnt;
   int k = 0;
@@ -71,7 +76,8 @@ __global__ void ball_plan_kernel(BallState b, BallPrefs bp, const int32_t *__res
 }
 
 __global__ void ball_update_kernel(BallState b, BallPrefs bp, const CandIn *__restrict__ cand,
-                                   const CandOut *__restrict__ out, int n_rank_total, int Q, int *__restrict__ n_active) {
+                                   const CandOut *__restrict__ out, int n_rank_total, int n_nodes, int Q, int *__restrict__ n_active,
+                                   int *__restrict__ exhausted) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= Q || b.done[q]) return;
   int nres = b.n_results[q], strikes = b.n_strikes[q];
@@ -96,7 +102,10 @@ __global__ void ball_update_kernel(BallState b, BallPrefs bp, const CandIn *__re
     }
   }
   b.n_results[q] = nres; b.n_strikes[q] = strikes; b.like_record[q] = record;
-  if (b.next_rank[q] >= n_rank_total) stop = true;
+  if (b.next_rank[q] >= n_rank_total) {
+    if (!stop && n_rank_total < n_nodes) atomicAdd(exhausted, 1);
+    stop = true;
+  }
   if (stop) b.done[q] = 1; else atomicAdd(n_active, 1);
 }
 
@@ -238,6 +247,95 @@ __global__ void rank_keys_kernel(const double *__restrict__ scores, double *__re
     const bool bad = (i % n_nodes) == root_id || s != s;
     keys[i] = bad ? -__longlong_as_double(0x7ff0000000000000LL) : s;
   }
+}
+
+
+// Truncated ranking: the first KTOP entries of Fig.enum_by_score's stable descending order
+// (fig.ml:143-148), which is all baseball ever reads unless a query runs through more than KTOP
+// locations (then the caller falls back to the full segmented sort).  One block per query: an
+// eight-pass MSB radix select finds the KTOP-th largest key, ties at the threshold are taken in
+// ascending edge order (stability), the survivors are sorted in shared memory.
+constexpr int kTopK = 256;
+__device__ __forceinline__ unsigned long long rank_key_bits(double s, bool bad) {
+  if (bad) s = -__longlong_as_double(0x7ff0000000000000LL);
+  const unsigned long long u = (unsigned long long)__double_as_longlong(s);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);  // monotone: larger score <=> larger key
+}
+__global__ void __launch_bounds__(256)
+topk_rank_kernel(const double *__restrict__ scores, int32_t *__restrict__ rank_loc, int n_nodes, int root_id) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_remaining, s_gt, s_eq_base;
+  __shared__ unsigned long long skey[kTopK];
+  __shared__ int sidx[kTopK];
+  __shared__ int warp_cnt[8];
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const double *sc = scores + (int64_t)q * n_nodes;
+  if (tid == 0) { s_prefix = 0; s_remaining = kTopK; }
+  for (int pass = 0; pass < 8; ++pass) {
+    const int shift = 56 - 8 * pass;
+    hist[tid] = 0;
+    __syncthreads();
+    const unsigned long long prefix = s_prefix;
+    for (int i = tid; i < n_nodes; i += 256) {
+      const double v = sc[i];
+      const unsigned long long k = rank_key_bits(v, i == root_id || v != v);
+      if (pass == 0 || (k >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int need = s_remaining, cum = 0, bsel = 0;
+      for (int bb = 255; bb >= 0; --bb) {
+        if (cum + (int)hist[bb] >= need) { bsel = bb; break; }
+        cum += (int)hist[bb];
+      }
+      s_prefix = prefix | ((unsigned long long)bsel << shift);
+      s_remaining = need - cum;  // still to take from the selected bin
+    }
+    __syncthreads();
+  }
+  const unsigned long long T = s_prefix;  // the KTOP-th largest key
+  const int need_eq = s_remaining;        // how many entries equal to T belong to the top KTOP
+  if (tid == 0) { s_gt = 0; s_eq_base = 0; }
+  __syncthreads();
+  for (int base = 0; base < n_nodes; base += 256) {  // ascending edge order: ties keep the smallest ids
+    const int i = base + tid;
+    unsigned long long k = 0;
+    bool gt = false, eq = false;
+    if (i < n_nodes) {
+      const double v = sc[i];
+      k = rank_key_bits(v, i == root_id || v != v);
+      gt = k > T; eq = k == T;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, eq);
+    if ((tid & 31) == 0) warp_cnt[tid >> 5] = __popc(bal);
+    __syncthreads();
+    int before = s_eq_base;
+    for (int w = 0; w < (tid >> 5); ++w) before += warp_cnt[w];
+    const int my_eq_rank = before + __popc(bal & ((1u << (tid & 31)) - 1u));
+    if (gt) { const int slot = atomicAdd(&s_gt, 1); skey[slot] = k; sidx[slot] = i; }
+    if (eq && my_eq_rank < need_eq) { const int slot = kTopK - 1 - my_eq_rank; skey[slot] = k; sidx[slot] = i; }
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += warp_cnt[w]; s_eq_base += t; }
+    __syncthreads();
+  }
+  // bitonic sort of the KTOP (key, id) pairs: key descending, id ascending
+  unsigned long long mk = skey[tid];
+  int mi = sidx[tid];
+  for (int size = 2; size <= kTopK; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      skey[tid] = mk; sidx[tid] = mi;
+      __syncthreads();
+      const int partner = tid ^ stride;
+      const unsigned long long pk = skey[partner];
+      const int pi = sidx[partner];
+      const bool up = (tid & size) == 0;               // this block of the network sorts "forward"
+      const bool mine_first = mk > pk || (mk == pk && mi < pi);  // (key desc, id asc) order
+      const bool keep_mine = ((tid < partner) == up) ? mine_first : !mine_first;
+      if (!keep_mine) { mk = pk; mi = pi; }
+    }
+  rank_loc[(int64_t)q * n_nodes + tid] = mi;
 }
 
 // FP64 FMA throughput probe: 8 independent chains per thread.

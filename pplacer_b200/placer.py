@@ -201,6 +201,13 @@ class Placer:
         _lib.check(_lib.load().pp_phase_times_ms(self.ctx, _lib.dp(out), 1 if reset else 0))
         return out
 
+    def set_rank_mode(self, mode: int):
+        """0 truncated ranking on large trees (default), 1 always the full sort."""
+        _lib.check(_lib.load().pp_set_rank_mode(self.ctx, int(mode)))
+
+    def rank_fallbacks(self) -> int:
+        return int(_lib.load().pp_rank_fallbacks(self.ctx))
+
     def three_tax_work(self, reset: bool = False) -> np.ndarray:
         """[pendant calls, distal calls, pendant call-sites, distal call-sites] of the warp engine."""
         out = np.zeros(4)

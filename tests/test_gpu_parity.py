@@ -448,3 +448,26 @@ def test_second_stage_work_counters(c2_small):
     assert w[0] > 0 and w[1] > 0 and w[0] + w[1] == info["n_like_calls"].sum()
     nq = seqio.informative(q).sum(axis=1)
     assert nq.min() * (w[0] + w[1]) <= w[2] + w[3] <= nq.max() * (w[0] + w[1])
+
+
+def test_truncated_ranking_equals_full_sort_and_falls_back(c2_small):
+    """Large trees rank with topk_rank_kernel (first 256 entries of Fig.enum_by_score's order); the
+    placements must be byte-identical to the full segmented sort, also when a query runs through more
+    than 256 locations and the batch is redone on the full order."""
+    prob, p = c2_small                                  # 1598 nodes > 1024: the truncated ranking is used
+    q = prob.query_chars[:96]
+    try:
+        p.set_rank_mode(1)
+        full, n_full, st_full, _ = p.place(q, p.prefs())
+        wide_full, nw_full, _, iw_full = p.place(q[:6], p.prefs(max_pitches=300, max_strikes=300, strike_box=1e9), debug=True)
+        p.set_rank_mode(0)
+        before = p.rank_fallbacks()
+        got, n_got, st_got, _ = p.place(q, p.prefs())
+        assert p.rank_fallbacks() == before             # defaults never leave the first 256 ranks
+        assert got.tobytes() == full.tobytes() and np.array_equal(n_got, n_full) and np.array_equal(st_got, st_full)
+        wide, nw, _, iw = p.place(q[:6], p.prefs(max_pitches=300, max_strikes=300, strike_box=1e9), debug=True)
+        assert p.rank_fallbacks() == before + 1         # 301 pitches per query: fallback to the full order
+        assert (iw["n_pitches"] == 301).all() and np.array_equal(iw["n_pitches"], iw_full["n_pitches"])
+        assert wide.tobytes() == wide_full.tobytes() and np.array_equal(nw, nw_full)
+    finally:
+        p.set_rank_mode(0)
