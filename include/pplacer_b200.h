@@ -197,7 +197,7 @@ int pp_three_tax_engine_used(pp_ctx *);
  * and accumulated device time (ms, CUDA events) of the named phase kernels. */
 int64_t pp_kernel_launches(pp_ctx *, int32_t reset);
 int pp_phase_times_ms(pp_ctx *, double *out4 /* prefilter, rank, optimise, pp */, int32_t reset);
-/* Second-stage work done by the warp engine since the last reset: objective calls (three_tax.ml:51-54)
+/* Second-stage work done by engines 2 and 3 since the last reset (engine 1 does not count): objective calls (three_tax.ml:51-54)
  * with the pendant length moving, with the distal length moving, and each weighted by the query's number
  * of informative sites (the unit of SURVEY.md 8d's second-stage roofline).  --pp integrands not counted. */
 int pp_three_tax_work(pp_ctx *, double *out4 /* pendant calls, distal calls, pendant call-sites, distal call-sites */, int32_t reset);
