@@ -247,7 +247,7 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     p.set_stream(stream.cuda_stream)
     p.set_prefilter_kernel({"default": 0, "direct": 1, "table": 2}[args.prefilter])
-    p.set_three_tax_engine({"default": 0, "block": 1, "warp": 2, "group": 3}[args.tt_engine], args.tt_blocks_per_sm)
+    p.set_three_tax_engine({"default": 0, "block": 1, "warp": 2, "group": 3, "eigen": 4}[args.tt_engine], args.tt_blocks_per_sm)
     fp64_peak = p.measure_fp64_peak()
 
     # ---- device-resident arm -------------------------------------------------------------------
@@ -344,7 +344,7 @@ def run_ours(args):
     tt_tflops = tt_flops / (opt_ms * 1e-3) / 1e12 if opt_ms > 0 else 0.0
     engine = p.three_tax_engine_used()
     roofline_tt = {
-        "kernel": {2: "tt_warp_kernel", 3: "tt_group_kernel"}.get(engine, "three_tax_kernel"), "bound": "fp64", "achieved": tt_tflops, "peak": fp64_peak,
+        "kernel": {2: "tt_warp_kernel", 3: "tt_group_kernel", 4: "tt_eigen_kernel"}.get(engine, "three_tax_kernel"), "bound": "fp64", "achieved": tt_tflops, "peak": fp64_peak,
         "unit": "TFLOP/s", "frac": tt_tflops / fp64_peak if fp64_peak else None,
         "peak_source": "DFMA micro-benchmark in this run (pp_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
         "algorithmic_flops_per_step": tt_flops, "ms_per_step": opt_ms,
@@ -416,7 +416,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prefilter", default="default", choices=["default", "direct", "table"],
                     help="prefilter kernel: library default, the FMA form, or the four-base table form")
-    ap.add_argument("--tt-engine", default="default", choices=["default", "block", "warp", "group"],
+    ap.add_argument("--tt-engine", default="default", choices=["default", "block", "warp", "group", "eigen"],
                     help="second-stage engine: library default (group), block-per-candidate, warp-per-candidate, block + shared-memory w")
     ap.add_argument("--tt-blocks-per-sm", type=int, default=0, help="cap on resident blocks of the warp engine (0 = max)")
     args = ap.parse_args()

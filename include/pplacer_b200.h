@@ -186,10 +186,12 @@ int pp_set_rank_mode(pp_ctx *, int32_t mode);
 int pp_rank_fallbacks(pp_ctx *);
 
 /* Which engine runs the second stage (Three_tax.optimize / calc_marg_prob, three_tax.ml:70-83,169-215):
- * 0 = default (engine 3 for the DNA Gamma-4 model with the --pp integrals on engine 2; engine 1 otherwise),
+ * 0 = default (engine 4 for the DNA Gamma-4 model; engine 1 otherwise),
  * 1 = block-per-candidate (every model), 2 = warp-per-candidate, 3 = block-per-candidate with the cached
- * (statd*prox*dist) product in shared memory.  blocks_per_sm > 0 caps the resident thread blocks of engine
- * 2 (8 candidates each); 0 = default.  pp_three_tax_engine_used: 1, 2 or 3. */
+ * (statd*prox*dist) product in shared memory, 4 = block-per-candidate with the pendant objective in the
+ * eigenbasis of the rate matrix (3R multiply-adds per site and call, everything in shared memory).
+ * blocks_per_sm > 0 caps the resident thread blocks of engine 2 (8 candidates each); 0 = default.
+ * pp_three_tax_engine_used: 1, 2, 3 or 4. */
 int pp_set_three_tax_engine(pp_ctx *, int32_t engine, int32_t blocks_per_sm);
 int pp_three_tax_engine_used(pp_ctx *);
 
@@ -201,6 +203,10 @@ int pp_phase_times_ms(pp_ctx *, double *out4 /* prefilter, rank, optimise, pp */
  * with the pendant length moving, with the distal length moving, and each weighted by the query's number
  * of informative sites (the unit of SURVEY.md 8d's second-stage roofline).  --pp integrands not counted. */
 int pp_three_tax_work(pp_ctx *, double *out4 /* pendant calls, distal calls, pendant call-sites, distal call-sites */, int32_t reset);
+/* Per-phase cycle counters of the block engines (only filled when the library is built with -DPPB_TT_PROFILE, see
+ * tools/tt_profile.py): out32[4] scalar cycles, [5] matrix-build cycles, [6] passes with a build, [7] build jobs,
+ * [8+cmd] pass cycles by command, [16+cmd] passes by command, [24] candidates, [25] cycles per candidate summed. */
+int pp_three_tax_profile(pp_ctx *, double *out32, int32_t reset);
 /* FP64 FMA micro-benchmark on the context's device: returns measured DFMA throughput in TFLOP/s. */
 int pp_measure_fp64_peak(pp_ctx *, double *tflops_out);
 

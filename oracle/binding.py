@@ -99,6 +99,17 @@ def lib():
         L.orc_place.argtypes = [C.c_void_p, C.POINTER(Prefs), C.c_int64, c_u8_p, C.c_void_p, c_i32_p,
                                 c_i32_p, C.POINTER(Debug), C.c_int]
         L.orc_three_tax_ll.argtypes = [C.c_void_p, c_u8_p, C.c_int, C.c_double, C.c_double, c_double_p]
+        i, d = C.c_int, C.c_double
+        L.orc_k_gemmish.argtypes = [c_double_p, c_double_p, c_double_p, i, i]
+        L.orc_k_dediagonalize.argtypes = [c_double_p, c_double_p, c_double_p, c_double_p, i]
+        L.orc_k_pairwise_prod.argtypes = [c_double_p, c_double_p, c_double_p, i, i, i, i]
+        L.orc_k_statd_pairwise_prod.argtypes = [c_double_p, c_double_p, c_double_p, c_double_p, i, i, i, i]
+        L.orc_k_log_like3.restype = d
+        L.orc_k_log_like3.argtypes = [c_double_p, c_double_p, c_double_p, c_double_p, i, i, i, i]
+        L.orc_k_masked_logdot.restype = d
+        L.orc_k_masked_logdot.argtypes = [c_double_p, c_double_p, c_u16_p, i, i, i, i]
+        L.orc_k_logdot.restype = d
+        L.orc_k_logdot.argtypes = [c_double_p, c_double_p, i, i, i, i]
         _lib = L
     return _lib
 

@@ -1316,3 +1316,63 @@ int orc_three_tax_ll(orc_ctx *c, const uint8_t *query, int edge, double pendant,
   worker_free(&w);
   return st;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Kernel-level hooks: the static inner loops above on caller-owned arrays, so that             */
+/* tests/test_oracle_vs_ref.py can hold them BIT FOR BIT against the reference's own            */
+/* linear_c.c (oracle/_ref).  Exponent vectors are zero, so the ln2 terms add exactly 0.        */
+/* ------------------------------------------------------------------------------------------ */
+static void k_ctx(orc_ctx *c, int S, int R, int gcat, const double *statd) {
+  memset(c, 0, sizeof *c);
+  c->S = S; c->R = R; c->gcat = gcat; c->Rg = gcat ? 1 : R;
+  if (statd) memcpy(c->statd, statd, sizeof(double) * (size_t)S);
+}
+static glv k_view(const double *a, int64_t *zeros, int n) { glv g; g.n = n; g.e = zeros; g.a = (double *)a; return g; }
+
+void orc_k_gemmish(double *dst, const double *a, const double *b, int S, int n_sites) { gemmish(dst, a, b, S, n_sites); }
+void orc_k_dediagonalize(double *dst, const double *u, const double *lambda, const double *uit, int n) {
+  dediagonalize(dst, u, lambda, uit, n);
+}
+void orc_k_pairwise_prod(double *dst, const double *x, const double *y, int R, int gcat, int n, int S) {
+  orc_ctx c; k_ctx(&c, S, R, gcat, NULL);
+  int64_t *z = (int64_t *)xcalloc((size_t)n, sizeof(int64_t)), *ze = (int64_t *)xcalloc((size_t)n, sizeof(int64_t));
+  glv gx = k_view(x, z, n), gy = k_view(y, z, n), gd = k_view(dst, ze, n);
+  pairwise_prod(&c, &gd, &gx, &gy);
+  free(z); free(ze);
+}
+void orc_k_statd_pairwise_prod(const double *statd, double *dst, const double *a, const double *b, int R, int gcat,
+                               int n, int S) {
+  orc_ctx c; k_ctx(&c, S, R, gcat, statd);
+  int64_t *z = (int64_t *)xcalloc((size_t)n, sizeof(int64_t)), *ze = (int64_t *)xcalloc((size_t)n, sizeof(int64_t));
+  glv ga = k_view(a, z, n), gb = k_view(b, z, n), gd = k_view(dst, ze, n);
+  statd_pairwise_prod(&c, &gd, &ga, &gb);
+  free(z); free(ze);
+}
+double orc_k_log_like3(const double *statd, const double *x, const double *y, const double *z_, int R, int gcat, int n,
+                       int S) {
+  orc_ctx c; k_ctx(&c, S, R, gcat, statd);
+  int64_t *z = (int64_t *)xcalloc((size_t)n, sizeof(int64_t));
+  double *util = (double *)xcalloc((size_t)n, sizeof(double));
+  glv gx = k_view(x, z, n), gy = k_view(y, z, n), gz = k_view(z_, z, n);
+  const double r = log_like3(&c, util, &gx, &gy, &gz);
+  free(z); free(util);
+  return r;
+}
+double orc_k_masked_logdot(const double *x, const double *y, const uint16_t *mask, int R, int gcat, int n, int S) {
+  orc_ctx c; k_ctx(&c, S, R, gcat, NULL);
+  int64_t *z = (int64_t *)xcalloc((size_t)n, sizeof(int64_t));
+  double *util = (double *)xcalloc((size_t)n, sizeof(double));
+  glv gx = k_view(x, z, n), gy = k_view(y, z, n);
+  const double r = masked_logdot(&c, util, &gx, &gy, mask);
+  free(z); free(util);
+  return r;
+}
+double orc_k_logdot(const double *x, const double *y, int R, int gcat, int n, int S) {
+  orc_ctx c; k_ctx(&c, S, R, gcat, NULL);
+  int64_t *z = (int64_t *)xcalloc((size_t)n, sizeof(int64_t));
+  double *util = (double *)xcalloc((size_t)n, sizeof(double));
+  glv gx = k_view(x, z, n), gy = k_view(y, z, n);
+  const double r = logdot_all(&c, util, &gx, &gy);
+  free(z); free(util);
+  return r;
+}

@@ -133,6 +133,18 @@ int orc_place(orc_ctx *, const orc_prefs *, int64_t Q, const uint8_t *query_char
 int orc_three_tax_ll(orc_ctx *, const uint8_t *query_chars, int edge, double pendant, double distal,
                      double *ll_out);
 
+/* kernel-level hooks (inner loops on caller arrays, zero exponents) for the bit-for-bit comparison
+ * with the reference's own linear_c.c in tests/test_oracle_vs_ref.py */
+void orc_k_gemmish(double *dst, const double *a, const double *b, int S, int n_sites);
+void orc_k_dediagonalize(double *dst, const double *u, const double *lambda, const double *uit, int n);
+void orc_k_pairwise_prod(double *dst, const double *x, const double *y, int R, int gcat, int n, int S);
+void orc_k_statd_pairwise_prod(const double *statd, double *dst, const double *a, const double *b, int R, int gcat,
+                               int n, int S);
+double orc_k_log_like3(const double *statd, const double *x, const double *y, const double *z, int R, int gcat, int n,
+                       int S);
+double orc_k_masked_logdot(const double *x, const double *y, const uint16_t *mask, int R, int gcat, int n, int S);
+double orc_k_logdot(const double *x, const double *y, int R, int gcat, int n, int S);
+
 #ifdef __cplusplus
 }
 #endif

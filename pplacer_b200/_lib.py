@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "pp_export_glvs", "pp_get_model", "pp_place", "pp_place_device", "pp_prefilter_scores",
     "pp_three_tax_log_like", "pp_evolve", "pp_discrete_gamma", "pp_diagd", "pp_emper_freq",
     "pp_kernel_launches", "pp_phase_times_ms", "pp_measure_fp64_peak", "pp_set_stream",
-    "pp_set_prefilter_kernel", "pp_prefilter_kernel_used", "pp_set_three_tax_engine", "pp_three_tax_engine_used", "pp_three_tax_work", "pp_set_rank_mode", "pp_rank_fallbacks",
+    "pp_set_prefilter_kernel", "pp_prefilter_kernel_used", "pp_set_three_tax_engine", "pp_three_tax_engine_used", "pp_three_tax_work", "pp_three_tax_profile", "pp_set_rank_mode", "pp_rank_fallbacks",
 ]
 
 
@@ -109,6 +109,7 @@ def load():
     L.pp_set_three_tax_engine.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     L.pp_three_tax_engine_used.argtypes = [C.c_void_p]
     L.pp_three_tax_work.argtypes = [C.c_void_p, c_double_p, C.c_int32]
+    L.pp_three_tax_profile.argtypes = [C.c_void_p, c_double_p, C.c_int32]
     L.pp_set_rank_mode.argtypes = [C.c_void_p, C.c_int32]
     L.pp_rank_fallbacks.argtypes = [C.c_void_p]
     _lib = L

@@ -37,6 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
            "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd[1:1] = os.environ.get("PPB_NVCC_FLAGS", "").split()   # e.g. -DPPB_TT_PROFILE (tools/tt_profile.py)
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -24,6 +24,7 @@
 #include "threetax.cuh"
 #include "threetax_warp.cuh"
 #include "threetax_group.cuh"
+#include "threetax_eigen.cuh"
 
 using namespace ppb;
 
@@ -123,6 +124,10 @@ struct pp_ctx {
   int rank_mode = -1;  // pp_set_rank_mode: -1 = default (PPB_RANK_FULL), 0 truncated ranking when possible, 1 always the full sort
   int rank_fallbacks = 0;  // batches that had to be redone on the full ranking
   bool ttg_pp = true;  // --pp integrals on the block engine (PPB_TTG_PP=0: on the warp engine)
+  // engine 4 (threetax_eigen.cuh): pendant objective in the eigenbasis; needs the zero eigenvalue of the rate matrix
+  EigModel<4> em4{};
+  bool eig_ok = false;
+  int tte_variant = 0;
   int ttw_blocks_per_sm = 0;  // 0 = occupancy maximum
   int ttw_max_blocks = 0;
   DevBuf<int32_t> ord_keys, ord_vals, ord_keys2, ord_vals2;
@@ -302,8 +307,8 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
   c->t.child_ptr = c->d_child_ptr; c->t.child_idx = c->d_child_idx; c->t.parent = c->d_parent; c->t.leaf_row = c->d_leaf_row;
   c->t.ref_codes = c->d_ref_codes; c->t.site_cat = c->d_site_cat;
   CK(cudaMallocHost(&c->h_counters, 8 * sizeof(int)));
-  if ((rc = c->counters.ensure(8)) != PP_OK || (rc = c->tt_work.ensure(4)) != PP_OK) { pp_destroy(c); return rc; }
-  CK(cudaMemsetAsync(c->tt_work.p, 0, 4 * sizeof(unsigned long long), c->stream));
+  if ((rc = c->counters.ensure(8)) != PP_OK || (rc = c->tt_work.ensure(32)) != PP_OK) { pp_destroy(c); return rc; }
+  CK(cudaMemsetAsync(c->tt_work.p, 0, 32 * sizeof(unsigned long long), c->stream));
   // QNG tables -> constant memory
   cudaMemcpyToSymbol(c_qng_x1, ppb_qng_x1, sizeof ppb_qng_x1); cudaMemcpyToSymbol(c_qng_w10, ppb_qng_w10, sizeof ppb_qng_w10);
   cudaMemcpyToSymbol(c_qng_x2, ppb_qng_x2, sizeof ppb_qng_x2); cudaMemcpyToSymbol(c_qng_w21a, ppb_qng_w21a, sizeof ppb_qng_w21a);
@@ -337,8 +342,31 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
     static const bool pp_on_group = [] { const char *e = std::getenv("PPB_TTG_PP"); return e ? std::atoi(e) != 0 : true; }();
     c->ttg_pp = pp_on_group;
     w_slots = std::max(w_slots, (size_t)6 * c->sm_count);
-    c->ttg_blocks = (variant == 0 ? 2 : (variant == 2 || variant == 5) ? 3 : variant == 6 ? 5 : variant == 7 ? 6 : 4) * c->sm_count;  // variants 1, 3, 4: four blocks per SM
+    c->ttg_blocks = 4 * c->sm_count;
     w_slots = std::max(w_slots, (size_t)c->ttg_blocks);
+  }
+  if (ttw_supported(c)) {
+    // engine 4: split off the zero eigenvalue (the rows of a rate matrix sum to zero, so one eigenvalue is 0 up to rounding)
+    int k0 = 0;
+    double lmax = 0.0;
+    for (int k = 0; k < 4; ++k) { if (std::fabs(hm.lam[k]) < std::fabs(hm.lam[k0])) k0 = k; lmax = std::max(lmax, std::fabs(hm.lam[k])); }
+    c->eig_ok = std::fabs(hm.lam[k0]) <= 1e-9 * lmax;
+    EigModel<4> &em = c->em4;
+    std::memcpy(em.statd, hm.statd, sizeof em.statd); std::memcpy(em.lam, hm.lam, sizeof em.lam);
+    std::memcpy(em.x, hm.x, sizeof em.x); std::memcpy(em.xit, hm.xit, sizeof em.xit); std::memcpy(em.rates, hm.rates, sizeof em.rates);
+    int kk[3], nk = 0;
+    for (int k = 0; k < 4; ++k) if (k != k0) kk[nk++] = k;
+    for (int j = 0; j < 3; ++j) em.lamn[j] = hm.lam[kk[j]];
+    for (int s = 0; s < 4; ++s) { em.xz[s] = hm.x[s * 4 + k0]; for (int j = 0; j < 3; ++j) em.xn[s * 3 + j] = hm.x[s * 4 + kk[j]]; }
+    for (int mask = 0; mask < 16; ++mask)
+      for (int j = 0; j < 4; ++j) {
+        const int k = j == 0 ? k0 : kk[j - 1];
+        double acc = 0.0;
+        for (int cc = 0; cc < 4; ++cc) if (mask >> cc & 1) acc += hm.xit[cc * 4 + k];
+        em.xq[mask * 4 + j] = acc;
+      }
+    static const int tte = [] { const char *e = std::getenv("PPB_TTE_VARIANT"); return e ? std::atoi(e) : 0; }();
+    c->tte_variant = tte;
   }
   if ((rc = c->wbuf.ensure(w_slots * c->K * c->Lp)) != PP_OK) { pp_destroy(c); return rc; }
   CK(cudaStreamSynchronize(c->stream));
@@ -653,6 +681,24 @@ static int launch_three_tax_warp(pp_ctx *c, const CandIn *in, CandOut *out, int 
     LAUNCH_CHECK(c);
     return PP_OK;
   }
+  if ((c->tt_engine == 0 || c->tt_engine == 4) && c->eig_ok && prm.mode != TT_MODE_MARGINAL) {  // engine 4: pendant objective in the eigenbasis
+#define PPB_LAUNCH_EIGEN(NW_, MINB_, WS_)                                                                                         \
+  do {                                                                                                                            \
+    const size_t sme = TTEig<4, NW_, WS_>::smem_bytes();                                                                          \
+    static const int cap = [] { const char *e = std::getenv("PPB_TTE_BLOCKS"); return e ? std::atoi(e) : 0; }();                     \
+    const int eblocks = std::min((cap > 0 ? std::min(cap, MINB_) : MINB_) * c->sm_count, n);                                         \
+    CK(cudaFuncSetAttribute(tt_eigen_kernel<4, NW_, MINB_, WS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sme));           \
+    tt_eigen_kernel<4, NW_, MINB_, WS_><<<eblocks, NW_ * 32, sme, c->stream>>>(c->em4, c->g, c->d_bl, c->qsite.p, c->nq.p, in, order, out, n, \
+                                                                           prm, c->wbuf.p, c->counters.p, c->tt_work.p);       \
+  } while (0)
+    if (c->tte_variant == 1) PPB_LAUNCH_EIGEN(4, 3, 608);
+    else if (c->tte_variant == 2) PPB_LAUNCH_EIGEN(8, 2, 960);
+    else if (c->tte_variant == 3) PPB_LAUNCH_EIGEN(4, 2, 960);
+    else PPB_LAUNCH_EIGEN(4, 4, 448);
+#undef PPB_LAUNCH_EIGEN
+    LAUNCH_CHECK(c);
+    return PP_OK;
+  }
   if (c->tt_engine != 2 && prm.mode != TT_MODE_MARGINAL) {  // block per candidate, w in shared memory
     const int gblocks = std::min(c->ttg_blocks, n);
     // the shared-memory attribute is per function, not per context: set it at every launch
@@ -663,14 +709,7 @@ static int launch_three_tax_warp(pp_ctx *c, const CandIn *in, CandOut *out, int 
     tt_group_kernel<4, G_, MINB_, TS_, WS_, RU_><<<gblocks, G_ * 32, smg, c->stream>>>(c->dm, c->g, c->d_bl, c->qsite.p, c->nq.p, in, order, out, \
                                                                                       n, prm, c->wbuf.p, c->counters.p, c->tt_work.p); \
   } while (0)
-    if (c->ttg_variant == 0) PPB_LAUNCH_GROUP(8, 2, 2, 768, false);
-    else if (c->ttg_variant == 2) PPB_LAUNCH_GROUP(4, 3, 1, 512, false);
-    else if (c->ttg_variant == 3) PPB_LAUNCH_GROUP(4, 4, 2, 256, false);
-    else if (c->ttg_variant == 4) PPB_LAUNCH_GROUP(4, 4, 2, 256, true);
-    else if (c->ttg_variant == 5) PPB_LAUNCH_GROUP(4, 3, 2, 512, false);
-    else if (c->ttg_variant == 6) PPB_LAUNCH_GROUP(4, 5, 1, 256, false);
-    else if (c->ttg_variant == 7) PPB_LAUNCH_GROUP(4, 6, 1, 128, false);
-    else PPB_LAUNCH_GROUP(4, 4, 1, 256, false);
+    PPB_LAUNCH_GROUP(4, 4, 2, 256, false);  // the r2 geometry sweep (profiles/README.md) settled on 4 warps x 4 blocks/SM, two sites per thread
 #undef PPB_LAUNCH_GROUP
     LAUNCH_CHECK(c);
     return PP_OK;
@@ -1046,13 +1085,19 @@ extern "C" int pp_set_rank_mode(pp_ctx *c, int32_t mode) {
 extern "C" int pp_rank_fallbacks(pp_ctx *c) { return c ? c->rank_fallbacks : -1; }
 
 extern "C" int pp_set_three_tax_engine(pp_ctx *c, int32_t engine, int32_t blocks_per_sm) {
-  if (!c || engine < 0 || engine > 3 || blocks_per_sm < 0) return fail(PP_EINVAL, "pp_set_three_tax_engine: engine must be 0, 1, 2 or 3");
-  if (engine >= 2 && !ttw_supported(c)) return fail(PP_EINVAL, "pp_set_three_tax_engine: the warp engine exists for the DNA Gamma-4 model only");
+  if (!c || engine < 0 || engine > 4 || blocks_per_sm < 0) return fail(PP_EINVAL, "pp_set_three_tax_engine: engine must be 0, 1, 2, 3 or 4");
+  if (engine >= 2 && !ttw_supported(c)) return fail(PP_EINVAL, "pp_set_three_tax_engine: engines 2-4 exist for the DNA Gamma-4 model only");
+  if (engine == 4 && !c->eig_ok) return fail(PP_EINVAL, "pp_set_three_tax_engine: engine 4 needs a rate matrix with a zero eigenvalue");
   c->tt_engine = engine;
   c->ttw_blocks_per_sm = blocks_per_sm;
   return PP_OK;
 }
-extern "C" int pp_three_tax_engine_used(pp_ctx *c) { return !c ? -1 : !(ttw_supported(c) && c->tt_engine != 1) ? 1 : (c->tt_engine == 2 ? 2 : 3); }
+extern "C" int pp_three_tax_engine_used(pp_ctx *c) {
+  if (!c) return -1;
+  if (!(ttw_supported(c) && c->tt_engine != 1)) return 1;
+  if (c->tt_engine == 2) return 2;
+  return ((c->tt_engine == 0 || c->tt_engine == 4) && c->eig_ok) ? 4 : 3;
+}
 
 extern "C" int64_t pp_kernel_launches(pp_ctx *c, int32_t reset) {
   if (!c) return -1;
@@ -1073,6 +1118,16 @@ extern "C" int pp_three_tax_work(pp_ctx *c, double *out4, int32_t reset) {
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaMemcpy(h, c->tt_work.p, sizeof h, cudaMemcpyDeviceToHost));
   for (int i = 0; i < 4; ++i) out4[i] = (double)h[i];
+  if (reset) CK(cudaMemset(c->tt_work.p, 0, sizeof h));
+  return PP_OK;
+}
+extern "C" int pp_three_tax_profile(pp_ctx *c, double *out32, int32_t reset) {
+  if (!c || !out32) return fail(PP_EINVAL, "pp_three_tax_profile: bad arguments");
+  CK(cudaSetDevice(c->device));
+  unsigned long long h[32];
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(h, c->tt_work.p, sizeof h, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 32; ++i) out32[i] = (double)h[i];
   if (reset) CK(cudaMemset(c->tt_work.p, 0, sizeof h));
   return PP_OK;
 }

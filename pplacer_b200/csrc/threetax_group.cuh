@@ -628,6 +628,10 @@ tt_group_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__res
     __syncthreads();
     const int idx = job[2];
     if (idx >= n) break;
+#ifdef PPB_TT_PROFILE
+    long long pf_t0 = clock64(), pf_scalar = 0, pf_build = 0, pf_pass[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int pf_n[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pf_nb = 0, pf_jobs = 0;
+#endif
     const int ci = order ? order[idx] : idx;
     const CandIn cin = in[ci];
     GCand c;
@@ -664,16 +668,27 @@ tt_group_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__res
       if (tt.optimise) tt.opt_init(prm.tol, prm.max_pend, prm.max_iter);
     }
     for (bool first = true;; first = false) {
+#ifdef PPB_TT_PROFILE
+      const long long pf_a = clock64();
+#endif
       if (warp == 0) {
         if (!tt.scalar_step(first, &ll)) {
           __syncwarp();
           if (lane == 0) { job[0] = TT::CMD_DONE; job[1] = 0; }
         }
       }
+#ifdef PPB_TT_PROFILE
+      const long long pf_b = clock64();
+      pf_scalar += pf_b - pf_a;
+#endif
       __syncthreads();  // the command is posted
       const int cmd = job[0], nj = job[1];
       if (cmd == TT::CMD_DONE) break;
       if (nj > 0) TT::build_jobs(nj);
+#ifdef PPB_TT_PROFILE
+      const long long pf_c = clock64();
+      pf_build += pf_c - pf_b; pf_nb += nj > 0; pf_jobs += nj;
+#endif
       switch (cmd) {
         case TT::CMD_DIST1: tt.template pass_dist<1, TS>(c, TT::OFF_PD); break;
         case TT::CMD_PEND1_FUSED: tt.template pass_pend<1, true, TS>(c, TT::OFF_PQ); break;
@@ -682,7 +697,18 @@ tt_group_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__res
         case TT::CMD_PEND_BATCH_FUSED: tt.template pass_pend<TT::NBP, true, 1>(c, TT::OFF_PB); break;
         default: tt.template pass_pend<TT::NBP, false, 1>(c, TT::OFF_PB); break;
       }
+#ifdef PPB_TT_PROFILE
+      pf_pass[cmd & 7] += clock64() - pf_c; pf_n[cmd & 7]++;
+#endif
     }
+#ifdef PPB_TT_PROFILE
+    if (threadIdx.x == 0) {  // work[4..]: cycles of thread 0 by phase, pass counts by command
+      atomicAdd(work + 4, (unsigned long long)pf_scalar); atomicAdd(work + 5, (unsigned long long)pf_build);
+      atomicAdd(work + 6, (unsigned long long)pf_nb); atomicAdd(work + 7, (unsigned long long)pf_jobs);
+      for (int k = 1; k < 7; ++k) { atomicAdd(work + 8 + k, (unsigned long long)pf_pass[k]); atomicAdd(work + 16 + k, (unsigned long long)pf_n[k]); }
+      atomicAdd(work + 24, 1ull); atomicAdd(work + 25, (unsigned long long)(clock64() - pf_t0));
+    }
+#endif
     if (threadIdx.x == 0) {
       CandOut o;
       o.marg = __longlong_as_double(0x7ff8000000000000LL);

@@ -214,6 +214,12 @@ class Placer:
         _lib.check(_lib.load().pp_three_tax_work(self.ctx, _lib.dp(out), 1 if reset else 0))
         return out
 
+    def three_tax_profile(self, reset: bool = False) -> np.ndarray:
+        """pp_three_tax_profile: per-phase cycle counters (library built with -DPPB_TT_PROFILE)."""
+        out = np.zeros(32)
+        _lib.check(_lib.load().pp_three_tax_profile(self.ctx, _lib.dp(out), 1 if reset else 0))
+        return out
+
     def measure_fp64_peak(self) -> float:
         v = C.c_double(0)
         _lib.check(_lib.load().pp_measure_fp64_peak(self.ctx, C.byref(v)))
