@@ -238,7 +238,20 @@ def run_ours(args):
 
     wl = WORKLOADS[args.workload]
     Q = args.queries if args.queries > 0 else (2000 if args.workload == "c5" else 10_000)
-    prob = build_workload(args.workload, Q, rank)
+    strong = args.scaling == "strong"
+    if strong:
+        # ONE fixed query set (the same on every rank: seeded), contiguous shards (pplacer_b200/shard.py) - what
+        # Multiprocessing's fork-per-job does to a query file (pplacer_run.ml:618-649)
+        from pplacer_b200 import shard
+        Q_total = args.total_queries if args.total_queries > 0 else Q
+        prob = build_workload(args.workload, Q_total, 0)
+        q_lo, q_hi = shard.shard_range(Q_total, rank, world)
+        all_chars = prob.query_chars
+        prob.query_chars = np.ascontiguousarray(all_chars[q_lo:q_hi])
+    else:
+        prob = build_workload(args.workload, Q, rank)
+        Q_total = prob.query_chars.shape[0] * world
+        q_lo = rank * prob.query_chars.shape[0]
     Q = prob.query_chars.shape[0]
     p = Placer(prob, device=local)
     t0 = time.perf_counter(); p.precompute(); torch.cuda.synchronize(); precompute_ms = (time.perf_counter() - t0) * 1e3
@@ -287,19 +300,52 @@ def run_ours(args):
     chars_np = h_chars.numpy()
     for _ in range(min(args.warmup, 2)):
         p.place(chars_np, prefs)
+    from pplacer_b200 import shard as shard_mod
+    gathered = None
+    gather_ms = 0.0
+    if world > 1:   # warm the gather's communicator and buffers
+        shard_mod.gather_results(*p.place(chars_np, prefs)[:3], Q_total, rank, world, device=dev)
     barrier()
     t0 = time.perf_counter()
     with torch.cuda.stream(stream):
         ev0.record(stream)
         for _ in range(args.steps):
             out, n_out, st, _ = p.place(chars_np, prefs)
+            if world > 1:
+                # the path's one collective: the final gather of the result records on rank 0 (NCCL gather of the
+                # pp_result bytes, torch.distributed), inside the end-to-end region
+                tg = time.perf_counter()
+                gathered = shard_mod.gather_results(out, n_out, st, Q_total, rank, world, device=dev)
+                gather_ms += (time.perf_counter() - tg) * 1e3
         ev1.record(stream)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), 0.0))
     e2e_value = total_q / (e2e_ms * 1e-3)
+    gather_ms = max_over_ranks(gather_ms) / args.steps
     clocks = sampler.stop() if rank == 0 else None
     assert np.array_equal(n_out, n_host) and np.array_equal(st, st_host), "device and host entry points disagree"
+    gather_check = None
+    if world > 1 and rank == 0:
+        # sharded == single GPU: rank 0 recomputes a sample of the LAST rank's queries on its own GPU and compares the
+        # gathered records byte for byte (placements do not depend on the batch they are computed in)
+        g_out, g_n, g_st = gathered
+        assert g_out.shape[0] == Q_total
+        assert np.array_equal(g_out[q_lo:q_lo + Q].tobytes(), out.tobytes()), "rank 0's own shard changed in the gather"
+        n_chk = min(256, Q)
+        if strong:
+            lo = shard_mod.shard_range(Q_total, world - 1, world)[0]
+            chk_chars = np.ascontiguousarray(all_chars[lo:lo + n_chk])
+        else:
+            lo = (world - 1) * Q
+            chk_chars = np.ascontiguousarray(build_workload(args.workload, Q, world - 1).query_chars[:n_chk])
+        c_out, c_n, c_st, _ = p.place(chk_chars, prefs)
+        same = (c_out.tobytes() == g_out[lo:lo + n_chk].tobytes() and np.array_equal(c_n, g_n[lo:lo + n_chk])
+                and np.array_equal(c_st, g_st[lo:lo + n_chk]))
+        assert same, "gathered records of rank %d differ from a single-GPU recomputation" % (world - 1)
+        gather_check = {"collective": "torch.distributed gather over NCCL (pp_result bytes + counts + status) to rank 0, every step",
+                        "bytes_per_rank_per_step": int(Q * (K * 56 + 8)), "ms_per_step_max_over_ranks": gather_ms,
+                        "verified": "%d gathered records of rank %d byte-equal to a single-GPU recomputation on rank 0" % (n_chk, world - 1)}
 
     if rank != 0:
         if world > 1:
@@ -329,11 +375,42 @@ def run_ours(args):
                 "note": "compulsory bytes: one pass over the supernodes (or their four-base table) + query codes + scores"},
         "traffic": None,
     }
+    props = torch.cuda.get_device_properties(dev)
+    sm_mhz = (clocks or {}).get("sm_max_mhz") or getattr(props, "clock_rate", 0) / 1e3 or None
+    peak_theory = props.multi_processor_count * 64 * 2 * float(sm_mhz) * 1e6 / 1e12 if sm_mhz else None   # 64 DFMA lanes per SM per clock
+    units = E * sum_nq                                   # (query, edge, informative site) units per launch
     if used == 2:
-        roofline_prefilter["note"] = ("table form: the four-base table turns a (query, edge, site) unit into one select and one "
-                                      "multiply, so the ALGORITHMIC rate 2RS flops/unit can exceed what the FP64 pipe executes "
-                                      "(frac may pass 1); the kernel is bound by issue slots (ncu: 71 % issue-active, FP64 pipe 6 %); "
-                                      "--prefilter direct runs the FMA form the roofline was defined on")
+        # The table form does NOT execute 2RS flops per unit (the four-base table turns a unit into a select and a
+        # multiply), so it has no place on the FP64 roofline: it is reported in its own unit against its own limiter,
+        # instruction issue (ncu, profiles/: issue-active and FP64-pipe fractions of the committed capture).
+        roofline_prefilter.update({
+            "bound": "issue", "achieved": units / (pre_ms * 1e-3) / 1e9 if pre_ms > 0 else 0.0, "unit": "G units/s",
+            "peak": None, "frac": None, "peak_source": None,
+            "ncu": {"issue_active": 0.71, "fp64_pipe": 0.06, "thread_inst_per_unit": 25,
+                    "source": "profiles/r2v_full_ncu.txt (same kernel, same geometry)"},
+            "algorithmic_tflops_equivalent": pre_tflops,
+            "note": "table form: one select + one multiply per (query, edge, site) unit; issue-bound, not FP64-bound - no FP64 "
+                    "fraction is claimed for it; roofline.prefilter_direct carries the FMA form the FP64 roofline is defined on",
+        })
+    # the graded prefilter form: K = R*S DFMAs per unit exactly as ten_masked_logdot_c writes them (linear_c.c:465),
+    # timed on the same batch outside the step loop (pp_prefilter_time: CUDA events on the launching stream)
+    roofline_direct = None
+    if not args.no_direct_prefilter and world == 1:
+        try:
+            d_ms = p.prefilter_time_ms(prob.query_chars, kernel=1, reps=2)
+            d_tf = pre_flops / (d_ms * 1e-3) / 1e12
+            roofline_direct = {
+                "kernel": "prefilter_direct_kernel", "bound": "fp64", "achieved": d_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": d_tf / fp64_peak if fp64_peak else None, "peak_theoretical": peak_theory,
+                "frac_of_theoretical": d_tf / peak_theory if peak_theory else None,
+                "peak_source": "DFMA micro-benchmark in this run (pp_measure_fp64_peak); peak_theoretical = SMs x 64 x 2 x SM clock",
+                "algorithmic_flops_per_launch": pre_flops, "ms_per_launch": d_ms, "units_per_launch": units,
+                "hbm": {"achieved": ((8.0 * R * S + 4.0) * p.L * (E + 1) + Q * p.L + 8.0 * Q * (E + 1)) / (d_ms * 1e-3) / 1e9,
+                        "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "peak_source": peaks_src},
+                "note": "one launch over the step's whole batch, not part of the timed step (the step uses the table form)",
+            }
+        except Exception as ex:   # e.g. a model without a direct/table split
+            roofline_direct = {"error": str(ex)}
     # second stage: unit = one objective evaluation on n_q sites.  A distal move re-evolves the
     # distal and proximal GLVs (2 x 2RS^2 flops per site) and takes log_like3 (4RS); a pendant move is a
     # P-column lookup plus log_like3.  Compulsory bytes: the d/p gathers 2*8*R*S per site of a distal
@@ -375,6 +452,9 @@ def run_ours(args):
     roofline["share_of_step_ms"] = share
     roofline["step_ms"] = ms / args.steps
     roofline["other_kernel"] = roofline_prefilter if dominant_tt else roofline_tt
+    roofline["peak_theoretical"] = peak_theory
+    if roofline_direct is not None:
+        roofline["prefilter_direct"] = roofline_direct
 
     # ---- CPU baseline on a bounded sample ------------------------------------------------------
     cpu = None
@@ -386,10 +466,12 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": "placements/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl[2], "queries_per_gpu_per_step": Q, "flags": wl[3],
-                   "sharding": "queries sharded over ranks, reference GLVs replicated, no data-path collective",
+        "config": {"workload": wl[2], "queries_per_gpu_per_step": Q, "queries_per_step_all_gpus": int(Q_total), "flags": wl[3],
+                   "sharding": ("one fixed query set sharded over ranks (strong scaling)" if strong else "every rank places its own queries (weak scaling)")
+                               + ", reference GLVs replicated, no data-path collective; results gathered on rank 0 inside e2e",
+                   "gather": gather_check,
                    "l2": "inputs larger than L2: supernodes %.0f MB + darr/parr %.0f MB per pass" % (
                        8.0 * R * S * p.L * (E + 1) / 1e6, 16.0 * R * S * p.L * (E + 1) / 1e6),
                    "placed_ok_frac": float((st_host == 0).mean()), "mean_kept": float(n_host.mean())},
@@ -414,6 +496,10 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline sample budget")
     ap.add_argument("--ref-step-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-direct-prefilter", action="store_true", help="skip the extra launch that times the direct-FMA prefilter form")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = every rank places its own --queries; strong = one fixed set of --total-queries sharded over the ranks")
+    ap.add_argument("--total-queries", type=int, default=0, help="--scaling strong: size of the fixed query set (default: --queries)")
     ap.add_argument("--prefilter", default="default", choices=["default", "direct", "table"],
                     help="prefilter kernel: library default, the FMA form, or the four-base table form")
     ap.add_argument("--tt-engine", default="default", choices=["default", "block", "warp", "group", "eigen"],

@@ -155,6 +155,11 @@ int pp_place_device(pp_ctx *, const pp_prefs *, int64_t Q, const uint8_t *d_quer
 /* Stage-level entry points (host buffers) for parity tests against the oracle / linear_c.c. */
 int pp_prefilter_scores(pp_ctx *, double start_pend, int64_t Q, const uint8_t *query_chars,
                         double *scores /* Q x n_nodes, NaN at root */, int32_t kernel /* 0 default, 1 direct-FMA, 2 table */);
+/* The same prefilter pass timed on the device: after one untimed launch, `reps` launches of the chosen kernel
+ * form over the same Q queries bracketed by CUDA events on the context's stream; *ms_per_launch is their mean.
+ * (bench.py reports the direct-FMA form against the FP64 roofline next to the default table form.) */
+int pp_prefilter_time(pp_ctx *, double start_pend, int64_t Q, const uint8_t *query_chars, int32_t kernel, int32_t reps,
+                      double *ms_per_launch);
 int pp_three_tax_log_like(pp_ctx *, int64_t n, const uint8_t *query_chars /* n x L */, const int32_t *edge,
                           const double *pendant, const double *distal, double *ll_out);
 /* dst = evolve(src, bl) on GLVs given in the reference layout (n_sites sites; Gcat uses site_cat of

@@ -22,7 +22,7 @@ PP_OK, PP_EINVAL, PP_ENODEVICE, PP_ECUDA, PP_ENOMEM, PP_ESTATE = 0, 1, 2, 3, 4, 
 
 EXPORTED_SYMBOLS = [
     "pp_last_error", "pp_abi_version", "pp_default_prefs", "pp_create", "pp_destroy", "pp_precompute",
-    "pp_export_glvs", "pp_get_model", "pp_place", "pp_place_device", "pp_prefilter_scores",
+    "pp_export_glvs", "pp_get_model", "pp_place", "pp_place_device", "pp_prefilter_scores", "pp_prefilter_time",
     "pp_three_tax_log_like", "pp_evolve", "pp_discrete_gamma", "pp_diagd", "pp_emper_freq",
     "pp_kernel_launches", "pp_phase_times_ms", "pp_measure_fp64_peak", "pp_set_stream",
     "pp_set_prefilter_kernel", "pp_prefilter_kernel_used", "pp_set_three_tax_engine", "pp_three_tax_engine_used", "pp_three_tax_work", "pp_three_tax_profile", "pp_set_rank_mode", "pp_rank_fallbacks",
@@ -94,6 +94,7 @@ def load():
     L.pp_place_device.argtypes = [C.c_void_p, C.POINTER(Prefs), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p]
     L.pp_prefilter_scores.argtypes = [C.c_void_p, C.c_double, C.c_int64, c_u8_p, c_double_p, C.c_int32]
+    L.pp_prefilter_time.argtypes = [C.c_void_p, C.c_double, C.c_int64, c_u8_p, C.c_int32, C.c_int32, c_double_p]
     L.pp_three_tax_log_like.argtypes = [C.c_void_p, C.c_int64, c_u8_p, c_i32_p, c_double_p, c_double_p, c_double_p]
     L.pp_evolve.argtypes = [C.c_void_p, c_double_p, c_i64_p, C.c_int32, C.c_double, c_double_p, c_i64_p]
     L.pp_discrete_gamma.argtypes = [C.c_int32, C.c_double, c_double_p]

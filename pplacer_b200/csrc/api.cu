@@ -210,6 +210,13 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
   if (m->model_class == 1 && (!m->site_cat || !m->rates)) return fail(PP_EINVAL, "pp_create: Gcat needs rates and site_cat");
   if (L < 1 || t->n_nodes < 2) return fail(PP_EINVAL, "pp_create: empty problem");
   if (L > kSiteMask) return fail(PP_EINVAL, "pp_create: alignment longer than 2^24 - 1 columns");
+  if (t->n_nodes > 2000000) return fail(PP_EINVAL, "pp_create: more than 2,000,000 tree nodes (the edge-major transpose indexes edge tiles by grid.y)");
+  if (t->root_id < 0 || t->root_id >= t->n_nodes) return fail(PP_EINVAL, "pp_create: root_id out of range");
+  if (!t->child_ptr || !t->child_idx || !t->bl || !t->leaf_row || t->child_ptr[0] != 0) return fail(PP_EINVAL, "pp_create: malformed tree arrays");
+  for (int i = 0; i < t->n_nodes; ++i)
+    if (t->child_ptr[i + 1] < t->child_ptr[i] || t->child_ptr[i + 1] > t->n_nodes) return fail(PP_EINVAL, "pp_create: child_ptr must be non-decreasing and bounded by n_nodes");
+  for (int i = 0; i < t->n_nodes; ++i)
+    if (i != t->root_id && !(t->bl[i] >= 0.0)) return fail(PP_EINVAL, "pp_create: missing or negative branch length on a non-root edge (Gtree.get_bl raises in the reference)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(PP_ENODEVICE, "pp_create: no CUDA device (libpplacer_b200 has no CPU fallback)"); }
   if (device < 0 || device >= ndev) return fail(PP_EINVAL, "pp_create: bad device index");
@@ -436,10 +443,8 @@ extern "C" int pp_precompute(pp_ctx *c) {
       }
     }
     for (int s0 = 0; s0 < c->n_nodes; s0 += 65535) {
-      // supernode_kernel indexes nodes by blockIdx.y; shift arrays by chunk via a node offset
-      if (s0 != 0) { rc = fail(PP_EINVAL, "pp_precompute: more than 65535 nodes not supported yet"); break; }
-      dim3 grid(tiles, std::min(65535, c->n_nodes));
-      supernode_kernel<S_, G_><<<grid, kPreThreads, sm_l, c->stream>>>(c->dm, c->g, c->t, Phalf, Rt); LAUNCH_CHECK(c);
+      dim3 grid(tiles, std::min(65535, c->n_nodes - s0));
+      supernode_kernel<S_, G_><<<grid, kPreThreads, sm_l, c->stream>>>(c->dm, c->g, c->t, Phalf, Rt, s0); LAUNCH_CHECK(c);
     }
   });
   if (rc == PP_OK) {
@@ -592,7 +597,9 @@ static int launch_prefilter_table(pp_ctx *c, int64_t Q, double pend, int blocks_
   if (c->mt_pend != pend) {  // four-base table: once per (reference, pendant length)
     if ((rc = c->MT.ensure((size_t)c->L * 4 * c->Np)) || (rc = c->MTe.ensure((size_t)c->L * c->Np))) return rc;
     SnT sn; sn.a = c->snT_a; sn.e = c->snT_e; sn.Np = c->Np; sn.L = c->L; sn.K = c->K; sn.n_nodes = c->n_nodes;
-    mtable_kernel<16><<<dim3((unsigned)((c->Np + 127) / 128), c->L), 128, 0, c->stream>>>(sn, c->tqp, c->MT.p, c->MTe.p); LAUNCH_CHECK(c);
+    for (int s0 = 0; s0 < c->L; s0 += 65535) {  // grid.y is capped at 65535 sites per launch
+      mtable_kernel<16><<<dim3((unsigned)((c->Np + 127) / 128), std::min(65535, c->L - s0)), 128, 0, c->stream>>>(sn, c->tqp, c->MT.p, c->MTe.p, s0); LAUNCH_CHECK(c);
+    }
     c->mt_pend = pend;
   }
   const PreGeom g = prefilter_geometry(c, Q, QT, TE, W, blocks_per_sm);
@@ -646,6 +653,26 @@ extern "C" int pp_prefilter_scores(pp_ctx *c, double start_pend, int64_t Q, cons
   if ((rc = prep_queries(c, Q, c->chars.p)) || (rc = build_query_table(c, start_pend)) || (rc = run_prefilter(c, Q, kernel, start_pend))) return rc;
   CK(cudaMemcpyAsync(scores, c->scores.p, sizeof(double) * (size_t)Q * c->n_nodes, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  return PP_OK;
+}
+
+extern "C" int pp_prefilter_time(pp_ctx *c, double start_pend, int64_t Q, const uint8_t *query_chars, int32_t kernel, int32_t reps,
+                                 double *ms_per_launch) {
+  if (!c || !query_chars || !ms_per_launch || Q < 1 || reps < 1) return fail(PP_EINVAL, "pp_prefilter_time: bad arguments");
+  if (!c->precomputed) return fail(PP_ESTATE, "pp_prefilter_time: call pp_precompute first");
+  CK(cudaSetDevice(c->device));
+  int rc;
+  if ((rc = c->chars.ensure((size_t)Q * c->L))) return rc;
+  CK(cudaMemcpyAsync(c->chars.p, query_chars, (size_t)Q * c->L, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = prep_queries(c, Q, c->chars.p)) || (rc = build_query_table(c, start_pend)) || (rc = run_prefilter(c, Q, kernel, start_pend))) return rc;
+  CK(cudaEventRecord(c->ev[0], c->stream));
+  for (int i = 0; i < reps; ++i)
+    if ((rc = run_prefilter(c, Q, kernel, start_pend))) return rc;
+  CK(cudaEventRecord(c->ev[1], c->stream));
+  CK(cudaEventSynchronize(c->ev[1]));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+  *ms_per_launch = (double)ms / reps;
   return PP_OK;
 }
 

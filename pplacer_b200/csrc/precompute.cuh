@@ -172,11 +172,11 @@ __global__ void set_unit_kernel(GlvArrays g, int which, int node) {
 // grid = (site tiles, n_nodes).
 template <int S, bool GCAT>
 __global__ void __launch_bounds__(kPreThreads)
-supernode_kernel(const DevModel *__restrict__ m, GlvArrays g, TreeDev t, const double *__restrict__ Phalf, int Rt) {
+supernode_kernel(const DevModel *__restrict__ m, GlvArrays g, TreeDev t, const double *__restrict__ Phalf, int Rt, int node0) {
   extern __shared__ double sm[];
   constexpr int RS = p_rstride<S, GCAT>();
   double *P = sm;
-  const int node = blockIdx.y;
+  const int node = node0 + blockIdx.y;  // grid.y is capped at 65535: the launch is chunked over nodes
   const double *Pn = Phalf + (int64_t)node * Rt * S * S;
   for (int i = threadIdx.x; i < Rt * S * S; i += blockDim.x) P[(i / (S * S)) * RS + (i % (S * S))] = Pn[i];
   __syncthreads();

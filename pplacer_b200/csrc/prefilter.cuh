@@ -338,10 +338,10 @@ __global__ void combine_partials_kernel(const double *__restrict__ partial, doub
 // leaves the safe range of the deferred renormalisation.
 template <int K>
 __global__ void __launch_bounds__(128)
-mtable_kernel(const SnT sn, const TqPrimary tp, double *__restrict__ MT, int32_t *__restrict__ MTe) {
+mtable_kernel(const SnT sn, const TqPrimary tp, double *__restrict__ MT, int32_t *__restrict__ MTe, int site0) {
   const int64_t Np = sn.Np;
   const int e = blockIdx.x * 128 + threadIdx.x;
-  const int site = blockIdx.y;
+  const int site = site0 + blockIdx.y;
   if (e >= Np) return;
   const double *col = sn.a + ((int64_t)site * K) * Np + e;
   double v[K];

@@ -32,7 +32,12 @@ class Placer:
         rates = None if m.rates is None else np.ascontiguousarray(m.rates, dtype=np.float64)
         site_cat = None if prob.site_cat is None else np.ascontiguousarray(prob.site_cat, dtype=np.int32)
         ptr, idx = t.csr()
-        bl = np.ascontiguousarray(np.nan_to_num(t.bl, nan=0.0), dtype=np.float64)
+        bl = np.array(t.bl, dtype=np.float64)
+        missing = [i for i in range(t.n_nodes) if i != t.root and not np.isfinite(bl[i])]
+        if missing:   # Gtree.get_bl raises for a missing branch length (gtree.ml); only the root edge may lack one
+            raise ValueError("tree edges without a branch length: %s" % missing[:8])
+        bl[t.root] = 0.0 if not np.isfinite(bl[t.root]) else bl[t.root]
+        bl = np.ascontiguousarray(bl)
         leaf_row = np.ascontiguousarray(prob.leaf_row, dtype=np.int32)
         ref_chars = np.ascontiguousarray(prob.ref_chars, dtype=np.uint8)
         self._keep = (exch, statd, statd_chars, rates, site_cat, ptr, idx, bl, leaf_row, ref_chars)
@@ -98,6 +103,13 @@ class Placer:
         out = np.zeros((q.shape[0], self.n_nodes))
         _lib.check(_lib.load().pp_prefilter_scores(self.ctx, start_pend, q.shape[0], _lib.up(q), _lib.dp(out), kernel))
         return out
+
+    def prefilter_time_ms(self, query_chars: np.ndarray, kernel: int = 0, reps: int = 3, start_pend: float = 0.1) -> float:
+        """pp_prefilter_time: mean device time of one prefilter launch (kernel: 0 default, 1 direct FMA form, 2 table form)."""
+        q = np.ascontiguousarray(query_chars, dtype=np.uint8)
+        ms = C.c_double(0)
+        _lib.check(_lib.load().pp_prefilter_time(self.ctx, start_pend, q.shape[0], _lib.up(q), kernel, reps, C.byref(ms)))
+        return ms.value
 
     def three_tax_log_like(self, query_chars, edge, pendant, distal) -> np.ndarray:
         q = np.ascontiguousarray(query_chars, dtype=np.uint8)

@@ -356,6 +356,60 @@ def test_c2_properties(c2_small, oracle_binding):
     o.close()
 
 
+def test_c5_shape_posterior_probability_matches_oracle(c2_small, oracle_binding):
+    """BASELINE config 5 at its own shape: the C2 tree (800 taxa x 1500 columns) with -p --keep-at-most 40
+    (calc_pp, keep_factor 0.001, max_strikes 20; prefs.ml:198-203): nested QNG integrals over up to 40 kept
+    locations per query, against the oracle."""
+    prob, p = c2_small
+    q = prob.query_chars[:32]
+    kw = dict(calc_pp=1, keep_at_most=40, keep_factor=0.001, max_strikes=20)
+    o = oracle_binding.Oracle(prob)
+    o.precompute()
+    exp, n_exp, st_exp, oi = o.place(q, oracle_prefs(oracle_binding, prob, **kw), n_threads=os.cpu_count(), debug=True)
+    o.close()
+    got, n_got, st_got, gi = p.place(q, p.prefs(pp=True, keep_at_most=40), debug=True)
+    assert n_exp.max() >= 4 and (n_exp > 1).mean() > 0.4   # several kept locations per query: the integrals run for each
+    near = assert_placements_match(got, n_got, st_got, exp, n_exp, st_exp, pp=True, near_tie_ll=1e-3, keep_factor=0.001, keep_at_most=40)
+    assert len(near_queries(near)) <= 1, near
+    assert (gi["n_pitches"] == oi["n_pitches"]).mean() >= 0.95
+    for i in range(len(n_got)):
+        r = got[i][:n_got[i]]
+        assert abs(r["post_prob"].sum() - 1.0) < 1e-9 and abs(r["ml_ratio"].sum() - 1.0) < 1e-9
+
+
+@pytest.mark.slow
+def test_c4_shape_matches_oracle(oracle_binding):
+    """BASELINE config 4 at its own shape: the 10k-taxon tree (19 998 nodes, mean branch length 0.002), where
+    the four-base prefilter table (960 MB) streams from HBM, the edge dimension is tiled (Np) and the ranking is
+    the truncated one.  Prefilter scores over EVERY edge, the head of the ranking and the placements of 32
+    queries against the oracle (its precompute is 11.5 GB of host memory and ~25 s)."""
+    prob = configs.c4(Q=32)
+    assert prob.tree.n_nodes > 19_000
+    o = oracle_binding.Oracle(prob)
+    o.precompute()
+    exp, n_exp, st_exp, oi = o.place(prob.query_chars, oracle_prefs(oracle_binding, prob), n_threads=os.cpu_count(), debug=True)
+    o.close()
+    with Placer(prob) as p:
+        p.precompute()
+        got, n_got, st_got, gi = p.place(prob.query_chars, p.prefs(), debug=True)
+        assert p.rank_fallbacks() == 0
+        direct = p.prefilter_scores(prob.query_chars[:8], kernel=1)
+    root = prob.tree.root
+    keep = np.array([i for i in range(prob.tree.n_nodes) if i != root])
+    g, w = gi["scores"][:, keep], oi["scores"][:, keep]
+    assert np.isfinite(w).all()
+    assert np.all(np.abs(g - w) <= 1e-10 * np.abs(w)), np.abs((g - w) / w).max()
+    d = direct[:, keep]
+    assert np.all(np.abs(d - w[:8]) <= 1e-10 * np.abs(w[:8])), np.abs((d - w[:8]) / w[:8]).max()
+    for q in range(g.shape[0]):
+        og, ow = np.argsort(-g[q], kind="stable"), np.argsort(-w[q], kind="stable")
+        for a, b in zip(og[:41], ow[:41]):
+            assert a == b or abs(w[q][a] - w[q][b]) <= 1e-9 * abs(w[q][a]), (q, a, b)
+    near = assert_placements_match(got, n_got, st_got, exp, n_exp, st_exp, near_tie_ll=1e-3)
+    assert len(near_queries(near)) <= 1, near
+    assert (gi["n_pitches"] == oi["n_pitches"]).mean() >= 0.95
+
+
 def test_device_resident_entry_point_matches_host_entry_point(c2_small):
     import torch
     prob, p = c2_small

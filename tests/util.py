@@ -33,6 +33,8 @@ def assert_placements_match(got, n_got, st_got, exp, n_exp, st_exp, pp=False, na
         entries) with its last entry within near_tie_ll of this edge ("truncation");
       * a differing best edge needs both sides' best log-likelihoods within near_tie_ll of each
         other (two different edges tie for the maximum, e.g. every edge for an all-N query).
+      * a like_weight_ratio / post_prob off by more than 1e-5 must be fully explained by log-likelihood differences
+        that are themselves within tolerance ("stop-point", see _stop_point_explains).
     Anything else raises.  Returns the list of (query, category) near-ties found."""
     near = []
     Q = len(n_exp)
@@ -73,11 +75,55 @@ def assert_placements_match(got, n_got, st_got, exp, n_exp, st_exp, pp=False, na
             assert abs(a["pendant"] - b["pendant"]) <= BL_ABS, (tag, edge, a, b)
             assert abs(a["distal"] - b["distal"]) <= BL_ABS, (tag, edge, a, b)
             if not is_near:
-                assert abs(a["ml_ratio"] - b["ml_ratio"]) <= RATIO_ABS, (tag, edge, a, b)
+                if abs(a["ml_ratio"] - b["ml_ratio"]) > RATIO_ABS:
+                    # like_weight_ratio is exp(ll - best) normalised over the kept set: a log-likelihood that moved
+                    # by d (inside its own 1e-6 relative tolerance) moves the ratios by up to d.  Accept ONLY when that
+                    # is verifiably the whole story (see _stop_point_explains); counted as a near-tie ("stop-point").
+                    assert near_tie_ll is not None and _stop_point_explains(g, e, "ml_ratio", "log_like", near_tie_ll), \
+                        ("%s: ml_ratio differs beyond 1e-5 and the log-likelihood differences do not explain it" % tag, _dump(g), _dump(e))
+                    near.append((q, "stop-point"))
+                    is_near = True
+                    continue
                 if pp:
                     assert abs(a["marginal_like"] - b["marginal_like"]) <= LL_REL * abs(b["marginal_like"]), (tag, edge, a, b)
-                    assert abs(a["post_prob"] - b["post_prob"]) <= RATIO_ABS, (tag, edge, a, b)
+                    if abs(a["post_prob"] - b["post_prob"]) > RATIO_ABS:
+                        assert near_tie_ll is not None and _stop_point_explains(g, e, "post_prob", "marginal_like", near_tie_ll), \
+                            ("%s: post_prob differs beyond 1e-5 and the marginal likelihoods do not explain it" % tag, _dump(g), _dump(e))
+                        near.append((q, "stop-point"))
+                        is_near = True
     return near
+
+
+def _dump(recs):
+    return [(int(r["edge"]), float(r["log_like"]), float(r["pendant"]), float(r["distal"]), float(r["ml_ratio"])) for r in recs]
+
+
+def _stop_point_explains(g, e, ratio_field, ll_field, near_tie_ll):
+    """Brent stops when its bracket is narrower than the tolerance (minimization.ml:88-96), so two runs whose objective
+    values differ in the last bits may stop a step apart: branch lengths within 1e-4 of each other, log-likelihoods
+    within a few 1e-5 ABSOLUTE - inside the 1e-6 relative tolerance, but enough to move a like_weight_ratio by more
+    than 1e-5.  True when (checked, not assumed)
+      * both sides kept the same edges, every log-likelihood within min(near_tie_ll, 1e-6 relative) of the other side's,
+      * each side's ratios are exactly the normalised exp(ll - max ll) of ITS OWN log-likelihoods (ppatteries.ml:175-183)
+        to 1e-9, i.e. nothing but the log-likelihoods differs, and
+      * every ratio difference is bounded by the largest log-likelihood difference (d ratio <= ratio (1 - ratio) d ll)."""
+    ge = {int(r["edge"]): r for r in g}
+    ee = {int(r["edge"]): r for r in e}
+    if set(ge) != set(ee):
+        return False
+    dmax = 0.0
+    for edge in ge:
+        d = abs(float(ge[edge][ll_field]) - float(ee[edge][ll_field]))
+        if not d <= min(near_tie_ll, LL_REL * abs(float(ee[edge][ll_field]))):
+            return False
+        dmax = max(dmax, d)
+    for side in (g, e):
+        ll = np.array([float(r[ll_field]) for r in side])
+        w = np.exp(ll - ll.max())
+        w /= w.sum()
+        if not np.allclose(w, [float(r[ratio_field]) for r in side], rtol=0, atol=1e-9):
+            return False
+    return all(abs(float(ge[k][ratio_field]) - float(ee[k][ratio_field])) <= 2.0 * dmax + 1e-12 for k in ge)
 
 
 def near_queries(near):
