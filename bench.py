@@ -259,7 +259,7 @@ def run_ours(args):
     K = prefs.keep_at_most
     stream = torch.cuda.Stream(device=dev)
     p.set_stream(stream.cuda_stream)
-    p.set_prefilter_kernel({"default": 0, "direct": 1, "table": 2}[args.prefilter])
+    p.set_prefilter_kernel({"default": 0, "direct": 1, "table": 2, "staged": 4, "dmma": 5}[args.prefilter])
     p.set_three_tax_engine({"default": 0, "block": 1, "warp": 2, "group": 3, "eigen": 4}[args.tt_engine], args.tt_blocks_per_sm)
     fp64_peak = p.measure_fp64_peak()
 
@@ -362,9 +362,9 @@ def run_ours(args):
     pre_ms = share["prefilter"]
     pre_tflops = pre_flops / (pre_ms * 1e-3) / 1e12 if pre_ms > 0 else 0.0
     used = p.prefilter_kernel_used()
-    kname = {1: "prefilter_direct_kernel", 2: "prefilter_table_kernel"}.get(used, "?")
+    kname = {1: "prefilter_direct_kernel", 2: "prefilter_table_kernel", 4: "prefilter_staged_kernel<MMA=false>", 5: "prefilter_staged_kernel<MMA=true>"}.get(used, "?")
     # compulsory HBM bytes: one pass over the prefilter copy of the supernodes + query codes + scores
-    pre_bytes = (8.0 * (R * S if used == 1 else 4) + 4.0) * p.L * (E + 1) + Q * p.L + 8.0 * Q * (E + 1)
+    pre_bytes = (8.0 * (4 if used == 2 else R * S) + 4.0) * p.L * (E + 1) + Q * p.L + 8.0 * Q * (E + 1)
     roofline_prefilter = {
         "kernel": kname, "bound": "fp64", "achieved": pre_tflops, "peak": fp64_peak,
         "unit": "TFLOP/s", "frac": pre_tflops / fp64_peak if fp64_peak else None,
@@ -395,12 +395,18 @@ def run_ours(args):
     # the graded prefilter form: K = R*S DFMAs per unit exactly as ten_masked_logdot_c writes them (linear_c.c:465),
     # timed on the same batch outside the step loop (pp_prefilter_time: CUDA events on the launching stream)
     roofline_direct = None
+    other_forms = {}
     if not args.no_direct_prefilter and world == 1:
         try:
-            d_ms = p.prefilter_time_ms(prob.query_chars, kernel=1, reps=2)
+            forms = {"direct": (1, "prefilter_direct_kernel"), "staged": (4, "prefilter_staged_kernel<MMA=false> (TMA bulk copies + mbarrier ring, DFMA)"),
+                     "dmma": (5, "prefilter_staged_kernel<MMA=true> (TMA bulk copies + mbarrier ring, DMMA m8n8k4)")}
+            times = {k: p.prefilter_time_ms(prob.query_chars, kernel=v[0], reps=2) for k, v in forms.items()}
+            best = min(times, key=times.get)
+            d_ms = times[best]
             d_tf = pre_flops / (d_ms * 1e-3) / 1e12
+            other_forms = {k: {"kernel": forms[k][1], "ms_per_launch": t, "frac": pre_flops / (t * 1e-3) / 1e12 / fp64_peak} for k, t in times.items()}
             roofline_direct = {
-                "kernel": "prefilter_direct_kernel", "bound": "fp64", "achieved": d_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                "kernel": forms[best][1], "forms": other_forms, "bound": "fp64", "achieved": d_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": d_tf / fp64_peak if fp64_peak else None, "peak_theoretical": peak_theory,
                 "frac_of_theoretical": d_tf / peak_theory if peak_theory else None,
                 "peak_source": "DFMA micro-benchmark in this run (pp_measure_fp64_peak); peak_theoretical = SMs x 64 x 2 x SM clock",
@@ -500,7 +506,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = every rank places its own --queries; strong = one fixed set of --total-queries sharded over the ranks")
     ap.add_argument("--total-queries", type=int, default=0, help="--scaling strong: size of the fixed query set (default: --queries)")
-    ap.add_argument("--prefilter", default="default", choices=["default", "direct", "table"],
+    ap.add_argument("--prefilter", default="default", choices=["default", "direct", "table", "staged", "dmma"],
                     help="prefilter kernel: library default, the FMA form, or the four-base table form")
     ap.add_argument("--tt-engine", default="default", choices=["default", "block", "warp", "group", "eigen"],
                     help="second-stage engine: library default (group), block-per-candidate, warp-per-candidate, block + shared-memory w")

@@ -20,6 +20,7 @@
 #include "model_host.hpp"
 #include "precompute.cuh"
 #include "prefilter.cuh"
+#include "prefilter_staged.cuh"
 #include "query.cuh"
 #include "threetax.cuh"
 #include "threetax_warp.cuh"
@@ -132,6 +133,10 @@ struct pp_ctx {
   int ttw_max_blocks = 0;
   DevBuf<int32_t> ord_keys, ord_vals, ord_keys2, ord_vals2;
   DevBuf<uint8_t> ord_tmp;
+  // prefilter tiling: queries sorted by the window of sites they cover (prefilter.cuh window_keys_kernel)
+  DevBuf<unsigned long long> win_keys, win_keys2;
+  DevBuf<int32_t> win_vals, qorder, tile_lo, tile_hi;
+  DevBuf<uint8_t> win_tmp;
 };
 
 constexpr int kTTWarpsPerBlock = 8;
@@ -192,6 +197,7 @@ extern "C" void pp_destroy(pp_ctx *c) {
   c->prep_status.release(); c->rank_in.release(); c->rank_loc.release(); c->seg_off.release(); c->i32pool.release();
   c->n_out.release(); c->Tq.release(); c->scores.release(); c->keys_in.release(); c->keys_out.release();
   c->ord_keys.release(); c->ord_vals.release(); c->ord_keys2.release(); c->ord_vals2.release(); c->ord_tmp.release();
+  c->win_keys.release(); c->win_keys2.release(); c->win_vals.release(); c->qorder.release(); c->tile_lo.release(); c->tile_hi.release(); c->win_tmp.release();
   c->wbuf.release(); c->f64pool.release(); c->cand.release(); c->cand_out.release(); c->pp_out.release();
   c->place_out.release(); c->n_calls.release(); c->counters.release(); c->tt_work.release();
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -499,6 +505,14 @@ static int prep_queries(pp_ctx *c, int64_t Q, const uint8_t *d_chars) {
   query_prep_kernel<<<(unsigned)Q, kPrepThreads, 0, c->stream>>>(d_chars, c->d_code_of_char, c->L, c->Lp, c->codes.p, c->qsite.p,
                                                                   c->nq.p, c->prep_status.p, PP_Q_BAD_CHAR, PP_Q_NO_INFORMATIVE);
   LAUNCH_CHECK(c);
+  // tile order of the prefilter: by the window of sites each query covers (library sort of Q keys: plumbing)
+  if ((rc = c->win_keys.ensure(Q)) || (rc = c->win_keys2.ensure(Q)) || (rc = c->win_vals.ensure(Q)) || (rc = c->qorder.ensure(Q))) return rc;
+  window_keys_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, c->stream>>>(c->qsite.p, c->nq.p, (int)Q, c->Lp, c->win_keys.p, c->win_vals.p); LAUNCH_CHECK(c);
+  size_t tmp = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->win_keys.p, c->win_keys2.p, c->win_vals.p, c->qorder.p, (int)Q, 0, 64, c->stream));
+  if ((rc = c->win_tmp.ensure(tmp))) return rc;
+  CK(cub::DeviceRadixSort::SortPairs(c->win_tmp.p, tmp, c->win_keys.p, c->win_keys2.p, c->win_vals.p, c->qorder.p, (int)Q, 0, 64, c->stream));
+  c->launches += 1;
   return PP_OK;
 }
 
@@ -548,8 +562,10 @@ template <int QT>
 static int pack_codes(pp_ctx *c, int64_t Q, int nqt) {
   int rc;
   if ((rc = c->qc.ensure((size_t)nqt * c->L * QT + 16))) return rc;
+  if ((rc = c->tile_lo.ensure(nqt)) || (rc = c->tile_hi.ensure(nqt))) return rc;
   dim3 grid((c->L + 255) / 256, nqt);
-  pack_codes_kernel<QT><<<grid, 256, 0, c->stream>>>(c->codes.p, c->qc.p, (int)Q, c->L, c->Lp); LAUNCH_CHECK(c);
+  pack_codes_kernel<QT><<<grid, 256, 0, c->stream>>>(c->codes.p, c->qorder.p, c->qc.p, (int)Q, c->L, c->Lp); LAUNCH_CHECK(c);
+  tile_range_kernel<QT><<<(nqt + 127) / 128, 128, 0, c->stream>>>(c->qsite.p, c->nq.p, c->qorder.p, (int)Q, nqt, c->Lp, c->tile_lo.p, c->tile_hi.p); LAUNCH_CHECK(c);
   return PP_OK;
 }
 
@@ -557,6 +573,7 @@ static int prefilter_args(pp_ctx *c, int64_t Q, const PreGeom &g, PreArgs *A) {
   int rc;
   A->sn.a = c->snT_a; A->sn.e = c->snT_e; A->sn.Np = c->Np; A->sn.L = c->L; A->sn.K = c->K; A->sn.n_nodes = c->n_nodes;
   A->qc = c->qc.p; A->Tq = c->Tq.p; A->site_cat = c->d_site_cat; A->nq = c->nq.p; A->bad_edge = nullptr;
+  A->order = c->qorder.p; A->tile_lo = c->tile_lo.p; A->tile_hi = c->tile_hi.p;
   A->Q = (int)Q; A->nqt = g.nqt; A->root_id = c->root_id; A->R = c->R; A->nc = c->al.n_codes; A->zs = g.zs; A->sites_per_z = g.sites_per_z;
   if (g.zs > 1) {
     if ((rc = c->partial.ensure((size_t)g.zs * Q * c->n_nodes))) return rc;
@@ -610,7 +627,24 @@ static int launch_prefilter_table(pp_ctx *c, int64_t Q, double pend, int blocks_
   return prefilter_finish(c, Q, g);
 }
 
-// kernel_choice: 0 default (table form for DNA Gamma-4, direct otherwise), 1 direct FMA form, 2 table form
+// staged form (prefilter_staged.cuh): TMA bulk copies + mbarrier ring; MMA = the K-contraction on the FP64 tensor cores
+template <int W, int SPS, int NS, bool MMA, int MINB>
+static int launch_prefilter_staged(pp_ctx *c, int64_t Q, int blocks_per_sm) {
+  int rc;
+  using G = StagedGeom<W, SPS, NS>;
+  const PreGeom g = prefilter_geometry(c, Q, G::QT, 2, W, blocks_per_sm);
+  PreArgs A;
+  if ((rc = pack_codes<G::QT>(c, Q, g.nqt)) || (rc = prefilter_args(c, Q, g, &A))) return rc;
+  const size_t sm = G::smem_bytes(c->al.n_codes);
+  auto kern = prefilter_staged_kernel<W, SPS, NS, MMA, MINB>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  kern<<<dim3(g.gx, g.gy, g.zs), (W + 1) * 32, sm, c->stream>>>(A); LAUNCH_CHECK(c);
+  c->prefilter_kernel_used = MMA ? 5 : 4;
+  return prefilter_finish(c, Q, g);
+}
+
+// kernel_choice: 0 default (table form for DNA Gamma-4, direct otherwise), 1 direct FMA form, 2 table form,
+// 4 staged FMA form, 5 staged DMMA form (DNA Gamma-4)
 static int run_prefilter(pp_ctx *c, int64_t Q, int kernel_choice, double pend) {
   int rc;
   if ((rc = c->scores.ensure((size_t)Q * c->n_nodes))) return rc;
@@ -620,6 +654,18 @@ static int run_prefilter(pp_ctx *c, int64_t Q, int kernel_choice, double pend) {
     // direct form: 8 queries per warp x 4 warps (157 registers, 3 blocks/SM) measured 35.9 ms against 42.9 ms for 16 x 8 (r2q)
     if (kernel_choice == 1) return few ? launch_prefilter_direct<4, false, 4, 2, 8, 1, TQ_CONST>(c, Q, 8) : launch_prefilter_direct<4, false, 4, 2, 8, 4, TQ_CONST>(c, Q, 3);
     if (kernel_choice == 3) return launch_prefilter_direct<4, false, 4, 2, 16, 8, TQ_SMEM>(c, Q, 1);
+    if (kernel_choice == 4 || kernel_choice == 5) {
+      static const int sv = [] { const char *e = std::getenv("PPB_PFS_VARIANT"); return e ? std::atoi(e) : 0; }();
+      if (kernel_choice == 4) {
+        if (sv == 1) return launch_prefilter_staged<8, 4, 4, false, 1>(c, Q, 1);
+        if (sv == 2) return launch_prefilter_staged<4, 2, 4, false, 2>(c, Q, 2);
+        return launch_prefilter_staged<4, 4, 3, false, 2>(c, Q, 2);
+      }
+      if (sv == 1) return launch_prefilter_staged<8, 4, 3, true, 2>(c, Q, 2);
+      if (sv == 2) return launch_prefilter_staged<4, 4, 3, true, 2>(c, Q, 2);
+      if (sv == 3) return launch_prefilter_staged<8, 4, 6, true, 1>(c, Q, 1);
+      return launch_prefilter_staged<4, 2, 4, true, 3>(c, Q, 3);
+    }
     // Geometry of the table form (measured, profiles/README.md r2k): the kernel is latency-bound, so FEW
     // queries per warp and many resident warps win over register-level reuse of the table entries
     // (16 queries per warp, 3 blocks/SM: 18.1 ms; 4 queries per warp, 8 blocks/SM: 13.3 ms for C2).
@@ -1097,8 +1143,8 @@ extern "C" int pp_set_stream(pp_ctx *c, void *cuda_stream) {
 }
 
 extern "C" int pp_set_prefilter_kernel(pp_ctx *c, int32_t kernel) {
-  if (!c || kernel < 0 || kernel > 3) return fail(PP_EINVAL, "pp_set_prefilter_kernel: kernel must be 0, 1, 2 or 3");
-  if (kernel == 2 && !(c->S == 4 && !c->gcat && c->K == 16)) return fail(PP_EINVAL, "pp_set_prefilter_kernel: the table form exists for the DNA Gamma-4 model only");
+  if (!c || kernel < 0 || kernel > 5) return fail(PP_EINVAL, "pp_set_prefilter_kernel: kernel must be 0 ... 5");
+  if ((kernel == 2 || kernel >= 4) && !(c->S == 4 && !c->gcat && c->K == 16)) return fail(PP_EINVAL, "pp_set_prefilter_kernel: the table and staged forms exist for the DNA Gamma-4 model only");
   c->prefilter_choice = kernel;
   return PP_OK;
 }

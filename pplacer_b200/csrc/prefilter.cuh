@@ -46,8 +46,47 @@ struct PreArgs {
   const int32_t *nq;        // [Q]
   double *out;              // zs == 1: scores[Q][n_nodes]; else partial[zs][Q][n_nodes]
   const int32_t *bad_edge;  // table path: edges whose table left the safe range (or null)
+  const int32_t *order;     // [Q] tile slot -> query: queries sorted by the window of sites they cover (window_keys_kernel)
+  const int32_t *tile_lo;   // [n_qtiles] first / one-past-last site at which ANY query of the tile is informative
+  const int32_t *tile_hi;
   int Q, nqt, root_id, R, nc, zs, sites_per_z;
 };
+
+// Reads cover a WINDOW of the alignment (an amplicon, a shotgun read): a tile of queries with similar windows walks
+// only the union of its windows instead of all L columns, and nearly every site it visits is informative for every
+// query of the tile.  Sort key: (first informative site / 64, last informative site); queries without informative
+// sites go last.  Scores do not depend on the tiling (every (query, edge) product is private to one thread and the
+// renormalisations are exact powers of two), so placements are independent of the order (tested).
+__global__ void window_keys_kernel(const int32_t *__restrict__ qsite, const int32_t *__restrict__ nq, int Q, int64_t Lp,
+                                   unsigned long long *__restrict__ keys, int32_t *__restrict__ vals) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const int n = nq[q];
+  unsigned long long key = ~0ull;
+  if (n > 0) {
+    const unsigned first = (unsigned)(qsite[(int64_t)q * Lp] & kSiteMask), last = (unsigned)(qsite[(int64_t)q * Lp + n - 1] & kSiteMask);
+    key = ((unsigned long long)(first >> 6) << 24) | last;
+  }
+  keys[q] = key;
+  vals[q] = q;
+}
+template <int QT>
+__global__ void tile_range_kernel(const int32_t *__restrict__ qsite, const int32_t *__restrict__ nq, const int32_t *__restrict__ order,
+                                  int Q, int nqt, int64_t Lp, int32_t *__restrict__ lo, int32_t *__restrict__ hi) {
+  const int qt = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qt >= nqt) return;
+  int a = 0x7fffffff, b = 0;
+  for (int i = 0; i < QT; ++i) {
+    const int slot = qt * QT + i;
+    if (slot >= Q) break;
+    const int q = order[slot], n = nq[q];
+    if (n <= 0) continue;
+    a = min(a, qsite[(int64_t)q * Lp] & kSiteMask);
+    b = max(b, (qsite[(int64_t)q * Lp + n - 1] & kSiteMask) + 1);
+  }
+  lo[qt] = min(a, b);
+  hi[qt] = b;
+}
 
 // ---- layout kernels ---------------------------------------------------------------------------
 // [n_nodes][K][Lp] (site fastest) -> [L][K][Np] (edge fastest); pad edges get `fill`.
@@ -74,7 +113,7 @@ transpose_to_edge_major_kernel(const T *__restrict__ in, T *__restrict__ out, in
 // codes[Q][Lp] -> qc[n_qtiles][L][QT]
 template <int QT>
 __global__ void __launch_bounds__(256)
-pack_codes_kernel(const uint8_t *__restrict__ codes, uint8_t *__restrict__ qc, int Q, int L, int64_t Lp) {
+pack_codes_kernel(const uint8_t *__restrict__ codes, const int32_t *__restrict__ order, uint8_t *__restrict__ qc, int Q, int L, int64_t Lp) {
   const int site = blockIdx.x * blockDim.x + threadIdx.x;
   const int qt = blockIdx.y;
   if (site >= L) return;
@@ -84,8 +123,8 @@ pack_codes_kernel(const uint8_t *__restrict__ codes, uint8_t *__restrict__ qc, i
     uint32_t v = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int q = qt * QT + i * 4 + j;
-      const uint32_t c = q < Q ? codes[(int64_t)q * Lp + site] : 0xFFu;
+      const int slot = qt * QT + i * 4 + j;
+      const uint32_t c = slot < Q ? codes[(int64_t)order[slot] * Lp + site] : 0xFFu;
       v |= c << (8 * j);
     }
     w[i] = v;
@@ -199,7 +238,7 @@ prefilter_direct_kernel(const PreArgs A) {
   const int L = A.sn.L;
   const int64_t Np = A.sn.Np;
   const int e0 = (blockIdx.y * 32 + lane) * TE;
-  const int s0 = blockIdx.z * A.sites_per_z, s1 = min(L, s0 + A.sites_per_z);
+  const int s0 = max(blockIdx.z * A.sites_per_z, __ldg(A.tile_lo + qt)), s1 = min(min(L, (blockIdx.z + 1) * A.sites_per_z), __ldg(A.tile_hi + qt));
 
   double mm[QT][TE];
   int ex[QT][TE];
@@ -302,8 +341,8 @@ prefilter_direct_kernel(const PreArgs A) {
   double *outz = A.out + (int64_t)blockIdx.z * A.Q * A.sn.n_nodes;
 #pragma unroll
   for (int b = 0; b < QT; ++b) {
-    const int q = qt * QT + b;
-    if (q >= A.Q) continue;
+    if (qt * QT + b >= A.Q) continue;
+    const int q = __ldg(A.order + qt * QT + b);
     const double rate_term = (!GCAT && blockIdx.z == 0) ? (double)((float)A.nq[q]) * log((double)((float)A.R)) : 0.0;  // linear_c.c:536
 #pragma unroll
     for (int a = 0; a < TE; ++a) {
@@ -390,7 +429,7 @@ prefilter_table_kernel(const PreArgs A, const double *__restrict__ MT, const int
   const int L = A.sn.L;
   const int64_t Np = A.sn.Np;
   const int e0 = (blockIdx.y * 32 + lane) * TE;
-  const int s0 = blockIdx.z * A.sites_per_z, s1 = min(L, s0 + A.sites_per_z);
+  const int s0 = max(blockIdx.z * A.sites_per_z, __ldg(A.tile_lo + qt)), s1 = min(min(L, (blockIdx.z + 1) * A.sites_per_z), __ldg(A.tile_hi + qt));
   double mm[QT][TE];
   int ex[QT][TE];
 #pragma unroll
@@ -527,8 +566,8 @@ prefilter_table_kernel(const PreArgs A, const double *__restrict__ MT, const int
   double *outz = A.out + (int64_t)blockIdx.z * A.Q * A.sn.n_nodes;
 #pragma unroll
   for (int b = 0; b < QT; ++b) {
-    const int q = qt * QT + b;
-    if (q >= A.Q) continue;
+    if (qt * QT + b >= A.Q) continue;
+    const int q = __ldg(A.order + qt * QT + b);
     const double rate_term = (blockIdx.z == 0) ? (double)((float)A.nq[q]) * log((double)((float)A.R)) : 0.0;  // linear_c.c:536
 #pragma unroll
     for (int a = 0; a < TE; ++a) {

@@ -116,15 +116,16 @@ def test_prefilter_scores_and_ranking_match_oracle(oracle_binding, name):
             assert a == b or abs(w[q][a] - w[q][b]) <= 1e-9 * abs(w[q][a]), (q, a, b)
 
 
-@pytest.mark.parametrize("name,kernel", [("c1_gtr", 1), ("c1_gtr", 2), ("c1_gtr", 3), ("synth", 1), ("synth", 2), ("synth", 3)])
+@pytest.mark.parametrize("name,kernel", [(n, k) for n in ("c1_gtr", "synth", "zero_cat") for k in (1, 2, 3, 4, 5)])
 def test_prefilter_kernel_variants_match_oracle(oracle_binding, name, kernel):
-    """The direct FMA form (1: evolved-query table in the constant bank, 3: in shared memory) and the
-    four-base table form (2) of the DNA Gamma-4 prefilter all reproduce ten_masked_logdot_c."""
+    """The direct FMA form (1: evolved-query table in the constant bank, 3: in shared memory), the
+    four-base table form (2) and the staged forms (TMA bulk copies + mbarrier ring; 4: FMA, 5: FP64 tensor
+    cores, DMMA) of the DNA Gamma-4 prefilter all reproduce ten_masked_logdot_c."""
     prob, o, p = setup(name, oracle_binding)
     _, _, st, info = o.place(prob.query_chars, oracle_prefs(oracle_binding, prob), n_threads=4, debug=True)
     want = info["scores"]
     got = p.prefilter_scores(prob.query_chars, kernel=kernel)
-    assert p.prefilter_kernel_used() == (2 if kernel == 2 else 1)
+    assert p.prefilter_kernel_used() == {1: 1, 2: 2, 3: 1, 4: 4, 5: 5}[kernel]
     root = prob.tree.root
     keep = [i for i in range(prob.tree.n_nodes) if i != root]
     g, w = got[:, keep], want[:, keep]
@@ -139,7 +140,7 @@ def test_prefilter_many_queries_matches_few_query_kernels(oracle_binding):
     q = prob.query_chars
     big = np.concatenate([q, q, q[:17]], axis=0)
     assert big.shape[0] > 64
-    for kernel in (0, 1, 2, 3):
+    for kernel in (0, 1, 2, 3, 4, 5):
         a = p.prefilter_scores(q, kernel=kernel)
         b = p.prefilter_scores(big, kernel=kernel)
         for lo in (0, q.shape[0]):
@@ -394,13 +395,15 @@ def test_c4_shape_matches_oracle(oracle_binding):
         got, n_got, st_got, gi = p.place(prob.query_chars, p.prefs(), debug=True)
         assert p.rank_fallbacks() == 0
         direct = p.prefilter_scores(prob.query_chars[:8], kernel=1)
+        staged = [p.prefilter_scores(prob.query_chars[:8], kernel=k) for k in (4, 5)]
     root = prob.tree.root
     keep = np.array([i for i in range(prob.tree.n_nodes) if i != root])
     g, w = gi["scores"][:, keep], oi["scores"][:, keep]
     assert np.isfinite(w).all()
     assert np.all(np.abs(g - w) <= 1e-10 * np.abs(w)), np.abs((g - w) / w).max()
-    d = direct[:, keep]
-    assert np.all(np.abs(d - w[:8]) <= 1e-10 * np.abs(w[:8])), np.abs((d - w[:8]) / w[:8]).max()
+    for d in [direct] + staged:
+        d = d[:, keep]
+        assert np.all(np.abs(d - w[:8]) <= 1e-10 * np.abs(w[:8])), np.abs((d - w[:8]) / w[:8]).max()
     for q in range(g.shape[0]):
         og, ow = np.argsort(-g[q], kind="stable"), np.argsort(-w[q], kind="stable")
         for a, b in zip(og[:41], ow[:41]):
@@ -408,6 +411,21 @@ def test_c4_shape_matches_oracle(oracle_binding):
     near = assert_placements_match(got, n_got, st_got, exp, n_exp, st_exp, near_tie_ll=1e-3)
     assert len(near_queries(near)) <= 1, near
     assert (gi["n_pitches"] == oi["n_pitches"]).mean() >= 0.95
+
+
+def test_c2_prefilter_forms_agree(c2_small):
+    """At the bench shape (1598 nodes = 25 edge tiles, windows of 250-1500 sites, 300 queries = multi-warp blocks) every
+    prefilter form gives the same scores: table (default), direct FMA, staged FMA (TMA ring), staged DMMA."""
+    prob, p = c2_small
+    q = prob.query_chars[:300]
+    ref = p.prefilter_scores(q, kernel=1)
+    keep = np.array([i for i in range(prob.tree.n_nodes) if i != prob.tree.root])
+    assert np.isfinite(ref[:, keep]).all() and np.isnan(ref[:, prob.tree.root]).all()
+    for kernel in (0, 2, 4, 5):
+        got = p.prefilter_scores(q, kernel=kernel)
+        assert np.isnan(got[:, prob.tree.root]).all()
+        d = np.abs(got[:, keep] - ref[:, keep])
+        assert np.all(d <= 1e-11 * np.abs(ref[:, keep])), (kernel, float((d / np.abs(ref[:, keep])).max()))
 
 
 def test_device_resident_entry_point_matches_host_entry_point(c2_small):
