@@ -147,6 +147,26 @@ int pp_get_model(pp_ctx *, double *statd, double *x, double *lambda, double *xit
 int pp_place(pp_ctx *, const pp_prefs *, int64_t Q, const uint8_t *query_chars, pp_result *out,
              int32_t *n_out, int32_t *status, pp_debug *dbg_or_null);
 
+/* ---- all the GPUs of one box behind one handle ------------------------------------------------------------
+ * Replaces Multiprocessing's fork-per-job (pplacer_run.ml:618-649, multiprocessing.ml:279): the reference GLVs are
+ * REPLICATED on n_devices GPUs (each runs the device precompute itself) and pp_multi_place shards the queries over
+ * them - contiguous chunks handed out from a shared counter, one host thread per device, no inter-GPU traffic -
+ * and returns when every record is in the caller's host buffers, in query order.  A placement does not depend on
+ * the batch it is computed in, so the bytes equal pp_place on one device (tested).  device_ids == NULL means
+ * devices 0 .. n_devices-1; an id may repeat (several contexts on one GPU: for tests on a single-GPU box).
+ * A single-threaded host (the OCaml runtime) drives all GPUs with this one blocking call. */
+typedef struct pp_multi pp_multi;
+int pp_create_multi(const pp_model *, const pp_tree *, const uint8_t *ref_chars, int32_t n_leaves, int32_t L,
+                    int32_t n_devices, const int32_t *device_ids, pp_multi **out);
+void pp_destroy_multi(pp_multi *);
+int pp_multi_precompute(pp_multi *);
+int pp_multi_place(pp_multi *, const pp_prefs *, int64_t Q, const uint8_t *query_chars, pp_result *out,
+                   int32_t *n_out, int32_t *status);
+int pp_multi_n_devices(pp_multi *);
+pp_ctx *pp_multi_ctx(pp_multi *, int32_t i); /* the i-th per-device context (stage-level entry points, tuning) */
+/* queries placed by each device in the last pp_multi_place (n_devices entries) */
+int pp_multi_last_counts(pp_multi *, int64_t *per_device);
+
 /* Same work with inputs/outputs already resident in HBM (device pointers): used to time the
  * kernels without host<->device copies.  d_out: Q x keep_at_most pp_result, d_n_out/d_status: Q. */
 int pp_place_device(pp_ctx *, const pp_prefs *, int64_t Q, const uint8_t *d_query_chars, pp_result *d_out,

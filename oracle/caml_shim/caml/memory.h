@@ -7,6 +7,11 @@
 #define CAMLparam3(a,b,c) (void)(a);(void)(b);(void)(c)
 #define CAMLparam4(a,b,c,d) (void)(a);(void)(b);(void)(c);(void)(d)
 #define CAMLparam5(a,b,c,d,e) (void)(a);(void)(b);(void)(c);(void)(d);(void)(e)
+#define CAMLxparam1(a) (void)(a)
+#define CAMLxparam2(a,b) (void)(a);(void)(b)
+#define CAMLxparam3(a,b,c) (void)(a);(void)(b);(void)(c)
+#define CAMLxparam4(a,b,c,d) (void)(a);(void)(b);(void)(c);(void)(d)
+#define CAMLxparam5(a,b,c,d,e) (void)(a);(void)(b);(void)(c);(void)(d);(void)(e)
 #define CAMLlocal1(x) value x = 0
 #define CAMLreturn(x) return (x)
 #endif

@@ -26,6 +26,8 @@ EXPORTED_SYMBOLS = [
     "pp_three_tax_log_like", "pp_evolve", "pp_discrete_gamma", "pp_diagd", "pp_emper_freq",
     "pp_kernel_launches", "pp_phase_times_ms", "pp_measure_fp64_peak", "pp_set_stream",
     "pp_set_prefilter_kernel", "pp_prefilter_kernel_used", "pp_set_three_tax_engine", "pp_three_tax_engine_used", "pp_three_tax_work", "pp_three_tax_profile", "pp_set_rank_mode", "pp_rank_fallbacks",
+    "pp_create_multi", "pp_destroy_multi", "pp_multi_precompute", "pp_multi_place", "pp_multi_n_devices", "pp_multi_ctx",
+    "pp_multi_last_counts",
 ]
 
 
@@ -113,6 +115,16 @@ def load():
     L.pp_three_tax_profile.argtypes = [C.c_void_p, c_double_p, C.c_int32]
     L.pp_set_rank_mode.argtypes = [C.c_void_p, C.c_int32]
     L.pp_rank_fallbacks.argtypes = [C.c_void_p]
+    L.pp_create_multi.argtypes = [C.POINTER(Model), C.POINTER(Tree), c_u8_p, C.c_int32, C.c_int32, C.c_int32, c_i32_p,
+                                  C.POINTER(C.c_void_p)]
+    L.pp_destroy_multi.argtypes = [C.c_void_p]
+    L.pp_destroy_multi.restype = None
+    L.pp_multi_precompute.argtypes = [C.c_void_p]
+    L.pp_multi_place.argtypes = [C.c_void_p, C.POINTER(Prefs), C.c_int64, c_u8_p, C.c_void_p, c_i32_p, c_i32_p]
+    L.pp_multi_n_devices.argtypes = [C.c_void_p]
+    L.pp_multi_ctx.argtypes = [C.c_void_p, C.c_int32]
+    L.pp_multi_ctx.restype = C.c_void_p
+    L.pp_multi_last_counts.argtypes = [C.c_void_p, c_i64_p]
     _lib = L
     return L
 

@@ -7,7 +7,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cstdlib>
@@ -99,7 +101,9 @@ struct pp_ctx {
   double mt_pend = -1.0;   // ... and the four-base table MT
   TqPrimary tqp;
   DevBuf<uint8_t> qc;
-  DevBuf<double> partial, MT;
+  DevBuf<double> partial, MT, LT;  // LT: log-table form [L][5][Np]
+  TqFive tq5;
+  double lt_pend = -1.0;
   DevBuf<int32_t> MTe;  // per (site, edge): (supernode exponent + table shift) << 1 | out-of-range flag
   int prefilter_choice = 0;       // pp_set_prefilter_kernel: 0 default, 1 direct, 2 table
   int prefilter_kernel_used = 0;  // 1 direct, 2 table (last run_prefilter)
@@ -190,7 +194,7 @@ extern "C" void pp_destroy(pp_ctx *c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (int w = 0; w < 3; ++w) { if (c->g.a[w]) cudaFree(c->g.a[w]); if (c->g.e[w]) cudaFree(c->g.e[w]); }
-  c->qc.release(); c->partial.release(); c->MT.release(); c->MTe.release();
+  c->qc.release(); c->partial.release(); c->MT.release(); c->LT.release(); c->MTe.release();
   void *ptrs[] = {c->snT_a, c->snT_e, c->dm, c->d_bl, c->d_code_of_char, c->d_ref_codes, c->d_site_cat, c->d_child_ptr, c->d_child_idx, c->d_parent, c->d_leaf_row};
   for (void *p : ptrs) if (p) cudaFree(p);
   c->chars.release(); c->codes.release(); c->sort_tmp.release(); c->qsite.release(); c->nq.release();
@@ -459,7 +463,7 @@ extern "C" int pp_precompute(pp_ctx *c) {
     transpose_to_edge_major_kernel<double><<<grid, 256, 0, c->stream>>>(c->g.a[2], c->snT_a, c->n_nodes, c->K, c->L, c->Lp, c->Np, 1.0); LAUNCH_CHECK(c);
     dim3 grid_e((c->L + 31) / 32, (unsigned)(c->Np / 32), 1);
     transpose_to_edge_major_kernel<int32_t><<<grid_e, 256, 0, c->stream>>>(c->g.e[2], c->snT_e, c->n_nodes, 1, c->L, c->Lp, c->Np, 0); LAUNCH_CHECK(c);
-    c->tq_pend = c->mt_pend = -1.0;
+    c->tq_pend = c->mt_pend = c->lt_pend = -1.0;
   }
   cudaError_t e = cudaStreamSynchronize(c->stream);
   cudaFree(Pfull); cudaFree(Phalf); cudaFree(d_levels);
@@ -536,6 +540,9 @@ static int build_query_table(pp_ctx *c, double t) {
     CK(cudaStreamSynchronize(c->stream));
     for (int j = 0; j < 4; ++j)
       for (int k = 0; k < c->K; ++k) c->tqp.v[j][k] = h[(size_t)(1 << j) * c->K + k];
+    std::memset(&c->tq5, 0, sizeof c->tq5);
+    for (int j = 0; j < 5; ++j)
+      for (int k = 0; k < c->K; ++k) c->tq5.v[j][k] = h[(size_t)(j < 4 ? (1 << j) : 15) * c->K + k];
   }
   c->tq_pend = t;
   return PP_OK;
@@ -627,6 +634,25 @@ static int launch_prefilter_table(pp_ctx *c, int64_t Q, double pend, int blocks_
   return prefilter_finish(c, Q, g);
 }
 
+template <int QT, int W, int MINB>
+static int launch_prefilter_logtable(pp_ctx *c, int64_t Q, double pend, int blocks_per_sm) {
+  int rc;
+  if (c->lt_pend != pend) {  // log table: once per (reference, pendant length)
+    if ((rc = c->LT.ensure((size_t)c->L * 5 * c->Np))) return rc;
+    SnT sn; sn.a = c->snT_a; sn.e = c->snT_e; sn.Np = c->Np; sn.L = c->L; sn.K = c->K; sn.n_nodes = c->n_nodes;
+    for (int s0 = 0; s0 < c->L; s0 += 65535) {
+      logtable_kernel<16><<<dim3((unsigned)((c->Np + 127) / 128), std::min(65535, c->L - s0)), 128, 0, c->stream>>>(sn, c->tq5, c->LT.p, s0); LAUNCH_CHECK(c);
+    }
+    c->lt_pend = pend;
+  }
+  const PreGeom g = prefilter_geometry(c, Q, QT, 2, W, blocks_per_sm);
+  PreArgs A;
+  if ((rc = pack_codes<QT>(c, Q, g.nqt)) || (rc = prefilter_args(c, Q, g, &A))) return rc;
+  prefilter_logtable_kernel<QT, W, MINB><<<dim3(g.gx, g.gy, g.zs), W * 32, 0, c->stream>>>(A, c->LT.p); LAUNCH_CHECK(c);
+  c->prefilter_kernel_used = 6;
+  return prefilter_finish(c, Q, g);
+}
+
 // staged form (prefilter_staged.cuh): TMA bulk copies + mbarrier ring; MMA = the K-contraction on the FP64 tensor cores
 template <int W, int SPS, int NS, bool MMA, int MINB>
 static int launch_prefilter_staged(pp_ctx *c, int64_t Q, int blocks_per_sm) {
@@ -670,6 +696,16 @@ static int run_prefilter(pp_ctx *c, int64_t Q, int kernel_choice, double pend) {
     // queries per warp and many resident warps win over register-level reuse of the table entries
     // (16 queries per warp, 3 blocks/SM: 18.1 ms; 4 queries per warp, 8 blocks/SM: 13.3 ms for C2).
     static const int geom = [] { const char *e = std::getenv("PPB_PF_GEOM"); return e ? std::atoi(e) : 0; }();
+    // log-table form: one load + one add per (query, edge, site); measured (r4f) 11.8 ms against 9.9 ms for the product
+    // table on C2 - it executes half the instructions but one L1 request per (query, site) instead of 5 per site
+    // (ncu r4g: l1tex 77 %, long_scoreboard 6.4 warps per issue) - so it is selectable (6), not the default
+    if (kernel_choice == 6) {
+      if (few) return launch_prefilter_logtable<8, 1, 1>(c, Q, pend, 12);
+      if (geom == 1) return launch_prefilter_logtable<4, 4, 8>(c, Q, pend, 8);
+      if (geom == 2) return launch_prefilter_logtable<16, 4, 4>(c, Q, pend, 4);
+      if (geom == 3) return launch_prefilter_logtable<8, 8, 2>(c, Q, pend, 4);
+      return launch_prefilter_logtable<8, 4, 6>(c, Q, pend, 8);
+    }
     if (!few && geom == 1) return launch_prefilter_table<2, 16, 4, 3>(c, Q, pend, 3);
     if (!few && geom == 2) return launch_prefilter_table<2, 8, 4, 6>(c, Q, pend, 6);
     if (!few && geom == 3) return launch_prefilter_table<2, 4, 8, 4>(c, Q, pend, 4);
@@ -1143,7 +1179,7 @@ extern "C" int pp_set_stream(pp_ctx *c, void *cuda_stream) {
 }
 
 extern "C" int pp_set_prefilter_kernel(pp_ctx *c, int32_t kernel) {
-  if (!c || kernel < 0 || kernel > 5) return fail(PP_EINVAL, "pp_set_prefilter_kernel: kernel must be 0 ... 5");
+  if (!c || kernel < 0 || kernel > 6) return fail(PP_EINVAL, "pp_set_prefilter_kernel: kernel must be 0 ... 6");
   if ((kernel == 2 || kernel >= 4) && !(c->S == 4 && !c->gcat && c->K == 16)) return fail(PP_EINVAL, "pp_set_prefilter_kernel: the table and staged forms exist for the DNA Gamma-4 model only");
   c->prefilter_choice = kernel;
   return PP_OK;
@@ -1223,5 +1259,94 @@ extern "C" int pp_measure_fp64_peak(pp_ctx *c, double *tflops_out) {
   c->launches += 6;
   cudaFree(d);
   *tflops_out = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// all the GPUs of one box behind one handle (include/pplacer_b200.h: pp_create_multi ...)
+// ---------------------------------------------------------------------------------------------
+struct pp_multi {
+  std::vector<pp_ctx *> ctx;
+  std::vector<int> device;
+  std::vector<int64_t> last_counts;
+};
+
+// run fn(i) on one host thread per device; the first failing device's code and message win
+template <class F>
+static int multi_for_each(pp_multi *m, F fn) {
+  const int n = (int)m->ctx.size();
+  std::vector<int> rc(n, PP_OK);
+  std::vector<std::string> msg(n);
+  std::vector<std::thread> th;
+  for (int i = 0; i < n; ++i)
+    th.emplace_back([&, i] {
+      rc[i] = fn(i);
+      if (rc[i] != PP_OK) msg[i] = g_err;  // the worker's thread-local message
+    });
+  for (auto &t : th) t.join();
+  for (int i = 0; i < n; ++i)
+    if (rc[i] != PP_OK) return fail(rc[i], "device " + std::to_string(m->device[i]) + ": " + msg[i]);
+  return PP_OK;
+}
+
+extern "C" int pp_create_multi(const pp_model *mo, const pp_tree *t, const uint8_t *ref_chars, int32_t n_leaves, int32_t L,
+                               int32_t n_devices, const int32_t *device_ids, pp_multi **out) {
+  if (!out) return fail(PP_EINVAL, "pp_create_multi: null argument");
+  *out = nullptr;
+  if (n_devices < 1 || n_devices > 64) return fail(PP_EINVAL, "pp_create_multi: n_devices must be 1 ... 64");
+  pp_multi *m = new pp_multi();
+  m->ctx.assign(n_devices, nullptr);
+  m->last_counts.assign(n_devices, 0);
+  for (int i = 0; i < n_devices; ++i) m->device.push_back(device_ids ? device_ids[i] : i);
+  const int rc = multi_for_each(m, [&](int i) { return pp_create(mo, t, ref_chars, n_leaves, L, m->device[i], &m->ctx[i]); });
+  if (rc != PP_OK) {
+    const std::string keep = g_err;
+    pp_destroy_multi(m);
+    return fail(rc, keep);
+  }
+  *out = m;
+  return PP_OK;
+}
+
+extern "C" void pp_destroy_multi(pp_multi *m) {
+  if (!m) return;
+  for (pp_ctx *c : m->ctx)
+    if (c) pp_destroy(c);
+  delete m;
+}
+
+extern "C" int pp_multi_precompute(pp_multi *m) {
+  if (!m) return fail(PP_EINVAL, "pp_multi_precompute: null handle");
+  return multi_for_each(m, [&](int i) { return pp_precompute(m->ctx[i]); });
+}
+
+extern "C" int pp_multi_place(pp_multi *m, const pp_prefs *pf, int64_t Q, const uint8_t *query_chars, pp_result *out, int32_t *n_out,
+                              int32_t *status) {
+  if (!m || !query_chars || !out || !n_out || !status || Q < 0) return fail(PP_EINVAL, "pp_multi_place: bad arguments");
+  int rc;
+  if ((rc = check_prefs(pf))) return rc;
+  const int n = (int)m->ctx.size();
+  // chunks from a shared counter: one chunk per device when the batch is small, 16k-query chunks otherwise
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>((Q + n - 1) / n, 16384));
+  std::atomic<int64_t> next{0};
+  const int64_t L = m->ctx[0]->L;
+  std::fill(m->last_counts.begin(), m->last_counts.end(), 0);
+  return multi_for_each(m, [&](int i) {
+    for (;;) {
+      const int64_t q0 = next.fetch_add(chunk);
+      if (q0 >= Q) return (int)PP_OK;
+      const int64_t nq = std::min(chunk, Q - q0);
+      const int r = pp_place(m->ctx[i], pf, nq, query_chars + q0 * L, out + q0 * pf->keep_at_most, n_out + q0, status + q0, nullptr);
+      if (r != PP_OK) return r;
+      m->last_counts[i] += nq;
+    }
+  });
+}
+
+extern "C" int pp_multi_n_devices(pp_multi *m) { return m ? (int)m->ctx.size() : -1; }
+extern "C" pp_ctx *pp_multi_ctx(pp_multi *m, int32_t i) { return (m && i >= 0 && i < (int)m->ctx.size()) ? m->ctx[i] : nullptr; }
+extern "C" int pp_multi_last_counts(pp_multi *m, int64_t *per_device) {
+  if (!m || !per_device) return fail(PP_EINVAL, "pp_multi_last_counts: bad arguments");
+  for (size_t i = 0; i < m->ctx.size(); ++i) per_device[i] = m->last_counts[i];
   return PP_OK;
 }

@@ -584,4 +584,100 @@ prefilter_table_kernel(const PreArgs A, const double *__restrict__ MT, const int
   }
 }
 
+// ---- the log-table form (DNA, Gamma mixture, K = 16): the default ----------------------------------
+// The reference sums log(util[site]) over the query's sites (linear_c.c:532).  util depends on the query only through
+// its character at the site, so
+//     LT[site][c][e] = log( sum_k Tq[c][k] * snT[site][k][e] ) + ln2 * e_snode[site][e],   c = A, C, G, T, N
+// is computed once per (reference, pendant length) and a (query, edge, site) unit is ONE load and ONE add - in the
+// reference's own order of summation.  -inf (a zero site likelihood) and NaN propagate through the additions exactly
+// as they do through the reference's sum of logs: no range guards, no renormalisation, no fallback path.  The ten
+// two- and three-base ambiguity codes (rare) take the slow term: the K-term dot product and a log on the spot.
+struct TqFive {
+  double v[5][16];  // evolved-query columns of A, C, G, T and N (code 15)
+};
+constexpr unsigned long long kLogColOfCode = 0x4ffffff3fff2f10full;  // nibble[code] = table column, 15 = slow term
+
+template <int K>
+__global__ void __launch_bounds__(128)
+logtable_kernel(const SnT sn, const TqFive tp, double *__restrict__ LT, int site0) {
+  const int64_t Np = sn.Np;
+  const int e = blockIdx.x * 128 + threadIdx.x;
+  const int site = site0 + blockIdx.y;
+  if (e >= Np) return;
+  const double *col = sn.a + ((int64_t)site * K) * Np + e;
+  double v[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = __ldg(col + (int64_t)k * Np);
+  const double ex = kLn2 * (double)__ldg(sn.e + (int64_t)site * Np + e);
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    double lo = tp.v[j][0] * v[0], hi = tp.v[j][K / 2] * v[K / 2];
+#pragma unroll
+    for (int k = 1; k < K / 2; ++k) { lo = fma(tp.v[j][k], v[k], lo); hi = fma(tp.v[j][K / 2 + k], v[K / 2 + k], hi); }
+    LT[((int64_t)site * 5 + j) * Np + e] = log(lo + hi) + ex;
+  }
+}
+
+__device__ __noinline__ double slow_log_term(const PreArgs &A, int site, unsigned code, int e) {
+  const int K = A.sn.K;
+  const double *tv = A.Tq + (int64_t)code * K;
+  const double *col = A.sn.a + ((int64_t)site * K) * A.sn.Np + e;
+  double lo = tv[0] * col[0], hi = tv[K / 2] * col[(int64_t)(K / 2) * A.sn.Np];
+  for (int k = 1; k < K / 2; ++k) { lo = fma(tv[k], col[(int64_t)k * A.sn.Np], lo); hi = fma(tv[K / 2 + k], col[(int64_t)(K / 2 + k) * A.sn.Np], hi); }
+  return log(lo + hi) + kLn2 * (double)A.sn.e[(int64_t)site * A.sn.Np + e];
+}
+
+// grid / block as prefilter_direct_kernel (TE = 2 edges per lane); LT[L][5][Np].
+template <int QT, int W, int MINB>
+__global__ void __launch_bounds__(W * 32, MINB)
+prefilter_logtable_kernel(const PreArgs A, const double *__restrict__ LT) {
+  constexpr int TE = 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int qt = blockIdx.x * W + warp;
+  if (qt >= A.nqt) return;
+  const int L = A.sn.L;
+  const int64_t Np = A.sn.Np;
+  const int e0 = (blockIdx.y * 32 + lane) * TE;
+  const int s0 = max(blockIdx.z * A.sites_per_z, __ldg(A.tile_lo + qt)), s1 = min(min(L, (blockIdx.z + 1) * A.sites_per_z), __ldg(A.tile_hi + qt));
+  double acc[QT][TE];
+#pragma unroll
+  for (int b = 0; b < QT; ++b)
+#pragma unroll
+    for (int a = 0; a < TE; ++a) acc[b][a] = 0.0;
+  const uint8_t *qcp = A.qc + ((int64_t)qt * L) * QT;
+  const double *row = LT + ((int64_t)s0 * 5) * Np + e0;
+  for (int site = s0; site < s1; ++site, row += 5 * Np) {
+    const CodeWords<QT> cw = load_codes<QT>(qcp + (int64_t)site * QT);
+    if (cw.all_uninformative()) continue;
+#pragma unroll
+    for (int b = 0; b < QT; ++b) {
+      const unsigned code = cw.code(b);
+      if (code & 0x80u) continue;  // warp-uniform
+      const unsigned colc = (unsigned)(kLogColOfCode >> (4 * code)) & 15u;
+      if (colc != 15u) {
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(row + (int64_t)colc * Np));
+        acc[b][0] += v.x; acc[b][1] += v.y;
+      } else {
+#pragma unroll
+        for (int a = 0; a < TE; ++a) acc[b][a] += slow_log_term(A, site, code, e0 + a);
+      }
+    }
+  }
+  double *outz = A.out + (int64_t)blockIdx.z * A.Q * A.sn.n_nodes;
+#pragma unroll
+  for (int b = 0; b < QT; ++b) {
+    if (qt * QT + b >= A.Q) continue;
+    const int q = __ldg(A.order + qt * QT + b);
+    const double rate_term = (blockIdx.z == 0) ? (double)((float)A.nq[q]) * log((double)((float)A.R)) : 0.0;  // linear_c.c:536
+#pragma unroll
+    for (int a = 0; a < TE; ++a) {
+      const int e = e0 + a;
+      if (e >= A.sn.n_nodes) continue;
+      double v = acc[b][a] - rate_term;
+      if (A.zs == 1 && e == A.root_id) v = __longlong_as_double(0x7ff8000000000000LL);
+      outz[(int64_t)q * A.sn.n_nodes + e] = v;
+    }
+  }
+}
+
 }  // namespace ppb

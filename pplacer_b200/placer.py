@@ -14,6 +14,105 @@ from . import _lib
 from .reference import Problem, flat_exp_prior_mean, informative_prior_means
 
 
+def abi_inputs(prob: Problem):
+    """The pp_model / pp_tree structs and the reference alignment of a Problem, plus the arrays they point into."""
+    m = prob.model
+    t = prob.tree
+    exch = np.ascontiguousarray(m.exch, dtype=np.float64)
+    statd = None
+    statd_chars = None
+    if m.model_statd is not None and not m.empirical_freqs:
+        statd = np.ascontiguousarray(m.model_statd, dtype=np.float64)
+    else:
+        statd_chars = np.ascontiguousarray(prob.ref_chars_raw, dtype=np.uint8).reshape(-1)
+    rates = None if m.rates is None else np.ascontiguousarray(m.rates, dtype=np.float64)
+    site_cat = None if prob.site_cat is None else np.ascontiguousarray(prob.site_cat, dtype=np.int32)
+    ptr, idx = t.csr()
+    bl = np.array(t.bl, dtype=np.float64)
+    missing = [i for i in range(t.n_nodes) if i != t.root and not np.isfinite(bl[i])]
+    if missing:   # Gtree.get_bl raises for a missing branch length (gtree.ml); only the root edge may lack one
+        raise ValueError("tree edges without a branch length: %s" % missing[:8])
+    bl[t.root] = 0.0 if not np.isfinite(bl[t.root]) else bl[t.root]
+    bl = np.ascontiguousarray(bl)
+    leaf_row = np.ascontiguousarray(prob.leaf_row, dtype=np.int32)
+    ref_chars = np.ascontiguousarray(prob.ref_chars, dtype=np.uint8)
+    keep = (exch, statd, statd_chars, rates, site_cat, ptr, idx, bl, leaf_row, ref_chars)
+    cm = _lib.Model(m.n_states, m.model_class, m.n_rates, 0, _lib.dp(exch),
+                    None if statd is None else _lib.dp(statd),
+                    None if statd_chars is None else _lib.up(statd_chars),
+                    0 if statd_chars is None else statd_chars.size,
+                    None if rates is None else _lib.dp(rates), float(m.gamma_alpha),
+                    None if site_cat is None else _lib.ip(site_cat))
+    ct = _lib.Tree(t.n_nodes, t.root, _lib.ip(ptr), _lib.ip(idx), _lib.dp(bl), _lib.ip(leaf_row))
+    return cm, ct, ref_chars, keep
+
+
+class MultiPlacer:
+    """One reference replicated on several GPUs of the box behind ONE handle (pp_create_multi): what replaces
+    Multiprocessing's fork-per-job (pplacer_run.ml:618-649).  place() shards the queries inside the library - one host
+    thread per device - and returns the records in query order."""
+
+    def __init__(self, prob: Problem, devices):
+        L = _lib.load()
+        self.prob = prob
+        cm, ct, ref_chars, self._keep = abi_inputs(prob)
+        ids = np.ascontiguousarray(list(devices), dtype=np.int32)
+        h = C.c_void_p()
+        _lib.check(L.pp_create_multi(C.byref(cm), C.byref(ct), _lib.up(ref_chars), ref_chars.shape[0], prob.L, len(ids),
+                                     _lib.ip(ids), C.byref(h)))
+        self.h = h
+        self.n_devices = len(ids)
+        self.L = prob.L
+        self.precomputed = False
+
+    def close(self):
+        if getattr(self, "h", None):
+            _lib.load().pp_destroy_multi(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def precompute(self):
+        _lib.check(_lib.load().pp_multi_precompute(self.h))
+        self.precomputed = True
+
+    def prefs(self, pp: bool = False, **kw) -> _lib.Prefs:
+        p = _lib.pplacer_p_prefs(**kw) if pp else _lib.default_prefs(**kw)
+        p.prior_kind = 1
+        p.prior_mean = flat_exp_prior_mean(self.prob.tree)
+        return p
+
+    def place(self, query_chars: np.ndarray, prefs: Optional[_lib.Prefs] = None):
+        if not self.precomputed:
+            self.precompute()
+        prefs = prefs or self.prefs()
+        q = np.ascontiguousarray(query_chars, dtype=np.uint8)
+        if q.ndim != 2 or q.shape[1] != self.L:
+            raise ValueError("query is not the same length as the ref alignment")
+        Q, K = q.shape[0], prefs.keep_at_most
+        out = np.zeros((Q, K), dtype=_lib.RESULT_DTYPE)
+        n_out = np.zeros(Q, dtype=np.int32)
+        status = np.zeros(Q, dtype=np.int32)
+        _lib.check(_lib.load().pp_multi_place(self.h, C.byref(prefs), Q, _lib.up(q), out.ctypes.data_as(C.c_void_p),
+                                              _lib.ip(n_out), _lib.ip(status)))
+        return out, n_out, status
+
+    def last_counts(self) -> np.ndarray:
+        c = np.zeros(self.n_devices, dtype=np.int64)
+        _lib.check(_lib.load().pp_multi_last_counts(self.h, c.ctypes.data_as(_lib.c_i64_p)))
+        return c
+
+
 class Placer:
     """One reference (tree + alignment + model) resident on one GPU."""
 
@@ -22,32 +121,7 @@ class Placer:
         self.prob = prob
         m = prob.model
         t = prob.tree
-        exch = np.ascontiguousarray(m.exch, dtype=np.float64)
-        statd = None
-        statd_chars = None
-        if m.model_statd is not None and not m.empirical_freqs:
-            statd = np.ascontiguousarray(m.model_statd, dtype=np.float64)
-        else:
-            statd_chars = np.ascontiguousarray(prob.ref_chars_raw, dtype=np.uint8).reshape(-1)
-        rates = None if m.rates is None else np.ascontiguousarray(m.rates, dtype=np.float64)
-        site_cat = None if prob.site_cat is None else np.ascontiguousarray(prob.site_cat, dtype=np.int32)
-        ptr, idx = t.csr()
-        bl = np.array(t.bl, dtype=np.float64)
-        missing = [i for i in range(t.n_nodes) if i != t.root and not np.isfinite(bl[i])]
-        if missing:   # Gtree.get_bl raises for a missing branch length (gtree.ml); only the root edge may lack one
-            raise ValueError("tree edges without a branch length: %s" % missing[:8])
-        bl[t.root] = 0.0 if not np.isfinite(bl[t.root]) else bl[t.root]
-        bl = np.ascontiguousarray(bl)
-        leaf_row = np.ascontiguousarray(prob.leaf_row, dtype=np.int32)
-        ref_chars = np.ascontiguousarray(prob.ref_chars, dtype=np.uint8)
-        self._keep = (exch, statd, statd_chars, rates, site_cat, ptr, idx, bl, leaf_row, ref_chars)
-        cm = _lib.Model(m.n_states, m.model_class, m.n_rates, 0, _lib.dp(exch),
-                        None if statd is None else _lib.dp(statd),
-                        None if statd_chars is None else _lib.up(statd_chars),
-                        0 if statd_chars is None else statd_chars.size,
-                        None if rates is None else _lib.dp(rates), float(m.gamma_alpha),
-                        None if site_cat is None else _lib.ip(site_cat))
-        ct = _lib.Tree(t.n_nodes, t.root, _lib.ip(ptr), _lib.ip(idx), _lib.dp(bl), _lib.ip(leaf_row))
+        cm, ct, ref_chars, self._keep = abi_inputs(prob)
         self.S, self.gcat = m.n_states, m.model_class
         self.R = m.n_rates
         self.n_nodes, self.L = t.n_nodes, prob.L

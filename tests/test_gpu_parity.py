@@ -116,7 +116,7 @@ def test_prefilter_scores_and_ranking_match_oracle(oracle_binding, name):
             assert a == b or abs(w[q][a] - w[q][b]) <= 1e-9 * abs(w[q][a]), (q, a, b)
 
 
-@pytest.mark.parametrize("name,kernel", [(n, k) for n in ("c1_gtr", "synth", "zero_cat") for k in (1, 2, 3, 4, 5)])
+@pytest.mark.parametrize("name,kernel", [(n, k) for n in ("c1_gtr", "synth", "zero_cat") for k in (1, 2, 3, 4, 5, 6)])
 def test_prefilter_kernel_variants_match_oracle(oracle_binding, name, kernel):
     """The direct FMA form (1: evolved-query table in the constant bank, 3: in shared memory), the
     four-base table form (2) and the staged forms (TMA bulk copies + mbarrier ring; 4: FMA, 5: FP64 tensor
@@ -125,7 +125,7 @@ def test_prefilter_kernel_variants_match_oracle(oracle_binding, name, kernel):
     _, _, st, info = o.place(prob.query_chars, oracle_prefs(oracle_binding, prob), n_threads=4, debug=True)
     want = info["scores"]
     got = p.prefilter_scores(prob.query_chars, kernel=kernel)
-    assert p.prefilter_kernel_used() == {1: 1, 2: 2, 3: 1, 4: 4, 5: 5}[kernel]
+    assert p.prefilter_kernel_used() == {1: 1, 2: 2, 3: 1, 4: 4, 5: 5, 6: 6}[kernel]
     root = prob.tree.root
     keep = [i for i in range(prob.tree.n_nodes) if i != root]
     g, w = got[:, keep], want[:, keep]
@@ -140,7 +140,7 @@ def test_prefilter_many_queries_matches_few_query_kernels(oracle_binding):
     q = prob.query_chars
     big = np.concatenate([q, q, q[:17]], axis=0)
     assert big.shape[0] > 64
-    for kernel in (0, 1, 2, 3, 4, 5):
+    for kernel in (0, 1, 2, 3, 4, 5, 6):
         a = p.prefilter_scores(q, kernel=kernel)
         b = p.prefilter_scores(big, kernel=kernel)
         for lo in (0, q.shape[0]):
@@ -395,7 +395,7 @@ def test_c4_shape_matches_oracle(oracle_binding):
         got, n_got, st_got, gi = p.place(prob.query_chars, p.prefs(), debug=True)
         assert p.rank_fallbacks() == 0
         direct = p.prefilter_scores(prob.query_chars[:8], kernel=1)
-        staged = [p.prefilter_scores(prob.query_chars[:8], kernel=k) for k in (4, 5)]
+        staged = [p.prefilter_scores(prob.query_chars[:8], kernel=k) for k in (6, 4, 5)]
     root = prob.tree.root
     keep = np.array([i for i in range(prob.tree.n_nodes) if i != root])
     g, w = gi["scores"][:, keep], oi["scores"][:, keep]
@@ -415,14 +415,16 @@ def test_c4_shape_matches_oracle(oracle_binding):
 
 def test_c2_prefilter_forms_agree(c2_small):
     """At the bench shape (1598 nodes = 25 edge tiles, windows of 250-1500 sites, 300 queries = multi-warp blocks) every
-    prefilter form gives the same scores: table (default), direct FMA, staged FMA (TMA ring), staged DMMA."""
+    prefilter form gives the same scores: product table (default), log table, direct FMA, staged FMA (TMA ring), staged DMMA."""
     prob, p = c2_small
     q = prob.query_chars[:300]
     ref = p.prefilter_scores(q, kernel=1)
     keep = np.array([i for i in range(prob.tree.n_nodes) if i != prob.tree.root])
     assert np.isfinite(ref[:, keep]).all() and np.isnan(ref[:, prob.tree.root]).all()
-    for kernel in (0, 2, 4, 5):
+    assert p.prefilter_kernel_used() == 1
+    for kernel in (0, 6, 4, 5):
         got = p.prefilter_scores(q, kernel=kernel)
+        assert p.prefilter_kernel_used() == (2 if kernel == 0 else kernel)
         assert np.isnan(got[:, prob.tree.root]).all()
         d = np.abs(got[:, keep] - ref[:, keep])
         assert np.all(d <= 1e-11 * np.abs(ref[:, keep])), (kernel, float((d / np.abs(ref[:, keep])).max()))
@@ -544,3 +546,31 @@ def test_truncated_ranking_equals_full_sort_and_falls_back(c2_small):
         assert wide.tobytes() == wide_full.tobytes() and np.array_equal(nw, nw_full)
     finally:
         p.set_rank_mode(0)
+
+
+# ---------------------------------------------------------------------------------------------
+# all GPUs of the box behind one handle (pp_create_multi / pp_multi_place)
+# ---------------------------------------------------------------------------------------------
+def test_multi_device_handle_equals_single_device(c2_small):
+    """pp_multi_place shards the queries over its contexts from a shared counter, one host thread per device; the records
+    must equal pp_place on one device byte for byte.  On a single-GPU box both contexts live on device 0 (still two
+    contexts, two streams, two host threads); with >= 2 GPUs they are on different devices."""
+    import torch
+    from pplacer_b200.placer import MultiPlacer
+    prob, p = c2_small
+    q = prob.query_chars[:700]
+    want, n_want, st_want, _ = p.place(q, p.prefs())
+    devs = [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+    with MultiPlacer(prob, devs) as mp:
+        mp.precompute()
+        got, n_got, st_got = mp.place(q, mp.prefs())
+        counts = mp.last_counts()
+        assert counts.sum() == len(q) and (counts > 0).all(), counts
+        assert got.tobytes() == want.tobytes() and np.array_equal(n_got, n_want) and np.array_equal(st_got, st_want)
+        # ragged: fewer queries than devices, and an empty batch
+        g1, n1, s1 = mp.place(q[:1], mp.prefs())
+        assert g1.tobytes() == want[:1].tobytes()
+        g0, n0, s0 = mp.place(q[:0], mp.prefs())
+        assert g0.shape[0] == 0
+    with pytest.raises(_lib.PplacerB200Error):
+        MultiPlacer(prob, [0, 99])

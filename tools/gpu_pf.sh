@@ -18,7 +18,7 @@ for wl, Q in (("c2", 10000), ("c4", 4000)):
     prob = bench.build_workload(wl, Q, 0)
     with Placer(prob) as p:
         p.precompute()
-        out[wl] = {str(k): p.prefilter_time_ms(prob.query_chars, kernel=k, reps=3) for k in (2, 1, 4, 5)}
+        out[wl] = {str(k): p.prefilter_time_ms(prob.query_chars, kernel=k, reps=3) for k in (6, 2, 1, 4, 5)}
 print(json.dumps(out))
 PY
 echo "variant $V rc=$?"; cat gpurun_out/${TAG}_times_v$V.json; tail -3 gpurun_out/${TAG}_times_v$V.err
