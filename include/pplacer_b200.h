@@ -137,6 +137,14 @@ int pp_create(const pp_model *, const pp_tree *, const uint8_t *ref_chars /* n_l
 void pp_destroy(pp_ctx *);
 /* a4-a9 on device (level-order pruning, exponent pulls at -50 then -10, supernodes). */
 int pp_precompute(pp_ctx *);
+/* Gcat_model.refine (gcat_model.ml:387-419; pplacer_run.ml:316-317, --always-refine): re-derive the Price-CAT site
+ * categories on the device - one tree-likelihood attempt per rate category with every site in that category
+ * (Like_stree.site_log_like_arr, like_stree.ml:113-131), best category per site under FastTree's Gamma(3, 1/3) prior.
+ * Replaces the context's site categories; call before pp_precompute.  site_cat_out [L] and site_ll_out [R x L]
+ * (log-likelihood of every site under every category) may be NULL. */
+int pp_refine_site_categories(pp_ctx *, int32_t *site_cat_out, double *site_ll_out);
+/* --check-like (pplacer_run.ml:344-377): out [n_nodes x 2] = (tree_likelihood, supernode_like) seen from every edge. */
+int pp_check_like(pp_ctx *, double *out);
 /* Copy GLVs [node_begin, node_end) of darr (which=0) / parr (1) / snodes (2) back in the REFERENCE
  * layout: Gmix a[R][L][S], Gcat a[L][S] per node (linear_c.c:5-12); e[L] as int64 per node. */
 int pp_export_glvs(pp_ctx *, int32_t which, int32_t node_begin, int32_t node_end, double *a, int64_t *e);

@@ -99,6 +99,7 @@ def lib():
         L.orc_place.argtypes = [C.c_void_p, C.POINTER(Prefs), C.c_int64, c_u8_p, C.c_void_p, c_i32_p,
                                 c_i32_p, C.POINTER(Debug), C.c_int]
         L.orc_three_tax_ll.argtypes = [C.c_void_p, c_u8_p, C.c_int, C.c_double, C.c_double, c_double_p]
+        L.orc_refine_site_categories.argtypes = [C.c_void_p, c_i32_p, c_double_p]
         i, d = C.c_int, C.c_double
         L.orc_k_gemmish.argtypes = [c_double_p, c_double_p, c_double_p, i, i]
         L.orc_k_dediagonalize.argtypes = [c_double_p, c_double_p, c_double_p, c_double_p, i]
@@ -269,6 +270,16 @@ class Oracle:
     def precompute(self):
         lib().orc_precompute(self.ctx)
         self.precomputed = True
+
+    def refine_site_categories(self, want_site_ll: bool = False):
+        """Gcat_model.refine (gcat_model.ml:387-419); the context keeps the new categories."""
+        cats = np.zeros(self.L, dtype=np.int32)
+        sll = np.zeros((self.R, self.L)) if want_site_ll else None
+        st = lib().orc_refine_site_categories(self.ctx, ip(cats), None if sll is None else dp(sll))
+        if st:
+            raise RuntimeError("a site has zero likelihood")
+        self.precomputed = False
+        return (cats, sll) if want_site_ll else cats
 
     def glv(self, which: int, node: int):
         """(a, e) in the reference layout: Gmix a[R][L][S], Gcat a[L][S]; copies."""

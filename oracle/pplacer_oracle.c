@@ -875,6 +875,55 @@ int orc_precompute(orc_ctx *c) {
   return ORC_OK;
 }
 
+/* Gcat_model.refine (gcat_model.ml:387-419) over Like_stree.site_log_like_arr (like_stree.ml:113-131) and
+ * site_log_like_arr3 (gcat_model.ml:355-375).  Replaces c->site_cat; returns ORC_OK or 1 when a site has zero
+ * likelihood (the reference raises Failure).  site_ll_out [R x L] may be NULL. */
+int orc_refine_site_categories(orc_ctx *c, int32_t *site_cat_out, double *site_ll_out) {
+  if (!c->gcat) return ORC_OK; /* gmix_model.ml: refine is a no-op */
+  const int L = c->L, S = c->S, R = c->R;
+  scratch s; scratch_init(c, &s);
+  double *best = (double *)xcalloc((size_t)L, sizeof(double));
+  int32_t *best_cat = (int32_t *)xcalloc((size_t)L, sizeof(int32_t));
+  for (int i = 0; i < L; i++) { best[i] = -INFINITY; best_cat[i] = -1; }
+  const int c0 = c->child_ptr[c->root_id], nch = c->child_ptr[c->root_id + 1] - c0;
+  int bad = 0;
+  glv util = glv_make(c, L);
+  for (int cat = 0; cat < R && !bad; cat++) {
+    for (int i = 0; i < L; i++) c->site_cat[i] = cat;              /* set_site_categories (:380-384) */
+    memset(c->occupied_rates, 0, (size_t)R); c->occupied_rates[cat] = 1;
+    for (int k = 0; k < nch; k++) calc_distal(c, &s, c->child_idx[c0 + k]); /* calc_distal_and_evolv_dist below the top */
+    glv x = glv_at(c, 2, c->child_idx[c0]), y = glv_at(c, 2, c->child_idx[c0 + 1]);
+    glv *z = &util;
+    if (nch == 2) glv_set_unit(c, &util);
+    else if (nch == 3) { static glv zz; zz = glv_at(c, 2, c->child_idx[c0 + 2]); z = &zz; }
+    else {
+      glv *rest = (glv *)xcalloc((size_t)nch, sizeof(glv));
+      glv **ptrs = (glv **)xcalloc((size_t)nch, sizeof(glv *));
+      for (int k = 2; k < nch; k++) { rest[k] = glv_at(c, 2, c->child_idx[c0 + k]); ptrs[k - 2] = &rest[k]; }
+      listwise_prod(c, &util, ptrs, nch - 2);
+      free(rest); free(ptrs);
+    }
+    const double lr = log(c->rates[cat]);
+    for (int site = 0; site < L; site++) {
+      double like = 0.0;
+      for (int st = 0; st < S; st++)
+        like = like + c->statd[st] * x.a[(size_t)site * S + st] * y.a[(size_t)site * S + st] * z->a[(size_t)site * S + st];
+      if (0.0 >= like) { bad = 1; break; }
+      const double ll = log(like) + LOG_OF_2 * (double)(x.e[site] + y.e[site] + z->e[site]);
+      if (site_ll_out) site_ll_out[(size_t)cat * L + site] = ll;
+      const double v = ll + 2.0 * lr - 3.0 * c->rates[cat];
+      if (v > best[site]) { best[site] = v; best_cat[site] = cat; }
+    }
+  }
+  if (!bad) {
+    memset(c->occupied_rates, 0, (size_t)R);
+    for (int i = 0; i < L; i++) { c->site_cat[i] = best_cat[i]; c->occupied_rates[best_cat[i]] = 1; if (site_cat_out) site_cat_out[i] = best_cat[i]; }
+  }
+  c->precomputed = 0;
+  glv_free(&util); free(best); free(best_cat); scratch_free(&s);
+  return bad ? 1 : ORC_OK;
+}
+
 /* tests/pplacer/test_like.ml:57-66 */
 void orc_node_tree_likes(orc_ctx *c, int node, double *slow_ll3, double *sn_logdot) {
   scratch s; scratch_init(c, &s);

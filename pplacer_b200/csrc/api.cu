@@ -407,6 +407,88 @@ extern "C" int pp_get_model(pp_ctx *c, double *statd, double *x, double *lambda,
 // ---------------------------------------------------------------------------------------------
 // precompute (pplacer_run.ml:322-340)
 // ---------------------------------------------------------------------------------------------
+struct LevelLists {
+  std::vector<int32_t> flat;
+  std::vector<int> off;
+  int max_depth = 0;
+};
+static LevelLists level_lists(const pp_ctx *c) {
+  LevelLists ll;
+  for (int d : c->depth) ll.max_depth = std::max(ll.max_depth, d);
+  std::vector<std::vector<int32_t>> levels(ll.max_depth + 1);
+  for (int i = 0; i < c->n_nodes; ++i) levels[c->depth[i]].push_back(i);
+  ll.off.assign(ll.max_depth + 2, 0);
+  for (int d = 0; d <= ll.max_depth; ++d) { ll.off[d] = (int)ll.flat.size(); ll.flat.insert(ll.flat.end(), levels[d].begin(), levels[d].end()); }
+  ll.off[ll.max_depth + 1] = (int)ll.flat.size();
+  return ll;
+}
+
+// Gcat_model.refine (gcat_model.ml:387-419; called from pplacer_run.ml:316-317 when the model does not come straight from
+// the reference package or with --always-refine): R attempts of the per-site tree likelihood with every site in one
+// category, best category per site under the FastTree prior.  The context's site categories are REPLACED (call before
+// pp_precompute, as the reference does); site_cat_out [L] and site_ll_out [R x L] (optional) receive the result.
+extern "C" int pp_refine_site_categories(pp_ctx *c, int32_t *site_cat_out, double *site_ll_out) {
+  if (!c) return fail(PP_EINVAL, "null ctx");
+  if (!c->gcat) return fail(PP_EINVAL, "pp_refine_site_categories: only the Price-CAT model has site categories (Gmix_model.refine is a no-op)");
+  CK(cudaSetDevice(c->device));
+  const int Rt = c->R;
+  const LevelLists ll = level_lists(c);
+  double *Pfull = nullptr, *best = nullptr, *site_ll = nullptr;
+  int32_t *d_levels = nullptr, *best_cat = nullptr;
+  int *n_bad = nullptr;
+  auto cleanup = [&] { cudaFree(Pfull); cudaFree(best); cudaFree(site_ll); cudaFree(d_levels); cudaFree(best_cat); cudaFree(n_bad); };
+  int rc = PP_OK;
+  auto body = [&]() -> int {
+    CK(cudaMalloc(&Pfull, (size_t)c->n_nodes * Rt * c->S * c->S * sizeof(double)));
+    CK(cudaMalloc(&best, (size_t)c->L * sizeof(double)));
+    CK(cudaMalloc(&best_cat, (size_t)c->L * sizeof(int32_t)));
+    CK(cudaMalloc(&n_bad, sizeof(int)));
+    if (site_ll_out) CK(cudaMalloc(&site_ll, (size_t)Rt * c->L * sizeof(double)));
+    CK(cudaMalloc(&d_levels, ll.flat.size() * sizeof(int32_t)));
+    CK(cudaMemcpyAsync(d_levels, ll.flat.data(), ll.flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(n_bad, 0, sizeof(int), c->stream));
+    fill_f64_kernel<<<64, 256, 0, c->stream>>>(best, -INFINITY, c->L); LAUNCH_CHECK(c);
+    fill_i32_kernel<<<64, 256, 0, c->stream>>>(best_cat, -1, c->L); LAUNCH_CHECK(c);
+    const int tiles = (c->L + kPreThreads - 1) / kPreThreads;
+    if (c->child_ptr[c->root_id + 1] - c->child_ptr[c->root_id] < 2) return fail(PP_EINVAL, "pp_refine_site_categories: degree two node at the root");
+    DISPATCH_MODEL(c, {
+      if (G_) {
+        const size_t sm_p = (size_t)(Rt * S_ + Rt * S_ * S_) * sizeof(double);
+        CK(cudaFuncSetAttribute(pmat_kernel<S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_p));
+        pmat_kernel<S_><<<c->n_nodes, 128, sm_p, c->stream>>>(c->dm, c->d_bl, c->n_nodes, 1.0, Rt, Pfull); LAUNCH_CHECK(c);
+        const size_t sm_l = (size_t)Rt * p_rstride<S_, true>() * sizeof(double);
+        CK(cudaFuncSetAttribute(distal_level_kernel<S_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_l));
+        for (int cat = 0; cat < Rt; ++cat) {
+          fill_i32_kernel<<<64, 256, 0, c->stream>>>(c->d_site_cat, cat, c->Lp); LAUNCH_CHECK(c);
+          for (int d = ll.max_depth; d >= 1; --d) {  // the root's own distal vector is not needed
+            const int n = ll.off[d + 1] - ll.off[d];
+            for (int s0 = 0; s0 < n; s0 += 65535) {
+              dim3 grid(tiles, std::min(65535, n - s0));
+              distal_level_kernel<S_, true><<<grid, kPreThreads, sm_l, c->stream>>>(c->dm, c->g, c->t, d_levels + ll.off[d] + s0, Pfull, Rt); LAUNCH_CHECK(c);
+            }
+          }
+          const double prior = 2.0 * std::log(c->hm.rates[cat]) - 3.0 * c->hm.rates[cat];
+          refine_attempt_kernel<S_><<<tiles, kPreThreads, 0, c->stream>>>(c->dm, c->g, c->t, c->root_id, cat, prior, best, best_cat, site_ll, n_bad); LAUNCH_CHECK(c);
+        }
+      }
+    });
+    // pad sites keep category 0
+    fill_i32_kernel<<<64, 256, 0, c->stream>>>(c->d_site_cat, 0, c->Lp); LAUNCH_CHECK(c);
+    CK(cudaMemcpyAsync(c->d_site_cat, best_cat, (size_t)c->L * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+    int h_bad = 0;
+    CK(cudaMemcpyAsync(&h_bad, n_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (site_cat_out) CK(cudaMemcpyAsync(site_cat_out, best_cat, (size_t)c->L * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (site_ll_out) CK(cudaMemcpyAsync(site_ll_out, site_ll, (size_t)Rt * c->L * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (h_bad > 0) return fail(PP_EINVAL, "pp_refine_site_categories: a site has zero likelihood (gcat_model.ml:368-369)");
+    c->precomputed = false;  // the GLVs on the device are those of the last attempt
+    return PP_OK;
+  };
+  rc = body();
+  cleanup();
+  return rc;
+}
+
 extern "C" int pp_precompute(pp_ctx *c) {
   if (!c) return fail(PP_EINVAL, "null ctx");
   CK(cudaSetDevice(c->device));
@@ -800,6 +882,7 @@ static int launch_three_tax_warp(pp_ctx *c, const CandIn *in, CandOut *out, int 
     tt_eigen_kernel<4, NW_, MINB_, WS_><<<eblocks, NW_ * 32, sme, c->stream>>>(c->em4, c->g, c->d_bl, c->qsite.p, c->nq.p, in, order, out, n, \
                                                                            prm, c->wbuf.p, c->counters.p, c->tt_work.p);       \
   } while (0)
+    // r4j: 2 warps x 8 blocks/SM (160 sites of y in shared memory) 85.3 ms, 4 x 5 (320 sites) 73.1, 2 x 6 (256) 102.1 - the default stays 4 x 4 (448): 67.2
     if (c->tte_variant == 1) PPB_LAUNCH_EIGEN(4, 3, 608);
     else if (c->tte_variant == 2) PPB_LAUNCH_EIGEN(8, 2, 960);
     else if (c->tte_variant == 3) PPB_LAUNCH_EIGEN(4, 2, 960);
@@ -1348,5 +1431,26 @@ extern "C" pp_ctx *pp_multi_ctx(pp_multi *m, int32_t i) { return (m && i >= 0 &&
 extern "C" int pp_multi_last_counts(pp_multi *m, int64_t *per_device) {
   if (!m || !per_device) return fail(PP_EINVAL, "pp_multi_last_counts: bad arguments");
   for (size_t i = 0; i < m->ctx.size(); ++i) per_device[i] = m->last_counts[i];
+  return PP_OK;
+}
+
+// --check-like (pplacer_run.ml:344-377): per node i the tree log-likelihood seen from edge i two ways -
+// log_like3(evolve(darr[i], bl/2), evolve(parr[i], bl/2), unit) and logdot(snodes[i], unit) - which must agree with each
+// other and across nodes.  An all-ones query (N / X) evolves to the unit vector for any pendant length (rows of P sum
+// to one), so the two columns are Three_tax.log_like and the prefilter score of that query.  out: n_nodes x 2
+// (tree_likelihood, supernode_like); the supernode column is NaN at the root.
+extern "C" int pp_check_like(pp_ctx *c, double *out) {
+  if (!c || !out) return fail(PP_EINVAL, "pp_check_like: bad arguments");
+  if (!c->precomputed) return fail(PP_ESTATE, "pp_check_like: call pp_precompute first");
+  const char any = c->S == 4 ? 'N' : 'X';
+  const int n = c->n_nodes;
+  std::vector<uint8_t> q((size_t)n * c->L, (uint8_t)any);
+  std::vector<double> sc(n), ll(n), pend(n, 0.1), dist(n);
+  std::vector<int32_t> edge(n);
+  for (int i = 0; i < n; ++i) { edge[i] = i; dist[i] = c->bl[i] / 2.0; }
+  int rc;
+  if ((rc = pp_prefilter_scores(c, 0.1, 1, q.data(), sc.data(), 0))) return rc;
+  if ((rc = pp_three_tax_log_like(c, n, q.data(), edge.data(), pend.data(), dist.data(), ll.data()))) return rc;
+  for (int i = 0; i < n; ++i) { out[2 * i] = ll[i]; out[2 * i + 1] = sc[i]; }
   return PP_OK;
 }

@@ -158,6 +158,47 @@ proximal_level_kernel(const DevModel *__restrict__ m, GlvArrays g, TreeDev t, co
   g.e[1][(int64_t)child * Lp + site] = e;
 }
 
+// Gcat_model.refine (gcat_model.ml:387-419): one attempt of Like_stree.site_log_like_arr (like_stree.ml:113-131) with
+// every site in category `cat`.  After the distal pass the evolved distal vectors of the root's children sit in the
+// snodes array (evolv_dist); per site  log(sum_s statd_s * x_s * y_s * z_s) + ln2 * (e_x + e_y + e_z)
+// (site_log_like_arr3, gcat_model.ml:355-375) with z = the product of the remaining children (listwise_prod) or the
+// unit vector for a bifurcating root, then the FastTree prior  + 2 log(rate) - 3 rate, keeping the FIRST best
+// category (strict >).  A non-positive site likelihood raises in the reference: counted in *n_bad.
+template <int S>
+__global__ void __launch_bounds__(kPreThreads)
+refine_attempt_kernel(const DevModel *__restrict__ m, GlvArrays g, TreeDev t, int root, int cat, double prior_term,
+                      double *__restrict__ best_ll, int32_t *__restrict__ best_cat, double *__restrict__ site_ll_out,
+                      int *__restrict__ n_bad) {
+  const int site = blockIdx.x * blockDim.x + threadIdx.x;
+  if (site >= g.L) return;
+  const int c0 = t.child_ptr[root], c1 = t.child_ptr[root + 1];
+  const int i = t.child_idx[c0], j = t.child_idx[c0 + 1];
+  double like = 0.0;
+  int e = g.e[2][(int64_t)i * g.Lp + site] + g.e[2][(int64_t)j * g.Lp + site];
+  double z[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) z[s] = 1.0;
+  for (int c = c0 + 2; c < c1; ++c) {
+    const int k = t.child_idx[c];
+#pragma unroll
+    for (int s = 0; s < S; ++s) z[s] = (c == c0 + 2) ? glv_plane(g, 2, k, s)[site] : z[s] * glv_plane(g, 2, k, s)[site];
+    e += g.e[2][(int64_t)k * g.Lp + site];
+  }
+#pragma unroll
+  for (int s = 0; s < S; ++s) like += m->statd[s] * glv_plane(g, 2, i, s)[site] * glv_plane(g, 2, j, s)[site] * z[s];
+  if (!(like > 0.0)) atomicAdd(n_bad, 1);
+  const double ll = log(like) + kLn2 * (double)e;
+  if (site_ll_out) site_ll_out[(int64_t)cat * g.L + site] = ll;
+  const double x = ll + prior_term;
+  if (x > best_ll[site]) { best_ll[site] = x; best_cat[site] = cat; }
+}
+__global__ void fill_i32_kernel(int32_t *p, int32_t v, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void fill_f64_kernel(double *p, double v, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
 // Root proximal = unit (like_stree.ml:98-99).
 __global__ void set_unit_kernel(GlvArrays g, int which, int node) {
   const int64_t n = (int64_t)g.K * g.Lp;

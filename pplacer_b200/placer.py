@@ -155,6 +155,21 @@ class Placer:
         _lib.check(_lib.load().pp_precompute(self.ctx))
         self.precomputed = True
 
+    def refine_site_categories(self, want_site_ll: bool = False):
+        """Gcat_model.refine on the device (gcat_model.ml:387-419): returns the new zero-based category per site (and
+        the R x L per-category site log-likelihoods).  The context keeps the new categories; precompute afterwards."""
+        cats = np.zeros(self.L, dtype=np.int32)
+        sll = np.zeros((self.R, self.L)) if want_site_ll else None
+        _lib.check(_lib.load().pp_refine_site_categories(self.ctx, _lib.ip(cats), None if sll is None else _lib.dp(sll)))
+        self.precomputed = False
+        return (cats, sll) if want_site_ll else cats
+
+    def check_like(self) -> np.ndarray:
+        """--check-like (pplacer_run.ml:344-377): [n_nodes, 2] = tree_likelihood, supernode_like per edge."""
+        out = np.zeros((self.n_nodes, 2))
+        _lib.check(_lib.load().pp_check_like(self.ctx, _lib.dp(out)))
+        return out
+
     def model_numerics(self):
         S, R = self.S, self.R
         statd, x, lam, xit, rates = np.zeros(S), np.zeros((S, S)), np.zeros(S), np.zeros((S, S)), np.zeros(R)

@@ -1,15 +1,15 @@
-"""Reference packages: the three inputs the placement path reads from a refpkg directory
+"""Reference packages: the inputs the placement path reads from a refpkg directory
 (pplacer_src/refpkg_parse.ml:86-104 CONTENTS.json -> file map; refpkg.ml:26-63 get_ref_tree /
-get_aln_fasta / get_model).  Only `tree`, `aln_fasta` and `phylo_model` are consumed; a refpkg that
-carries nothing but `tree_stats` (deprecated in the reference, refpkg.ml:51-59) is rejected with a
-clear message - PhyML / RAxML stats parsing (parse_stats.ml) is not part of this path."""
+get_aln_fasta / get_model): `tree`; `aln_fasta`, else `aln_sto` (Stockholm, refpkg.ml:33-36); `phylo_model` JSON, else
+the deprecated `tree_stats` statistics file of PhyML / RAxML (refpkg.ml:51-59, parse_stats.ml)."""
 from __future__ import annotations
 
 import json
 import os
+import sys
 from typing import List, Tuple
 
-from . import models, newick, seqio
+from . import models, newick, seqio, stats
 
 
 def contents(path: str) -> dict:
@@ -26,11 +26,19 @@ def load(path: str):
     if "tree" not in files:
         raise ValueError("refpkg has no tree")
     tree = newick.parse_file(os.path.join(path, files["tree"]))
-    if "aln_fasta" not in files:
-        raise ValueError("refpkg has no aln_fasta (Stockholm-only refpkgs are not supported on this path)")
-    aln: List[Tuple[str, str]] = seqio.read_fasta(os.path.join(path, files["aln_fasta"]), upper=True)
-    if "phylo_model" not in files:
-        raise ValueError("refpkg has no phylo_model JSON (statistics-file refpkgs are deprecated in the reference "
-                         "and not supported here; rebuild the refpkg with a current taxtastic)")
-    model = models.model_from_json_file(os.path.join(path, files["phylo_model"]))
+    aln: List[Tuple[str, str]]
+    if "aln_fasta" in files:
+        aln = seqio.read_fasta(os.path.join(path, files["aln_fasta"]), upper=True)
+    elif "aln_sto" in files:
+        aln = seqio.read_stockholm(os.path.join(path, files["aln_sto"]), upper=True)
+    else:
+        raise ValueError("refpkg has neither aln_fasta nor aln_sto")
+    if "phylo_model" in files:
+        model = models.model_from_json_file(os.path.join(path, files["phylo_model"]))
+    elif "tree_stats" in files:
+        sys.stderr.write("Warning: using a statistics file directly is now deprecated. We suggest using a reference "
+                         "package. If you already are, then please use the latest version of taxtastic.\n")
+        model = stats.model_from_stats_file(os.path.join(path, files["tree_stats"]))
+    else:
+        raise ValueError("refpkg has neither phylo_model nor tree_stats")
     return tree, aln, model

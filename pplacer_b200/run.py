@@ -18,9 +18,25 @@ from .placer import Placer
 from .reference import build_problem
 
 
-def place_problem(prob, device: int = 0, pp: bool = False, **prefs_kw):
+def place_problem(prob, device: int = 0, pp: bool = False, always_refine: bool = False, check_like: bool = False,
+                  devices: Optional[List[int]] = None, **prefs_kw):
+    """devices: several GPUs behind one handle (pp_create_multi) - what -j does in the reference."""
+    if devices is not None and len(devices) > 1 and not always_refine and not check_like:
+        from .placer import MultiPlacer
+        with MultiPlacer(prob, devices) as mp:
+            mp.precompute()
+            return mp.place(prob.query_chars, mp.prefs(pp=pp, **prefs_kw))
     with Placer(prob, device=device) as p:
+        if always_refine and prob.model.model_class == 1:     # Model.refine, pplacer_run.ml:316-317 (Gmix: a no-op)
+            sys.stderr.write("Optimizing site categories... ")
+            p.refine_site_categories()
+            sys.stderr.write("done.\n")
         p.precompute()
+        if check_like:                                         # pplacer_run.ml:344-377
+            t = p.check_like()
+            sys.stderr.write("node  tree_likelihood  supernode_like\n")
+            for i in range(t.shape[0]):
+                sys.stderr.write("%d  %g  %g\n" % (i, t[i, 0], t[i, 1]))
         prefs = p.prefs(pp=pp, **prefs_kw)
         out, n_out, st, _ = p.place(prob.query_chars, prefs)
     return out, n_out, st
@@ -28,12 +44,13 @@ def place_problem(prob, device: int = 0, pp: bool = False, **prefs_kw):
 
 def run_file(refpkg_path: str, query_fasta: str, out_path: Optional[str] = None, pp: bool = False,
              device: int = 0, pre_mask: bool = True, discard_nonoverlapped: bool = False, invocation: str = "",
-             **prefs_kw):
+             always_refine: bool = False, check_like: bool = False, devices: Optional[List[int]] = None, **prefs_kw):
     """Pplacer_run.run_file (pplacer_run.ml:682-783) for a refpkg and one query file."""
     tree, aln, model = refpkg.load(refpkg_path)
     queries = seqio.read_fasta(query_fasta, upper=True)          # pplacer_run.ml:409
     prob = build_problem(tree, model, aln, queries, pre_mask=pre_mask, discard_nonoverlapped=discard_nonoverlapped)
-    out, n_out, st = place_problem(prob, device=device, pp=pp, **prefs_kw)
+    out, n_out, st = place_problem(prob, device=device, pp=pp, always_refine=always_refine, check_like=check_like,
+                                   devices=devices, **prefs_kw)
     bad = np.nonzero(st != 0)[0]
     for q in bad:
         sys.stderr.write("Warning: %s: no placement (status %d)\n" % (prob.query_names[q][0], st[q]))
@@ -62,13 +79,17 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap.add_argument("--no-pre-mask", action="store_true")
     ap.add_argument("--discard-nonoverlapped", action="store_true")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--devices", type=str, default=None, help="comma-separated GPU ids: shard the queries over them (in place of -j)")
+    ap.add_argument("--always-refine", action="store_true", help="re-derive the Price-CAT site categories (prefs.ml always_refine)")
+    ap.add_argument("--check-like", action="store_true", help="print the tree likelihood seen from every edge (prefs.ml check_like)")
     ap.add_argument("queries")
     a = ap.parse_args(argv)
     kw = {k: getattr(a, k) for k in ("keep_at_most", "keep_factor", "max_strikes", "strike_box", "max_pitches", "max_pend")
           if getattr(a, k) is not None}
     t0 = time.perf_counter()
     path, prob, (out, n_out, st) = run_file(a.refpkg, a.queries, a.out, pp=a.pp, device=a.device, pre_mask=not a.no_pre_mask,
-                                           discard_nonoverlapped=a.discard_nonoverlapped,
+                                           discard_nonoverlapped=a.discard_nonoverlapped, always_refine=a.always_refine,
+                                           check_like=a.check_like, devices=None if a.devices is None else [int(x) for x in a.devices.split(",")],
                                            invocation=" ".join(["pplacer_b200"] + (argv if argv is not None else sys.argv[1:])), **kw)
     sys.stderr.write("placed %d unique queries (%d names) in %.2f s -> %s\n"
                      % (int((st == 0).sum()), sum(len(n) for n in prob.query_names), time.perf_counter() - t0, path))

@@ -52,3 +52,45 @@ def to_char_matrix(seqs: List[str]) -> np.ndarray:
 def informative(chars: np.ndarray) -> np.ndarray:
     """Alignment.informative (alignment.ml:235): everything except '?' and '-'."""
     return (chars != ord("-")) & (chars != ord("?"))
+
+
+def read_stockholm(path: str, upper: bool = True) -> List[Tuple[str, str]]:
+    """Stockholm 1.0 alignment (pplacer_src/stockholm.ml:9-90): '# STOCKHOLM 1.0' header, '#=' markup ignored, sequence
+    lines 'name  chunk' concatenated per name (interleaved blocks), '.' gaps become '-', '//' footer; every sequence
+    must have the same length.  The reference collects the names in a string map, so they come back SORTED."""
+    opener = gzip.open if path.endswith(".gz") else open
+    seqs = {}
+    state = 0   # 0 needs header, 1 needs footer, 2 found footer
+    with opener(path, "rt") as fh:
+        for raw in fh:
+            line = raw.strip()
+            if not line:
+                continue
+            if line == "# STOCKHOLM 1.0":
+                if state != 0:
+                    raise ValueError("stockholm: header unexpected")
+                state = 1
+            elif state == 0:
+                raise ValueError("stockholm: something before header")
+            elif line == "//":
+                if state != 1:
+                    raise ValueError("stockholm: footer unexpected")
+                state = 2
+            elif state == 2:
+                raise ValueError("stockholm: something after footer")
+            elif line.startswith("#"):
+                continue        # "#=GF", "#=GC", "#=GS", "#=GR" markup
+            else:
+                toks = line.split()
+                if len(toks) != 2:
+                    raise ValueError("stockholm: malformed sequence line: " + line[:40])
+                seqs.setdefault(toks[0], []).append(toks[1].replace(".", "-"))
+    if state != 2:
+        raise ValueError("stockholm: no footer")
+    out = [(n, "".join(chunks)) for n, chunks in sorted(seqs.items())]
+    for n, s in out:
+        if len(s) != len(out[0][1]):
+            raise ValueError("%s (length %d) doesn't match the previous sequence lengths (%d)" % (n, len(s), len(out[0][1])))
+    if upper:
+        out = [(n, s.upper()) for n, s in out]
+    return out

@@ -2,7 +2,7 @@
 """Copy the reference's own known-answer DATA for this path into tests/golden/ so the tests can run
 where /root/reference does not exist (the GPU box).  Data files only - no reference source code.
 
-  like/{gtr,wag,jtt}/   alignment, PhyML tree, phylo_model JSON of tests/pplacer/test_like.ml
+  like/{gtr,wag,jtt}/   alignment, PhyML tree, phylo_model JSON and PhyML statistics file of tests/pplacer/test_like.ml
                         (expected PhyML log-likelihoods: test_like.ml:71-90)
   ar53_golden.json      the three GOLDEN / TEST placements of donovan-test/ar53_pplacer_testset
   _ar53/ (git-ignored)  the ar53 refpkg (tree, model JSON, MSA as .npz) + the 3 query genomes, for
@@ -16,9 +16,9 @@ REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", ".."))
 
-for d, files in (("gtr", ["hiv.fasta", "hiv.phy_phyml_tree.txt", "phylo_model.jplace"]),
-                 ("wag", ["actin.fasta", "actin.phy_phyml_tree.txt", "phylo_model.jplace"]),
-                 ("jtt", ["actin.fasta", "actin.phy_phyml_tree.txt", "phylo_model.jplace"])):
+for d, files in (("gtr", ["hiv.fasta", "hiv.phy_phyml_tree.txt", "phylo_model.jplace", "hiv.phy_phyml_stats.txt"]),
+                 ("wag", ["actin.fasta", "actin.phy_phyml_tree.txt", "phylo_model.jplace", "actin.phy_phyml_stats.txt"]),
+                 ("jtt", ["actin.fasta", "actin.phy_phyml_tree.txt", "phylo_model.jplace", "actin.phy_phyml_stats.txt"])):
     os.makedirs(os.path.join(HERE, "like", d), exist_ok=True)
     for f in files:
         dst = os.path.join(HERE, "like", d, f)

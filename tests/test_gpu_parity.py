@@ -574,3 +574,51 @@ def test_multi_device_handle_equals_single_device(c2_small):
         assert g0.shape[0] == 0
     with pytest.raises(_lib.PplacerB200Error):
         MultiPlacer(prob, [0, 99])
+
+
+# ---------------------------------------------------------------------------------------------
+# Gcat_model.refine and --check-like on the device
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["gcat_dna", "gcat_aa"])
+def test_gcat_refine_site_categories_matches_oracle(oracle_binding, name):
+    """Gcat_model.refine (gcat_model.ml:387-419): per-site tree log-likelihood under every rate category (R passes of
+    Like_stree.site_log_like_arr on the device), best category under FastTree's prior; then the whole path with the
+    refined categories."""
+    prob = PROBLEMS[name]()
+    o = oracle_binding.Oracle(prob)
+    want_cats, want_ll = o.refine_site_categories(True)
+    with Placer(prob) as p:
+        got_cats, got_ll = p.refine_site_categories(True)
+        assert np.all(np.abs(got_ll - want_ll) <= 1e-10 * np.abs(want_ll)), np.abs((got_ll - want_ll) / want_ll).max()
+        differ = np.nonzero(got_cats != want_cats)[0]
+        rates = p.model_numerics()["rates"]
+        for s in differ:      # only at a tie of the two categories' penalised log-likelihoods
+            pen = want_ll[:, s] + 2 * np.log(rates) - 3 * rates
+            assert abs(pen[got_cats[s]] - pen[want_cats[s]]) <= 1e-9 * abs(pen[want_cats[s]]), (s, pen)
+        assert len(differ) <= 1
+        assert (got_cats != prob.site_cat).any()           # the refinement changed something
+        if len(differ) == 0:
+            o.precompute()
+            p.precompute()
+            exp, n_exp, st_exp, _ = o.place(prob.query_chars[:10], oracle_prefs(oracle_binding, prob), n_threads=4)
+            got, n_got, st_got, _ = p.place(prob.query_chars[:10], p.prefs())
+            assert_placements_match(got, n_got, st_got, exp, n_exp, st_exp, near_tie_ll=1e-3)
+    o.close()
+    with Placer(configs.c1()) as p:
+        with pytest.raises(_lib.PplacerB200Error):
+            p.refine_site_categories()                     # Gmix models have no site categories
+
+
+@pytest.mark.parametrize("name", ["gtr", "wag"])
+def test_check_like_table(name):
+    """--check-like (pplacer_run.ml:344-377): tree_likelihood and supernode_like agree at every edge and equal PhyML's."""
+    tree, aln, model = configs.like_inputs(name)
+    prob = reference.build_problem(tree, model, aln, [("q", aln[0][1])], pre_mask=False)
+    with Placer(prob) as p:
+        p.precompute()
+        t = p.check_like()
+    want = configs.PHYML_LL[name]
+    assert t.shape == (tree.n_nodes, 2)
+    assert np.all(np.abs(t[:, 0] - want) <= 1e-7 * abs(want))
+    nr = np.array(tree.nonroot_ids())
+    assert np.all(np.abs(t[nr, 1] - want) <= 1e-7 * abs(want)) and np.isnan(t[tree.root, 1])

@@ -90,3 +90,60 @@ def test_refpkg_loader_and_error_messages(tmp_path):
     (rp / "CONTENTS.json").write_text(json.dumps({"files": {k: v for k, v in files.items() if k != "phylo_model"}}))
     with pytest.raises(ValueError, match="phylo_model"):
         refpkg.load(str(rp))
+
+
+def test_phyml_stats_file_gives_the_json_model(tmp_path):
+    """parse_stats.ml:223-276 on the reference's own PhyML statistics files (tests/data/like/*): the model they describe
+    is the model of the phylo_model JSON next to them (same rates, alpha, categories)."""
+    import os
+    from pplacer_b200 import stats
+    for name, stem in (("gtr", "hiv"), ("wag", "actin"), ("jtt", "actin")):
+        d = os.path.join(configs.GOLDEN, "like", name)
+        got = stats.model_from_stats_file(os.path.join(d, stem + ".phy_phyml_stats.txt"))
+        want = models.model_from_json_file(os.path.join(d, "phylo_model.jplace"))
+        assert (got.n_states, got.model_class, got.subs_model, got.n_rates) == (want.n_states, 0, want.subs_model, want.n_rates)
+        assert got.gamma_alpha == want.gamma_alpha and np.array_equal(got.exch, want.exch)
+    assert stats.parse_stats(os.path.join(configs.GOLDEN, "like", "gtr", "hiv.phy_phyml_stats.txt")) == \
+        ("GTR", 4, 0.771, [1.17728, 3.08642, 0.60698, 0.92672, 4.74366, 1.0])
+    # RAxML 7.2.x info file (parse_stats.ml:84-126) and the re-estimated form (:129-190)
+    info = tmp_path / "RAxML_info.x"
+    info.write_text("This is RAxML version 7.2.6 released by Alexandros Stamatakis\n\nPartition: 0\nAlignment Patterns: 3\nName: No Name Provided\n"
+                    "DataType: DNA\nSubstitution Matrix: GTR\n\nInference[0]: Time 1.0 GAMMA-based likelihood -1.0, best rearrangement setting 5\n"
+                    "alpha[0]: 0.5421 rates[0] ac ag at cg ct gt: 1.1 2.2 3.3 4.4 5.5 1.000000\n")
+    assert stats.parse_stats(str(info)) == ("GTR", 4, 0.5421, [1.1, 2.2, 3.3, 4.4, 5.5, 1.0])
+    info.write_text("This is RAxML version 7.2.6\n\nraxmlHPC -f e -t tree -m GTRGAMMA -s aln -n x\n\nPartition: 0\nAlignment Patterns: 3\n"
+                    "DataType: AA\nSubstitution Matrix: WAG\nalpha: 0.9\n")
+    assert stats.parse_stats(str(info)) == ("WAG", 4, 0.9, None)
+    info.write_text("nothing useful\n")
+    with pytest.raises(stats.StatsParsingError):
+        stats.parse_stats(str(info))
+
+
+def test_refpkg_with_stockholm_alignment_and_stats_file(tmp_path):
+    """refpkg.ml:33-36,51-59: aln_sto is read when aln_fasta is absent ('.' gaps -> '-', interleaved blocks joined, names
+    sorted), and a tree_stats file stands in for the phylo_model JSON."""
+    import json, os, shutil
+    from pplacer_b200 import refpkg
+    src = os.path.join(configs.GOLDEN, "like", "gtr")
+    aln = seqio.read_fasta(os.path.join(src, "hiv.fasta"))
+    rp = tmp_path / "sto.refpkg"
+    rp.mkdir()
+    half = len(aln[0][1]) // 2
+    with open(rp / "hiv.sto", "w") as fh:
+        fh.write("# STOCKHOLM 1.0\n#=GF ID hiv\n\n")
+        for n, s in aln:
+            fh.write("%s  %s\n" % (n, s[:half].replace("-", ".")))
+        fh.write("#=GC RF xxxx\n\n")
+        for n, s in aln:
+            fh.write("%s\t%s   \n" % (n, s[half:].lower()))
+        fh.write("//\n")
+    shutil.copyfile(os.path.join(src, "hiv.phy_phyml_tree.txt"), rp / "t.nwk")
+    shutil.copyfile(os.path.join(src, "hiv.phy_phyml_stats.txt"), rp / "stats.txt")
+    (rp / "CONTENTS.json").write_text(json.dumps({"files": {"aln_sto": "hiv.sto", "tree": "t.nwk", "tree_stats": "stats.txt"}}))
+    tree, got_aln, model = refpkg.load(str(rp))
+    assert got_aln == sorted((n, s.upper()) for n, s in aln)
+    want = models.model_from_json_file(os.path.join(src, "phylo_model.jplace"))
+    assert np.array_equal(model.exch, want.exch) and model.gamma_alpha == want.gamma_alpha and model.n_rates == 4
+    (rp / "bad.sto").write_text("A  ACGT\n//\n")
+    with pytest.raises(ValueError, match="before header"):
+        seqio.read_stockholm(str(rp / "bad.sto"))
