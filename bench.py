@@ -261,6 +261,7 @@ def run_ours(args):
     p.set_stream(stream.cuda_stream)
     p.set_prefilter_kernel({"default": 0, "direct": 1, "table": 2, "staged": 4, "dmma": 5}[args.prefilter])
     p.set_three_tax_engine({"default": 0, "block": 1, "warp": 2, "group": 3, "eigen": 4}[args.tt_engine], args.tt_blocks_per_sm)
+    n_figs = p.set_figs(cutoff=args.fig_cutoff) if args.fig_cutoff > 0 else 0
     fp64_peak = p.measure_fp64_peak()
 
     # ---- device-resident arm -------------------------------------------------------------------
@@ -477,7 +478,7 @@ def run_ours(args):
         "config": {"workload": wl[2], "queries_per_gpu_per_step": Q, "queries_per_step_all_gpus": int(Q_total), "flags": wl[3],
                    "sharding": ("one fixed query set sharded over ranks (strong scaling)" if strong else "every rank places its own queries (weak scaling)")
                                + ", reference GLVs replicated, no data-path collective; results gathered on rank 0 inside e2e",
-                   "gather": gather_check,
+                   "gather": gather_check, "fig_cutoff": args.fig_cutoff, "n_figs": n_figs,
                    "l2": "inputs larger than L2: supernodes %.0f MB + darr/parr %.0f MB per pass" % (
                        8.0 * R * S * p.L * (E + 1) / 1e6, 16.0 * R * S * p.L * (E + 1) / 1e6),
                    "placed_ok_frac": float((st_host == 0).mean()), "mean_kept": float(n_host.mean())},
@@ -502,6 +503,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline sample budget")
     ap.add_argument("--ref-step-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fig-cutoff", type=float, default=0.0, help="rank through figs (pplacer --fig-cutoff); 0 = the reference's default, disabled")
     ap.add_argument("--no-direct-prefilter", action="store_true", help="skip the extra launch that times the direct-FMA prefilter form")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = every rank places its own --queries; strong = one fixed set of --total-queries sharded over the ranks")

@@ -155,6 +155,15 @@ int pp_get_model(pp_ctx *, double *statd, double *x, double *lambda, double *xit
 int pp_place(pp_ctx *, const pp_prefs *, int64_t Q, const uint8_t *query_chars, pp_result *out,
              int32_t *n_out, int32_t *status, pp_debug *dbg_or_null);
 
+/* Figs (--fig-cutoff; fig.ml): with n_figs > 0 the ranking of pp_place follows Fig._enum_by_score (fig.ml:120-138) -
+ * one representative edge per fig is scored for every query, the figs are taken in the order of those scores and each
+ * GROUP (a fig and the following ones within strike_box of its score) is expanded, its edges scored and sorted, only
+ * when baseball needs more locations.  The fig list is built by the host exactly as Fig._figs_of_gtree does
+ * (fig.ml:70-99; pplacer_b200/fig.py): rep[n_figs], CSR edge lists ptr[n_figs+1] / idx.  n_figs == 0 restores the plain
+ * ranking of every non-root edge (Fig.Dummy).  max_strikes == 0 (every edge is optimised) ignores figs. */
+int pp_set_figs(pp_ctx *, int32_t n_figs, const int32_t *rep, const int32_t *ptr, const int32_t *idx);
+int pp_n_figs(pp_ctx *);
+
 /* ---- all the GPUs of one box behind one handle ------------------------------------------------------------
  * Replaces Multiprocessing's fork-per-job (pplacer_run.ml:618-649, multiprocessing.ml:279): the reference GLVs are
  * REPLICATED on n_devices GPUs (each runs the device precompute itself) and pp_multi_place shards the queries over

@@ -99,6 +99,7 @@ def lib():
         L.orc_place.argtypes = [C.c_void_p, C.POINTER(Prefs), C.c_int64, c_u8_p, C.c_void_p, c_i32_p,
                                 c_i32_p, C.POINTER(Debug), C.c_int]
         L.orc_three_tax_ll.argtypes = [C.c_void_p, c_u8_p, C.c_int, C.c_double, C.c_double, c_double_p]
+        L.orc_set_figs.argtypes = [C.c_void_p, C.c_int, c_i32_p, c_i32_p, c_i32_p]
         L.orc_refine_site_categories.argtypes = [C.c_void_p, c_i32_p, c_double_p]
         i, d = C.c_int, C.c_double
         L.orc_k_gemmish.argtypes = [c_double_p, c_double_p, c_double_p, i, i]
@@ -270,6 +271,15 @@ class Oracle:
     def precompute(self):
         lib().orc_precompute(self.ctx)
         self.precomputed = True
+
+    def set_figs(self, figs):
+        """figs: list of (rep, edges) from pplacer_b200.fig.figs_of_tree, or None for the plain ranking"""
+        if not figs:
+            lib().orc_set_figs(self.ctx, 0, None, None, None)
+            return
+        from pplacer_b200.fig import figs_csr
+        rep, ptr, idx = figs_csr(figs)
+        lib().orc_set_figs(self.ctx, len(rep), ip(rep), ip(ptr), ip(idx))
 
     def refine_site_categories(self, want_site_ll: bool = False):
         """Gcat_model.refine (gcat_model.ml:387-419); the context keeps the new categories."""

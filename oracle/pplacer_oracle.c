@@ -470,6 +470,9 @@ struct orc_ctx {
   size_t map_bytes[3];
   int mapped;
   int precomputed;
+  /* Fig.t (fig.ml:4-12): n_figs == 0 is Dummy */
+  int n_figs;
+  int32_t *fig_rep, *fig_ptr, *fig_idx;
 };
 
 /* per-thread scratch: the reference mutates model.tensor and util vectors in place */
@@ -802,6 +805,7 @@ void orc_destroy(orc_ctx *c) {
     else { free(c->A[w]); free(c->E[w]); }
   }
   free(c->rates); free(c->site_cat); free(c->occupied_rates); free(c->child_ptr); free(c->child_idx);
+  free(c->fig_rep); free(c->fig_ptr); free(c->fig_idx);
   free(c->leaf_row); free(c->bl); free(c->ref_chars); free(c);
 }
 
@@ -922,6 +926,23 @@ int orc_refine_site_categories(orc_ctx *c, int32_t *site_cat_out, double *site_l
   c->precomputed = 0;
   glv_free(&util); free(best); free(best_cat); scratch_free(&s);
   return bad ? 1 : ORC_OK;
+}
+
+/* Fig.t for the ranking (fig.ml): m figs as (representative, CSR edge lists), built by the host (Fig._figs_of_gtree);
+ * m == 0 restores the Dummy ranking of every non-root edge */
+int orc_set_figs(orc_ctx *c, int m, const int32_t *rep, const int32_t *ptr, const int32_t *idx) {
+  free(c->fig_rep); free(c->fig_ptr); free(c->fig_idx);
+  c->fig_rep = c->fig_ptr = c->fig_idx = NULL;
+  c->n_figs = 0;
+  if (m <= 0) return ORC_OK;
+  c->fig_rep = (int32_t *)xcalloc((size_t)m, sizeof(int32_t));
+  c->fig_ptr = (int32_t *)xcalloc((size_t)m + 1, sizeof(int32_t));
+  c->fig_idx = (int32_t *)xcalloc((size_t)ptr[m] + 1, sizeof(int32_t));
+  memcpy(c->fig_rep, rep, sizeof(int32_t) * (size_t)m);
+  memcpy(c->fig_ptr, ptr, sizeof(int32_t) * ((size_t)m + 1));
+  memcpy(c->fig_idx, idx, sizeof(int32_t) * (size_t)ptr[m]);
+  c->n_figs = m;
+  return ORC_OK;
 }
 
 /* tests/pplacer/test_like.ml:57-66 */
@@ -1195,26 +1216,68 @@ static int process_query(worker *w, const orc_prefs *pf, const uint8_t *query, o
   tt.dist.bl = tt.prox.bl = pf->start_pend;
   edge_set_bl(&tt, &tt.pend, pf->start_pend);
   double t1 = now_s();
-  /* core.ml:187-197 + fig.ml:143-147 (Dummy: every non-root id ascending, stable sort descending) */
   int n_rank = 0;
-  for (int loc = 0; loc < c->n_nodes; loc++) {
-    if (loc == c->root_id) { if (dbg && dbg->scores) dbg->scores[qi * c->n_nodes + loc] = NAN; continue; }
-    glv sn = glv_at(c, 2, loc);
-    double sc = masked_logdot(c, w->s.util, &w->full_query_evolv, &sn, w->mask_vec);
-    if (dbg && dbg->scores) dbg->scores[qi * c->n_nodes + loc] = sc;
-    w->rank[n_rank].score = sc; w->rank[n_rank].loc = loc; n_rank++;
+  /* Fig._enum_by_score (fig.ml:120-138): representatives scored and sorted up front, groups expanded lazily */
+  scored *fig_sc = NULL, *fig_tmp = NULL;
+  uint8_t *yielded = NULL;
+  int fig_next = 0;
+  if (c->n_figs > 0) {
+    fig_sc = (scored *)xcalloc((size_t)c->n_figs, sizeof(scored)); fig_tmp = (scored *)xcalloc((size_t)c->n_figs, sizeof(scored));
+    yielded = (uint8_t *)xcalloc((size_t)c->n_nodes, 1);
+    if (dbg && dbg->scores) for (int loc = 0; loc < c->n_nodes; loc++) dbg->scores[qi * c->n_nodes + loc] = NAN;
+    for (int f = 0; f < c->n_figs; f++) {
+      glv sn = glv_at(c, 2, c->fig_rep[f]);
+      fig_sc[f].score = masked_logdot(c, w->s.util, &w->full_query_evolv, &sn, w->mask_vec);
+      fig_sc[f].loc = f;
+    }
+    stable_sort_desc(fig_sc, fig_tmp, c->n_figs);
+  } else {
+    /* core.ml:187-197 + fig.ml:143-147 (Dummy: every non-root id ascending, stable sort descending) */
+    for (int loc = 0; loc < c->n_nodes; loc++) {
+      if (loc == c->root_id) { if (dbg && dbg->scores) dbg->scores[qi * c->n_nodes + loc] = NAN; continue; }
+      glv sn = glv_at(c, 2, loc);
+      double sc = masked_logdot(c, w->s.util, &w->full_query_evolv, &sn, w->mask_vec);
+      if (dbg && dbg->scores) dbg->scores[qi * c->n_nodes + loc] = sc;
+      w->rank[n_rank].score = sc; w->rank[n_rank].loc = loc; n_rank++;
+    }
+    stable_sort_desc(w->rank, w->rank_tmp, n_rank);
   }
-  stable_sort_desc(w->rank, w->rank_tmp, n_rank);
   double t2 = now_s();
   /* core.ml:283-318 play_ball */
   int cap = (pf->max_strikes == 0) ? n_rank : (pf->max_pitches + 1);
   if (cap > n_rank) cap = n_rank;
-  ml_res *results = (ml_res *)xcalloc((size_t)n_rank, sizeof(ml_res));
+  ml_res *results = (ml_res *)xcalloc((size_t)c->n_nodes, sizeof(ml_res));
   int n_results = 0, n_strikes = 0, next = 0;
   double like_record = -INFINITY;
   int64_t calls = 0;
   int fatal = 0;
-  while (next < n_rank) {
+  for (;;) {
+    if (next >= n_rank) {
+      if (fig_next >= c->n_figs) break;
+      /* the next group: this fig plus the following ones whose representative scores lie within strike_box of its own
+       * (approx_equal, ppatteries.ml:96: strict <), minus everything yielded before, members scored and sorted */
+      const double s0 = fig_sc[fig_next].score;
+      int g0 = fig_next++;
+      while (fig_next < c->n_figs && fabs(s0 - fig_sc[fig_next].score) < pf->strike_box) fig_next++;
+      int n_new = 0;
+      uint8_t *in_group = (uint8_t *)xcalloc((size_t)c->n_nodes, 1);
+      for (int g = g0; g < fig_next; g++) {
+        const int f = fig_sc[g].loc;
+        for (int k = c->fig_ptr[f]; k < c->fig_ptr[f + 1]; k++) in_group[c->fig_idx[k]] = 1;
+      }
+      for (int loc = 0; loc < c->n_nodes; loc++) { /* IntSet.elements: ascending */
+        if (!in_group[loc] || yielded[loc]) continue;
+        yielded[loc] = 1;
+        glv sn = glv_at(c, 2, loc);
+        double sc = masked_logdot(c, w->s.util, &w->full_query_evolv, &sn, w->mask_vec);
+        if (dbg && dbg->scores) dbg->scores[qi * c->n_nodes + loc] = sc;
+        w->rank[n_rank + n_new].score = sc; w->rank[n_rank + n_new].loc = loc; n_new++;
+      }
+      free(in_group);
+      stable_sort_desc(w->rank + n_rank, w->rank_tmp, n_new);
+      n_rank += n_new;
+      continue;
+    }
     int loc = w->rank[next++].loc;
     set_tt_edges(&tt, c, loc, pf->start_pend, c->bl[loc] / 2.); /* prepare_tt */
     ml_res r;
@@ -1231,6 +1294,7 @@ static int process_query(worker *w, const orc_prefs *pf, const uint8_t *query, o
     }
   }
   (void)cap;
+  free(fig_sc); free(fig_tmp); free(yielded);
   if (fatal) { free(results); return fatal; }
   if (n_results == 0) { free(results); return ORC_EMPTY_RESULTS; }
   if (dbg) {

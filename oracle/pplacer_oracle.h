@@ -136,6 +136,9 @@ int orc_three_tax_ll(orc_ctx *, const uint8_t *query_chars, int edge, double pen
 /* Gcat_model.refine (gcat_model.ml:387-419): replaces the context's site categories; call before orc_precompute */
 int orc_refine_site_categories(orc_ctx *, int32_t *site_cat_out, double *site_ll_out);
 
+/* figs for the ranking (fig.ml:120-148); m == 0: plain ranking */
+int orc_set_figs(orc_ctx *, int m, const int32_t *rep, const int32_t *ptr, const int32_t *idx);
+
 /* kernel-level hooks (inner loops on caller arrays, zero exponents) for the bit-for-bit comparison
  * with the reference's own linear_c.c in tests/test_oracle_vs_ref.py */
 void orc_k_gemmish(double *dst, const double *a, const double *b, int S, int n_sites);

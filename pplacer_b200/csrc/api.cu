@@ -18,6 +18,7 @@
 
 #include "../../include/pplacer_b200.h"
 #include "baseball.cuh"
+#include "fig.cuh"
 #include "device_common.cuh"
 #include "model_host.hpp"
 #include "precompute.cuh"
@@ -137,6 +138,17 @@ struct pp_ctx {
   int ttw_max_blocks = 0;
   DevBuf<int32_t> ord_keys, ord_vals, ord_keys2, ord_vals2;
   DevBuf<uint8_t> ord_tmp;
+  // figs (fig.cuh): host CSR, device copies, the representatives' supernode columns in prefilter layout
+  std::vector<int32_t> fig_rep, fig_ptr, fig_idx;
+  DevBuf<int32_t> d_fig_rep, d_fig_ptr, d_fig_idx, rep_e, fig_order, fig_i32, fig_pair_q, fig_pair_e, fig_pair_e2, fig_seg;
+  DevBuf<double> rep_a, rep_scores, rep_MT, rep_LT;
+  DevBuf<int32_t> rep_MTe;
+  DevBuf<uint32_t> fig_bits;
+  DevBuf<unsigned long long> fig_keys, fig_keys2;
+  DevBuf<uint8_t> fig_tmp;
+  int64_t rep_Np = 0;
+  bool rep_ready = false;
+  double rep_mt_pend = -1.0, rep_lt_pend = -1.0;
   // prefilter tiling: queries sorted by the window of sites they cover (prefilter.cuh window_keys_kernel)
   DevBuf<unsigned long long> win_keys, win_keys2;
   DevBuf<int32_t> win_vals, qorder, tile_lo, tile_hi;
@@ -201,6 +213,9 @@ extern "C" void pp_destroy(pp_ctx *c) {
   c->prep_status.release(); c->rank_in.release(); c->rank_loc.release(); c->seg_off.release(); c->i32pool.release();
   c->n_out.release(); c->Tq.release(); c->scores.release(); c->keys_in.release(); c->keys_out.release();
   c->ord_keys.release(); c->ord_vals.release(); c->ord_keys2.release(); c->ord_vals2.release(); c->ord_tmp.release();
+  c->d_fig_rep.release(); c->d_fig_ptr.release(); c->d_fig_idx.release(); c->rep_e.release(); c->fig_order.release(); c->fig_i32.release();
+  c->fig_pair_q.release(); c->fig_pair_e.release(); c->fig_pair_e2.release(); c->fig_seg.release(); c->rep_a.release(); c->rep_scores.release();
+  c->rep_MT.release(); c->rep_LT.release(); c->rep_MTe.release(); c->fig_bits.release(); c->fig_keys.release(); c->fig_keys2.release(); c->fig_tmp.release();
   c->win_keys.release(); c->win_keys2.release(); c->win_vals.release(); c->qorder.release(); c->tile_lo.release(); c->tile_hi.release(); c->win_tmp.release();
   c->wbuf.release(); c->f64pool.release(); c->cand.release(); c->cand_out.release(); c->pp_out.release();
   c->place_out.release(); c->n_calls.release(); c->counters.release(); c->tt_work.release();
@@ -546,6 +561,7 @@ extern "C" int pp_precompute(pp_ctx *c) {
     dim3 grid_e((c->L + 31) / 32, (unsigned)(c->Np / 32), 1);
     transpose_to_edge_major_kernel<int32_t><<<grid_e, 256, 0, c->stream>>>(c->g.e[2], c->snT_e, c->n_nodes, 1, c->L, c->Lp, c->Np, 0); LAUNCH_CHECK(c);
     c->tq_pend = c->mt_pend = c->lt_pend = -1.0;
+    c->rep_ready = false; c->rep_mt_pend = c->rep_lt_pend = -1.0;
   }
   cudaError_t e = cudaStreamSynchronize(c->stream);
   cudaFree(Pfull); cudaFree(Phalf); cudaFree(d_levels);
@@ -971,6 +987,57 @@ extern "C" int pp_three_tax_log_like(pp_ctx *c, int64_t n, const uint8_t *query_
 }
 
 // ---------------------------------------------------------------------------------------------
+// figs (fig.ml): ranking by fig representatives, groups expanded lazily per baseball wave (fig.cuh)
+// ---------------------------------------------------------------------------------------------
+extern "C" int pp_set_figs(pp_ctx *c, int32_t n_figs, const int32_t *rep, const int32_t *ptr, const int32_t *idx) {
+  if (!c || n_figs < 0) return fail(PP_EINVAL, "pp_set_figs: bad arguments");
+  CK(cudaSetDevice(c->device));
+  c->fig_rep.clear(); c->fig_ptr.clear(); c->fig_idx.clear();
+  c->rep_ready = false; c->rep_mt_pend = c->rep_lt_pend = -1.0;
+  if (n_figs == 0) return PP_OK;  // Fig.Dummy: the plain ranking of every non-root edge
+  if (!rep || !ptr || !idx || ptr[0] != 0) return fail(PP_EINVAL, "pp_set_figs: bad arguments");
+  for (int f = 0; f < n_figs; ++f) {
+    if (rep[f] < 0 || rep[f] >= c->n_nodes || rep[f] == c->root_id || ptr[f + 1] < ptr[f]) return fail(PP_EINVAL, "pp_set_figs: bad representative or edge list");
+  }
+  for (int k = 0; k < ptr[n_figs]; ++k)
+    if (idx[k] < 0 || idx[k] >= c->n_nodes || idx[k] == c->root_id) return fail(PP_EINVAL, "pp_set_figs: edge out of range");
+  c->fig_rep.assign(rep, rep + n_figs); c->fig_ptr.assign(ptr, ptr + n_figs + 1); c->fig_idx.assign(idx, idx + ptr[n_figs]);
+  int rc;
+  if ((rc = c->d_fig_rep.ensure(n_figs)) || (rc = c->d_fig_ptr.ensure(n_figs + 1)) || (rc = c->d_fig_idx.ensure(std::max(ptr[n_figs], 1)))) return rc;
+  CK(cudaMemcpyAsync(c->d_fig_rep.p, rep, sizeof(int32_t) * n_figs, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_fig_ptr.p, ptr, sizeof(int32_t) * (n_figs + 1), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_fig_idx.p, idx, sizeof(int32_t) * ptr[n_figs], cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PP_OK;
+}
+extern "C" int pp_n_figs(pp_ctx *c) { return c ? (int)c->fig_rep.size() : -1; }
+
+// the prefilter over the fig representatives only: the same kernels on a compact copy of the representatives' columns
+static int run_prefilter_reps(pp_ctx *c, int64_t Q, int kernel_choice, double pend) {
+  int rc;
+  const int m = (int)c->fig_rep.size();
+  if (!c->rep_ready) {
+    c->rep_Np = ((int64_t)m + 63) / 64 * 64;
+    if ((rc = c->rep_a.ensure((size_t)c->L * c->K * c->rep_Np)) || (rc = c->rep_e.ensure((size_t)c->L * c->rep_Np))) return rc;
+    gather_rep_columns_kernel<double><<<c->sm_count * 8, 256, 0, c->stream>>>(c->snT_a, c->rep_a.p, c->d_fig_rep.p, m, (int64_t)c->L * c->K, c->Np, c->rep_Np, 1.0); LAUNCH_CHECK(c);
+    gather_rep_columns_kernel<int32_t><<<c->sm_count * 8, 256, 0, c->stream>>>(c->snT_e, c->rep_e.p, c->d_fig_rep.p, m, (int64_t)c->L, c->Np, c->rep_Np, 0); LAUNCH_CHECK(c);
+    c->rep_ready = true;
+  }
+  // view swap: the prefilter launchers read the supernode arrays, the table caches and the score buffer from the context
+  std::swap(c->snT_a, c->rep_a.p); std::swap(c->snT_e, c->rep_e.p); std::swap(c->Np, c->rep_Np);
+  std::swap(c->scores, c->rep_scores); std::swap(c->MT, c->rep_MT); std::swap(c->MTe, c->rep_MTe); std::swap(c->LT, c->rep_LT);
+  std::swap(c->mt_pend, c->rep_mt_pend); std::swap(c->lt_pend, c->rep_lt_pend);
+  const int nn = c->n_nodes, root = c->root_id;
+  c->n_nodes = m; c->root_id = -1;
+  rc = run_prefilter(c, Q, kernel_choice, pend);
+  c->n_nodes = nn; c->root_id = root;
+  std::swap(c->snT_a, c->rep_a.p); std::swap(c->snT_e, c->rep_e.p); std::swap(c->Np, c->rep_Np);
+  std::swap(c->scores, c->rep_scores); std::swap(c->MT, c->rep_MT); std::swap(c->MTe, c->rep_MTe); std::swap(c->LT, c->rep_LT);
+  std::swap(c->mt_pend, c->rep_mt_pend); std::swap(c->lt_pend, c->rep_lt_pend);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
 // the path: pp_place
 // ---------------------------------------------------------------------------------------------
 struct PhaseTimer {
@@ -992,9 +1059,15 @@ static int place_batch(pp_ctx *c, const pp_prefs *pf, int64_t Q, const uint8_t *
   // ---- stage 0: query prep, evolved-query table (core.ml:121-158) ----
   if ((rc = prep_queries(c, Q, d_chars)) || (rc = build_query_table(c, pf->start_pend))) return rc;
   // ---- stage 1: prefilter + ranking (core.ml:187-197) ----
+  const int n_figs = (int)c->fig_rep.size();
+  const bool figs = n_figs > 0 && !all_edges;  // max_strikes 0 optimises every edge: the order is irrelevant
   {
     PhaseTimer t(c, 0);
-    if ((rc = run_prefilter(c, Q, c->prefilter_choice, pf->start_pend))) return rc;
+    if (figs) {
+      // Fig._enum_by_score (fig.ml:120-138): only the representatives are scored up front
+      if ((rc = run_prefilter_reps(c, Q, c->prefilter_choice, pf->start_pend)) || (rc = c->scores.ensure((size_t)Q * n_nodes))) return rc;
+      fill_f64_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->scores.p, std::nan(""), Q * (int64_t)n_nodes); LAUNCH_CHECK(c);
+    } else if ((rc = run_prefilter(c, Q, c->prefilter_choice, pf->start_pend))) return rc;
     t.stop();
   }
   const int64_t total = Q * (int64_t)n_nodes;
@@ -1003,26 +1076,87 @@ static int place_batch(pp_ctx *c, const pp_prefs *pf, int64_t Q, const uint8_t *
   // batch back through the full segmented sort (second attempt below).
   static const bool rank_full_only = [] { const char *e = std::getenv("PPB_RANK_FULL"); return e && std::atoi(e) != 0; }();
   const bool full_only = c->rank_mode < 0 ? rank_full_only : c->rank_mode == 1;
-  const bool can_truncate = !all_edges && !full_only && n_nodes > 4 * kTopK;
-  auto rank_full = [&]() -> int {
+  const bool can_truncate = !all_edges && !full_only && !figs && n_nodes > 4 * kTopK;
+  // stable descending order of Q segments of n scores each (nan and `root` last): out[q][n] = indices
+  auto rank_sorted = [&](const double *sc, int n, int root, int32_t *out) -> int {
     int rc2;
-    if ((rc2 = c->keys_in.ensure(total)) || (rc2 = c->keys_out.ensure(total)) || (rc2 = c->rank_in.ensure(total)) ||
-        (rc2 = c->rank_loc.ensure(total)) || (rc2 = c->seg_off.ensure(Q + 1)))
+    const int64_t tot = Q * (int64_t)n;
+    if ((rc2 = c->keys_in.ensure(tot)) || (rc2 = c->keys_out.ensure(tot)) || (rc2 = c->rank_in.ensure(tot)) || (rc2 = c->seg_off.ensure(Q + 1)))
       return rc2;
-    rank_keys_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->scores.p, c->keys_in.p, n_nodes, c->root_id, total); LAUNCH_CHECK(c);
-    iota_segments_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->rank_in.p, n_nodes, total); LAUNCH_CHECK(c);
+    rank_keys_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(sc, c->keys_in.p, n, root, tot); LAUNCH_CHECK(c);
+    iota_segments_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->rank_in.p, n, tot); LAUNCH_CHECK(c);
     std::vector<int32_t> off(Q + 1);
-    if (total > 0x7fffffffLL) return fail(PP_EINVAL, "place_batch: batch too large for 32-bit segment offsets");
-    for (int64_t q = 0; q <= Q; ++q) off[q] = (int32_t)(q * n_nodes);
+    if (tot > 0x7fffffffLL) return fail(PP_EINVAL, "place_batch: batch too large for 32-bit segment offsets");
+    for (int64_t q = 0; q <= Q; ++q) off[q] = (int32_t)(q * n);
     CK(cudaMemcpyAsync(c->seg_off.p, off.data(), (Q + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     size_t tmp_bytes = 0;
-    CK(cub::DeviceSegmentedSort::StableSortPairsDescending(nullptr, tmp_bytes, c->keys_in.p, c->keys_out.p, c->rank_in.p, c->rank_loc.p,
-                                                           total, (int)Q, c->seg_off.p, c->seg_off.p + 1, c->stream));
+    CK(cub::DeviceSegmentedSort::StableSortPairsDescending(nullptr, tmp_bytes, c->keys_in.p, c->keys_out.p, c->rank_in.p, out,
+                                                           tot, (int)Q, c->seg_off.p, c->seg_off.p + 1, c->stream));
     if ((rc2 = c->sort_tmp.ensure(tmp_bytes))) return rc2;
-    CK(cub::DeviceSegmentedSort::StableSortPairsDescending(c->sort_tmp.p, tmp_bytes, c->keys_in.p, c->keys_out.p, c->rank_in.p, c->rank_loc.p,
-                                                           total, (int)Q, c->seg_off.p, c->seg_off.p + 1, c->stream));
+    CK(cub::DeviceSegmentedSort::StableSortPairsDescending(c->sort_tmp.p, tmp_bytes, c->keys_in.p, c->keys_out.p, c->rank_in.p, out,
+                                                           tot, (int)Q, c->seg_off.p, c->seg_off.p + 1, c->stream));
     c->launches += 3;
     CK(cudaStreamSynchronize(c->stream));  // `off` must outlive the async copy
+    return PP_OK;
+  };
+  auto rank_full = [&]() -> int {
+    int rc2;
+    if ((rc2 = c->rank_loc.ensure(total))) return rc2;
+    return rank_sorted(c->scores.p, n_nodes, c->root_id, c->rank_loc.p);
+  };
+  // ---- fig ranking state (fig.cuh) ----
+  FigState fs{};
+  FigDev fd{};
+  int32_t *fig_seg_begin = nullptr, *fig_seg_end = nullptr;
+  auto fig_setup = [&]() -> int {
+    int rc2;
+    const int words = (n_nodes + 31) / 32;
+    if ((rc2 = c->rank_loc.ensure(total)) || (rc2 = c->fig_order.ensure((size_t)Q * n_figs)) || (rc2 = c->fig_i32.ensure((size_t)6 * Q)) ||
+        (rc2 = c->fig_bits.ensure((size_t)Q * words)))
+      return rc2;
+    if ((rc2 = rank_sorted(c->rep_scores.p, n_figs, -1, c->fig_order.p))) return rc2;
+    fs.order = c->fig_order.p; fs.rep_sc = c->rep_scores.p;
+    fs.fig_next = c->fig_i32.p; fs.n_ranked = c->fig_i32.p + Q; fs.n_new = c->fig_i32.p + 2 * Q; fs.need = c->fig_i32.p + 3 * Q;
+    fig_seg_begin = c->fig_i32.p + 4 * Q; fig_seg_end = c->fig_i32.p + 5 * Q;
+    fs.yielded = c->fig_bits.p; fs.words = words;
+    fd.ptr = c->d_fig_ptr.p; fd.idx = c->d_fig_idx.p; fd.m = n_figs;
+    fig_init_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(fs, (int)Q); LAUNCH_CHECK(c);
+    return PP_OK;
+  };
+  // one expansion round for the flagged queries: next group -> score the new members -> sort -> append
+  auto fig_expand_round = [&]() -> int {
+    int rc2;
+    CK(cudaMemsetAsync(c->counters.p + 6, 0, 2 * sizeof(int), c->stream));
+    fig_expand_kernel<<<(unsigned)Q, 128, 0, c->stream>>>(fs, fd, pf->strike_box, c->rank_loc.p, n_nodes, (int)Q, c->counters.p + 6); LAUNCH_CHECK(c);
+    CK(cudaMemcpyAsync(c->h_counters, c->counters.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const int n_pairs = c->h_counters[6];
+    if (n_pairs > 0) {
+      if ((rc2 = c->fig_pair_q.ensure(n_pairs)) || (rc2 = c->fig_pair_e.ensure(n_pairs)) || (rc2 = c->fig_pair_e2.ensure(n_pairs)) ||
+          (rc2 = c->fig_keys.ensure(n_pairs)) || (rc2 = c->fig_keys2.ensure(n_pairs)))
+        return rc2;
+      fig_pairs_kernel<<<(unsigned)Q, 128, 0, c->stream>>>(fs, c->rank_loc.p, n_nodes, (int)Q, c->fig_pair_q.p, c->fig_pair_e.p, fig_seg_begin, fig_seg_end,
+                                                             c->counters.p + 7); LAUNCH_CHECK(c);
+      DISPATCH_MODEL(c, {
+        fig_score_kernel<S_, G_><<<(unsigned)(((int64_t)n_pairs * 32 + 127) / 128), 128, 0, c->stream>>>(c->dm, c->g, c->Tq.p, c->d_site_cat, c->qsite.p, c->nq.p,
+                                                                                                       c->fig_pair_q.p, c->fig_pair_e.p, n_pairs, c->scores.p);
+        LAUNCH_CHECK(c);
+      });
+      // the reference's order inside a group: IntSet.elements (edge ascending), then a stable sort by score descending
+      size_t t1 = 0, t2 = 0;
+      CK(cub::DeviceSegmentedSort::SortKeys(nullptr, t1, c->fig_pair_e.p, c->fig_pair_e2.p, n_pairs, (int)Q, fig_seg_begin, fig_seg_end, c->stream));
+      CK(cub::DeviceSegmentedSort::StableSortPairsDescending(nullptr, t2, c->fig_keys.p, c->fig_keys2.p, c->fig_pair_e2.p, c->fig_pair_e.p, n_pairs, (int)Q,
+                                                             fig_seg_begin, fig_seg_end, c->stream));
+      if ((rc2 = c->fig_tmp.ensure(std::max(t1, t2)))) return rc2;
+      CK(cub::DeviceSegmentedSort::SortKeys(c->fig_tmp.p, t1, c->fig_pair_e.p, c->fig_pair_e2.p, n_pairs, (int)Q, fig_seg_begin, fig_seg_end, c->stream));
+      fig_keys_kernel<<<(n_pairs + 255) / 256, 256, 0, c->stream>>>(c->fig_pair_q.p, c->fig_pair_e2.p, n_pairs, c->scores.p, n_nodes, c->fig_keys.p); LAUNCH_CHECK(c);
+      CK(cub::DeviceSegmentedSort::StableSortPairsDescending(c->fig_tmp.p, t2, c->fig_keys.p, c->fig_keys2.p, c->fig_pair_e2.p, c->fig_pair_e.p, n_pairs, (int)Q,
+                                                             fig_seg_begin, fig_seg_end, c->stream));
+      c->launches += 2;
+    } else {
+      CK(cudaMemsetAsync(fig_seg_begin, 0, 2 * Q * sizeof(int32_t), c->stream));
+    }
+    fig_append_kernel<<<(unsigned)Q, 128, 0, c->stream>>>(fs, fig_seg_begin, c->fig_pair_e.p, c->rank_loc.p, n_nodes, (int)Q); LAUNCH_CHECK(c);
     return PP_OK;
   };
   auto rank_truncated = [&]() -> int {
@@ -1059,23 +1193,34 @@ static int place_batch(pp_ctx *c, const pp_prefs *pf, int64_t Q, const uint8_t *
       const int n_rank = truncated ? kTopK : n_nodes;
       {
         PhaseTimer tr(c, 1);
-        if ((rc = truncated ? rank_truncated() : rank_full())) return rc;
+        if ((rc = figs ? fig_setup() : (truncated ? rank_truncated() : rank_full()))) return rc;
         tr.stop();
       }
       PhaseTimer tw(c, 2);
       ball_init_kernel<<<qb, 256, 0, c->stream>>>(b, c->prep_status.p, (int)Q); LAUNCH_CHECK(c);
       CK(cudaMemsetAsync(c->counters.p + 5, 0, sizeof(int), c->stream));
       for (int wave = 0;; ++wave) {
+        if (figs) {  // expand groups until every unfinished query has the locations this wave needs (or no fig left)
+          for (int round = 0;; ++round) {
+            CK(cudaMemsetAsync(c->counters.p + 4, 0, sizeof(int), c->stream));
+            fig_need_kernel<<<qb, 256, 0, c->stream>>>(b, bp, fs, n_figs, (int)Q, c->counters.p + 4); LAUNCH_CHECK(c);
+            CK(cudaMemcpyAsync(c->h_counters, c->counters.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            if (c->h_counters[4] == 0) break;
+            if ((rc = fig_expand_round())) return rc;
+            if (round > n_figs + 8) return fail(PP_ECUDA, "place_batch: fig expansion did not terminate");
+          }
+        }
         CK(cudaMemsetAsync(c->counters.p + 1, 0, 2 * sizeof(int), c->stream));
         ball_plan_kernel<<<qb, 256, 0, c->stream>>>(b, bp, c->rank_loc.p, n_nodes, n_rank, c->root_id, (int)Q, c->cand.p, c->counters.p + 1,
-                                                    c->counters.p + 5); LAUNCH_CHECK(c);
+                                                    c->counters.p + 5, figs ? fs.n_ranked : nullptr); LAUNCH_CHECK(c);
         CK(cudaMemcpyAsync(c->h_counters, c->counters.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         const int n_cand = c->h_counters[1];
         if (n_cand == 0) break;
         if ((rc = launch_three_tax(c, c->cand.p, c->cand_out.p, n_cand, prm))) return rc;
         ball_update_kernel<<<qb, 256, 0, c->stream>>>(b, bp, c->cand.p, c->cand_out.p, n_rank, n_nodes, (int)Q, c->counters.p + 2,
-                                                      c->counters.p + 5); LAUNCH_CHECK(c);
+                                                      c->counters.p + 5, figs ? fs.n_ranked : nullptr, figs ? fs.fig_next : nullptr, n_figs); LAUNCH_CHECK(c);
         if (wave > n_nodes + 64) return fail(PP_ECUDA, "place_batch: baseball did not terminate");
       }
       CK(cudaMemcpyAsync(c->h_counters, c->counters.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));

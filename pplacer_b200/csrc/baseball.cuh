@@ -47,9 +47,10 @@ __global__ void ball_init_kernel(BallState b, const int32_t *__restrict__ prep_s
 // root_id are skipped (the root is never scored: fig.ml:103, stree.ml:33-35).
 __global__ void ball_plan_kernel(BallState b, BallPrefs bp, const int32_t *__restrict__ rank_loc, int n_nodes, int n_rank,
                                  int root_id, int Q, CandIn *__restrict__ cand, int *__restrict__ wave_count,
-                                 int *__restrict__ exhausted) {
+                                 int *__restrict__ exhausted, const int32_t *__restrict__ n_ranked = nullptr) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= Q || b.done[q]) { if (q < Q) b.wave_n[q] = 0; return; }
+  if (n_ranked) n_rank = n_ranked[q];  // fig ranking (fig.cuh): the ranking grows group by group, per query
   long long need = (long long)bp.t_max_strikes - b.n_strikes[q];
   const long long by_pitch = (long long)bp.t_max_pitches + 1 - b.n_results[q];
   if (by_pitch < need) need = by_pitch;
@@ -59,7 +60,7 @@ __global__ void ball_plan_kernel(BallState b, BallPrefs bp, const int32_t *__res
   int r = b.next_rank[q], cnt = 0;
   for (int rr = r; rr < n_rank && cnt < need; ++rr) cnt += (rk[rr] != root_id);
   if (cnt == 0) {  // ranking used up (with a truncated ranking the caller must redo the batch on the full one)
-    if (n_rank < n_nodes) atomicAdd(exhausted, 1);
+    if (!n_ranked && n_rank < n_nodes) atomicAdd(exhausted, 1);
     b.done[q] = 1; b.wave_n[q] = 0;
     return;
   }
@@ -77,7 +78,8 @@ __global__ void ball_plan_kernel(BallState b, BallPrefs bp, const int32_t *__res
 
 __global__ void ball_update_kernel(BallState b, BallPrefs bp, const CandIn *__restrict__ cand,
                                    const CandOut *__restrict__ out, int n_rank_total, int n_nodes, int Q, int *__restrict__ n_active,
-                                   int *__restrict__ exhausted) {
+                                   int *__restrict__ exhausted, const int32_t *__restrict__ n_ranked = nullptr,
+                                   const int32_t *__restrict__ fig_next = nullptr, int n_figs = 0) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= Q || b.done[q]) return;
   int nres = b.n_results[q], strikes = b.n_strikes[q];
@@ -102,7 +104,9 @@ __global__ void ball_update_kernel(BallState b, BallPrefs bp, const CandIn *__re
     }
   }
   b.n_results[q] = nres; b.n_strikes[q] = strikes; b.like_record[q] = record;
-  if (b.next_rank[q] >= n_rank_total) {
+  if (n_ranked) {  // fig ranking: used up only when every fig has been expanded
+    if (b.next_rank[q] >= n_ranked[q] && fig_next[q] >= n_figs) stop = true;
+  } else if (b.next_rank[q] >= n_rank_total) {
     if (!stop && n_rank_total < n_nodes) atomicAdd(exhausted, 1);
     stop = true;
   }

@@ -155,6 +155,19 @@ class Placer:
         _lib.check(_lib.load().pp_precompute(self.ctx))
         self.precomputed = True
 
+    def set_figs(self, figs=None, cutoff: Optional[float] = None):
+        """--fig-cutoff (fig.ml): figs = list of (rep, edges) from pplacer_b200.fig.figs_of_tree, or a cutoff to build them
+        from this reference tree; None / 0 restores the plain ranking."""
+        from . import fig as figmod
+        if cutoff is not None:
+            figs = figmod.figs_of_tree(cutoff, self.prob.tree)
+        if not figs:
+            _lib.check(_lib.load().pp_set_figs(self.ctx, 0, None, None, None))
+            return 0
+        rep, ptr, idx = figmod.figs_csr(figs)
+        _lib.check(_lib.load().pp_set_figs(self.ctx, len(rep), _lib.ip(rep), _lib.ip(ptr), _lib.ip(idx)))
+        return len(rep)
+
     def refine_site_categories(self, want_site_ll: bool = False):
         """Gcat_model.refine on the device (gcat_model.ml:387-419): returns the new zero-based category per site (and
         the R x L per-category site log-likelihoods).  The context keeps the new categories; precompute afterwards."""

@@ -622,3 +622,58 @@ def test_check_like_table(name):
     assert np.all(np.abs(t[:, 0] - want) <= 1e-7 * abs(want))
     nr = np.array(tree.nonroot_ids())
     assert np.all(np.abs(t[nr, 1] - want) <= 1e-7 * abs(want)) and np.isnan(t[tree.root, 1])
+
+
+# ---------------------------------------------------------------------------------------------
+# fig ranking (--fig-cutoff)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,cutoffs", [("c1_gtr", (0.05, 0.3)), ("synth", (0.05, 0.2, 1.0)), ("gcat_aa", (0.2,)), ("wag", (0.3,))])
+def test_fig_ranking_matches_oracle(oracle_binding, name, cutoffs):
+    """Fig._enum_by_score on the device (fig.cuh): representatives scored for every query, groups of figs expanded and
+    their members scored only when baseball needs more locations.  Same placements, the same number of locations
+    visited AND THE SAME EDGES SCORED as the oracle's lazy enumeration (scores of untouched edges stay NaN)."""
+    from pplacer_b200 import fig
+    prob, o, p = setup(name, oracle_binding)
+    try:
+        for cutoff in cutoffs:
+            figs = fig.figs_of_tree(cutoff, prob.tree)
+            assert figs and p.set_figs(figs) == len(figs)
+            o.set_figs(figs)
+            exp, n_exp, st_exp, oi = o.place(prob.query_chars, oracle_prefs(oracle_binding, prob), n_threads=4, debug=True)
+            got, n_got, st_got, gi = p.place(prob.query_chars, p.prefs(), debug=True)
+            near = assert_placements_match(got, n_got, st_got, exp, n_exp, st_exp, near_tie_ll=1e-3)
+            assert len(near_queries(near)) <= max(1, len(n_exp) // 50), near
+            assert (gi["n_pitches"] == oi["n_pitches"]).mean() >= 0.97
+            scored_g, scored_o = np.isfinite(gi["scores"]), np.isfinite(oi["scores"])
+            assert (scored_g == scored_o).all(axis=1).mean() >= 0.97          # the lazy expansion stops where the reference's does
+            both = scored_g & scored_o
+            assert np.all(np.abs(gi["scores"][both] - oi["scores"][both]) <= 1e-10 * np.abs(oi["scores"][both]))
+            assert scored_o.sum(axis=1).mean() < prob.tree.n_nodes - 1         # fewer edges scored than the plain ranking
+    finally:
+        p.set_figs(None)
+        o.set_figs(None)
+    # back to the plain ranking
+    exp, n_exp, st_exp, _ = o.place(prob.query_chars[:8], oracle_prefs(oracle_binding, prob), n_threads=4)
+    got, n_got, st_got, _ = p.place(prob.query_chars[:8], p.prefs())
+    assert_placements_match(got, n_got, st_got, exp, n_exp, st_exp, near_tie_ll=1e-3)
+
+
+def test_fig_ranking_at_the_c2_shape(c2_small, oracle_binding):
+    from pplacer_b200 import fig
+    prob, p = c2_small
+    figs = fig.figs_of_tree(0.1, prob.tree)
+    q = prob.query_chars[:96]
+    o = oracle_binding.Oracle(prob)
+    o.precompute()
+    o.set_figs(figs)
+    exp, n_exp, st_exp, oi = o.place(q, oracle_prefs(oracle_binding, prob), n_threads=os.cpu_count(), debug=True)
+    o.close()
+    try:
+        p.set_figs(figs)
+        got, n_got, st_got, gi = p.place(q, p.prefs(), debug=True)
+    finally:
+        p.set_figs(None)
+    near = assert_placements_match(got, n_got, st_got, exp, n_exp, st_exp, near_tie_ll=1e-3)
+    assert len(near_queries(near)) <= 2, near
+    assert (np.isfinite(gi["scores"]) == np.isfinite(oi["scores"])).all(axis=1).mean() >= 0.97
+    assert np.isfinite(oi["scores"]).sum(axis=1).mean() < 0.5 * prob.tree.n_nodes

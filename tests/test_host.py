@@ -147,3 +147,24 @@ def test_refpkg_with_stockholm_alignment_and_stats_file(tmp_path):
     (rp / "bad.sto").write_text("A  ACGT\n//\n")
     with pytest.raises(ValueError, match="before header"):
         seqio.read_stockholm(str(rp / "bad.sto"))
+
+
+def test_figs_of_tree_by_hand():
+    """Fig._figs_of_gtree (fig.ml:70-99) on a tree small enough to work through by hand (see the comments)."""
+    from pplacer_b200 import fig
+    t = newick.parse("((A:1,B:1):1,(C:1,D:1):1,E:5):0;")      # ids: A0 B1 (AB)2 C3 D4 (CD)5 E6 root7
+    assert fig.figs_of_tree(0.0, t) is None                    # Dummy
+    # cutoff 2: A-B and C-D are 2 apart -> two figs of two leaves, E alone; closed at the root: only leaf edges inside
+    assert fig.figs_of_tree(2.0, t) == [(6, [6]), (3, [3, 4]), (0, [0, 1])]
+    # cutoff 0.5: every cherry splits at its own node, which is added to both halves (add_edge_to_figs); the root then
+    # appends its children's (now empty) leftovers after the accumulated figs, in reverse child order
+    assert fig.figs_of_tree(0.5, t) == [(4, [4, 5]), (3, [3, 5]), (1, [1, 2]), (0, [0, 2]), (6, [6]), (3, []), (0, [])]
+    # the enumeration: representatives sorted, groups merged within strike_box, members sorted, nothing yielded twice
+    score = {0: -10.0, 1: -11.0, 2: -10.5, 3: -20.0, 4: -19.0, 5: -30.0, 6: -12.5}.get
+    figs = fig.figs_of_tree(0.5, t)
+    order = [e for _, e in fig.enum_by_score(figs, score, 3.0, t.nonroot_ids())]
+    # reps sorted: 0(-10) 0(-10, the empty fig) 1(-11) 6(-12.5) 4(-19) 3(-20) 3(-20); group 1 = {0,2} u {} u {1,2} u {6} (all within 3 of -10)
+    assert order == [0, 2, 1, 6, 4, 3, 5]
+    assert [e for _, e in fig.enum_by_score(None, score, 3.0, t.nonroot_ids())] == [0, 2, 1, 6, 4, 3, 5]
+    order = [e for _, e in fig.enum_by_score(figs, score, 0.6, t.nonroot_ids())]
+    assert order == [0, 2, 1, 6, 4, 5, 3]                      # strike_box 0.6: {0,2} | {1,(2)} | {6} | {4,5} | {3,(5)}
