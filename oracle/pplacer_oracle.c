@@ -1053,6 +1053,8 @@ static int find_upper_limit(three_tax *tt, double max_pend, const prior_t *prior
 }
 
 /* three_tax.ml:169-215 calc_marg_prob */
+/* diagnostic counters (tools/pp_stats.py): placements, outer integrand calls, inner integrand calls, ETOL retries */
+static long long g_pp_stats[4];
 typedef struct { three_tax *tt; const prior_t *prior; double base_ll, upper_limit, rel_err; int status; } marg_ud;
 static double marg_inner_fun(double pend_bl, void *ud_) {
   marg_ud *ud = (marg_ud *)ud_;
@@ -1062,11 +1064,16 @@ static double marg_inner_fun(double pend_bl, void *ud_) {
 static double marg_inner_integration(marg_ud *ud) {
   double res, err; int neval;
   int st = orc_qng(marg_inner_fun, ud, 0., ud->upper_limit, 0., ud->rel_err, &res, &err, &neval);
+  __atomic_fetch_add(&g_pp_stats[2], neval, __ATOMIC_RELAXED);
   if (st && !ud->status) ud->status = st;
   return res;
 }
+void orc_pp_stats(long long *out4, int reset) {
+  for (int i = 0; i < 4; i++) { out4[i] = g_pp_stats[i]; if (reset) g_pp_stats[i] = 0; }
+}
 static double marg_outer_fun(double dist_bl, void *ud_) {
   marg_ud *ud = (marg_ud *)ud_;
+  __atomic_fetch_add(&g_pp_stats[1], 1, __ATOMIC_RELAXED);
   if (ud->status) return 0.0; /* exception already unwinding */
   if (tt_set_dist_bl(ud->tt, dist_bl) != ORC_OK) { ud->status = ORC_ASSERT; return 0.0; }
   return marg_inner_integration(ud);
@@ -1075,6 +1082,7 @@ static int calc_marg_prob(three_tax *tt, const prior_t *prior, double rel_err, d
   const int max_n_exceptions = 10;
   double base_ll = tt_log_like(tt), cut_bl = tt_cut_bl(tt);
   int n_exceptions = 0;
+  __atomic_fetch_add(&g_pp_stats[0], 1, __ATOMIC_RELAXED);
   double upper_limit;
   int st = find_upper_limit(tt, max_pend, prior, base_ll, &upper_limit);
   if (st) return st;
@@ -1091,7 +1099,7 @@ static int calc_marg_prob(three_tax *tt, const prior_t *prior, double rel_err, d
       if (!ud.status && so) ud.status = so;
       val = res / cut_bl;
     }
-    if (ud.status == ORC_GSL_ETOL) { n_exceptions++; upper_limit = upper_limit / 2.; continue; }
+    if (ud.status == ORC_GSL_ETOL) { n_exceptions++; upper_limit = upper_limit / 2.; __atomic_fetch_add(&g_pp_stats[3], 1, __ATOMIC_RELAXED); continue; }
     if (ud.status) return ud.status;
     *out = base_ll + log(val);
     return ORC_OK;

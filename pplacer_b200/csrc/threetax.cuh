@@ -249,7 +249,13 @@ struct TTDriver {
   }
 
   // integrands: inner (three_tax.ml:187-189) and outer (:192-197)
+  // the inner (pendant) integral: an engine may replace it by a form that evaluates a whole rule per pass
+  __device__ int qng_inner(double a, double b, double epsabs, double epsrel, double *result) { return qng<false>(a, b, epsabs, epsrel, result); }
+  // an engine that evaluates a whole rule's abscissae in one pass may also keep the integrand values (same arithmetic)
+  __device__ bool integrand_memo(double, double *) { return false; }
   __device__ __noinline__ double integrand_inner(double pend) {
+    double v;
+    if (self().integrand_memo(pend, &v)) return v;
     return exp(self().f_pend(pend) - base_ll) * prior(pend);
   }
   __device__ __noinline__ double integrand_outer(double dist) {
@@ -259,7 +265,7 @@ struct TTDriver {
     self().set_dist_prox(dist, prox);
     self().cache_w();
     double res;
-    const int st = qng<false>(0.0, upper_limit, 0.0, pp_rel_err, &res);
+    const int st = self().qng_inner(0.0, upper_limit, 0.0, pp_rel_err, &res);
     if (st) pp_status = st;
     return res;
   }
@@ -353,7 +359,7 @@ struct TTDriver {
       if (fabs(cut_bl - 0.0) < 1e-5) {  // cut_bl =~ 0.  (ppatteries.ml:96)
         self().set_dist_prox(cut_bl / 2.0, (dist_bl + prox_bl) - cut_bl / 2.0);
         self().cache_w();
-        pp_status = qng<false>(0.0, upper_limit, 0.0, rel_err, &val);
+        pp_status = self().qng_inner(0.0, upper_limit, 0.0, rel_err, &val);
       } else {
         double res;
         const int so = qng<true>(0.0, cut_bl, 0.0, rel_err, &res);

@@ -47,15 +47,16 @@ struct TTGroup : TTDriver<TTGroup<R, G, TS, WS, RU>>, TTMachine<TTGroup<R, G, TS
   using Mach::opt_init; using Mach::opt_advance; using Mach::b_kind; using Mach::req_x; using Mach::o_status;
   static constexpr int S = 4, K = 4 * R, PM = 16 * R, NT = 32 * G;
   static constexpr int PQS = 5 * K;  // pendant matrix set: rows [R*4][5] = P[rs][0..3], QN[rs] (row sum, for 'N')
-  static constexpr int NBP = 6, NBD = 4, MEMO = 24, MAXJOBS = 12;
+  static constexpr int NBP = 6, NBD = 4, MEMO = 88, MAXJOBS = 12;
+  static constexpr int NBE = 44, CHE = 8;  // --pp: pendant points per eigenbasis pass (a whole QNG rule), points per register chunk
   static constexpr unsigned FULL = 0xffffffffu;
-  enum : int { CMD_DONE = 0, CMD_DIST1, CMD_PEND1_FUSED, CMD_PEND1_CACHED, CMD_DIST_BATCH, CMD_PEND_BATCH_FUSED, CMD_PEND_BATCH_CACHED };
+  enum : int { CMD_DONE = 0, CMD_DIST1, CMD_PEND1_FUSED, CMD_PEND1_CACHED, CMD_DIST_BATCH, CMD_PEND_BATCH_FUSED, CMD_PEND_BATCH_CACHED, CMD_PEND_EIG };
   // block-shared layout (doubles)
   static constexpr int C_STATD = 0, C_LAM = 4, C_X = 8, C_XIT = 24, C_RATES = 40, C_TOTAL = (40 + R + 1) & ~1;
   static constexpr int OFF_EX = C_TOTAL;                 // [MAXJOBS][K] exponentials of the posted builds
   static constexpr int OFF_JBL = OFF_EX + MAXJOBS * K;   // [MAXJOBS] branch length of each build job
   static constexpr int OFF_JOB = OFF_JBL + MAXJOBS;      // ints: [0] pass, [1] n_jobs, [2] queue slot, [4..] dst[MAXJOBS], qn[MAXJOBS]
-  static constexpr int OFF_OUT = OFF_JOB + 2 + MAXJOBS;  // [8] pass results
+  static constexpr int OFF_OUT = OFF_JOB + 2 + MAXJOBS;  // [8] pass results ( JOB()[3]: points of an eigenbasis pass )
   static constexpr int OFF_BAD = OFF_OUT + 8;            // [8] non-finite log terms per point
   static constexpr int OFF_PART = OFF_BAD + 8;           // [G][8] per-warp partial sums
   static constexpr int OFF_ESUM = OFF_PART + G * 8;      // [G] per-warp exponent sums
@@ -66,10 +67,18 @@ struct TTGroup : TTDriver<TTGroup<R, G, TS, WS, RU>>, TTMachine<TTGroup<R, G, TS
   static constexpr int OFF_MX = OFF_PB + PB_SIZE;        // memo: argument, proximal length, value
   static constexpr int OFF_MA = OFF_MX + MEMO;
   static constexpr int OFF_MF = OFF_MA + MEMO;
-  static constexpr int OFF_OBJ = OFF_MF + MEMO;          // warp 0's scalar state (this object)
+  static constexpr int OFF_MI = OFF_MF + MEMO;           // --pp: integrand value exp(f - base_ll) * prior(x) of a memo entry
+  static constexpr int OFF_OBJ = OFF_MI + MEMO;          // warp 0's scalar state (this object)
   static constexpr int OBJ_DOUBLES = 96;
-  static constexpr int OFF_W = OFF_OBJ + OBJ_DOUBLES;    // w[K][WS] for the first WS sites of the query
+  // --pp, eigenbasis pendant batch (pass_pend_eig): exponentials [NBE][K], results [NBE], per-warp partials [G][NBE],
+  // change of basis of the query column xq[mask][k] = sum_{c in mask} xit[c][k]
+  static constexpr int OFF_EE = OFF_OBJ + OBJ_DOUBLES;
+  static constexpr int OFF_OUTE = OFF_EE + NBE * K;
+  static constexpr int OFF_PARTE = OFF_OUTE + NBE;
+  static constexpr int OFF_XQ = OFF_PARTE + G * NBE;
+  static constexpr int OFF_W = OFF_XQ + 64;              // w[K][WS] for the first WS sites of the query
   static_assert(WS % NT == 0, "an iteration's sites are all in shared memory or all in the global overflow");
+  static_assert((OFF_EE % 2) == 0 && (K % 2) == 0, "double2 alignment of the exponentials");
   static_assert((PQS % 2) == 0 && (PM % 2) == 0 && (MEMO % 2) == 0 && (G % 2) == 0 && (MAXJOBS % 2) == 0 && (OFF_PD % 2) == 0 &&
                 (OFF_PB % 2) == 0, "double2 alignment of the matrix sets");
 
@@ -82,6 +91,8 @@ struct TTGroup : TTDriver<TTGroup<R, G, TS, WS, RU>>, TTMachine<TTGroup<R, G, TS
   int feed, attempt, status, optimise, final_pending;
   bool w_stale, pq_dirty, pd_dirty;
   int memo_n, memo_pending, memo_kind;  // memo_kind: -1 none, 0 pendant values, 1 distal values
+  int memo_cur;     // QNG reads its abscissae back in the order it announced them: the expected slot is tried first
+  bool memo_integrand;  // OFF_MI holds the integrand values of the memo entries
   int n_jobs;
 
   __device__ __forceinline__ static double *SM() { return reinterpret_cast<double *>(ppb_ttw_smem); }
@@ -114,13 +125,29 @@ struct TTGroup : TTDriver<TTGroup<R, G, TS, WS, RU>>, TTMachine<TTGroup<R, G, TS
     __syncwarp();
     ++n_jobs;
   }
-  __device__ void memo_clear(int kind) { memo_n = 0; memo_pending = 0; memo_kind = kind; }
-  __device__ bool memo_get(int kind, double x, double aux, double *f) const {
-    if (memo_kind != kind) return false;
+  __device__ void memo_clear(int kind) { memo_n = 0; memo_pending = 0; memo_kind = kind; memo_cur = 0; memo_integrand = false; }
+  __device__ int memo_find(int kind, double x, double aux) {
+    if (memo_kind != kind) return -1;
     const double *s = SM();
+    if (memo_cur < memo_n && s[OFF_MX + memo_cur] == x && s[OFF_MA + memo_cur] == aux) return memo_cur++;
     for (int i = 0; i < memo_n; ++i)
-      if (s[OFF_MX + i] == x && s[OFF_MA + i] == aux) { *f = s[OFF_MF + i]; return true; }
-    return false;
+      if (s[OFF_MX + i] == x && s[OFF_MA + i] == aux) { memo_cur = i + 1; return i; }
+    return -1;
+  }
+  __device__ bool memo_get(int kind, double x, double aux, double *f) {
+    const int i = memo_find(kind, x, aux);
+    if (i < 0) return false;
+    *f = SM()[OFF_MF + i];
+    return true;
+  }
+  // TTDriver::integrand_inner: exp(f_pend(x) - base_ll) * prior(x), computed for a whole rule by the lanes of warp 0
+  __device__ bool integrand_memo(double x, double *v) {
+    if (!memo_integrand) return false;
+    const int i = memo_find(0, x, 0.0);
+    if (i < 0) return false;
+    pend_bl = x; pq_dirty = true;  // what f_pend leaves behind
+    *v = SM()[OFF_MI + i];
+    return true;
   }
   // Brent's predictable first calls, several per pass (TTWarp::hint_prepare): posts the batch's build jobs
   __device__ void hint_prepare(int kind, double left, double right, double start, double v) {
@@ -514,6 +541,67 @@ struct TTGroup : TTDriver<TTGroup<R, G, TS, WS, RU>>, TTMachine<TTGroup<R, G, TS
     pass_end<NB>(lp);
   }
 
+  // Three_tax.log_like at n_pts pendant lengths from the cached product w, in the eigenbasis of the rate matrix: with
+  // P_r(t) = X exp(rho_r t Lambda) Xit^T the site likelihood is  u(t) = sum_{r,k} exp(rho_r t lambda_k) * y[r,k],
+  // y[r,k] = (sum_s w[r,s] X[s,k]) * (sum_{c in code} Xit[c,k])  - no pendant table per point, 16 multiply-adds per
+  // point and site against exponentials shared by the block (OFF_EE, computed by warp 0 before the pass is posted).
+  // A whole QNG rule (21 / 22 / 44 abscissae, integration.ml:27-31) is one pass instead of four to eight.
+  __device__ __noinline__ void pass_pend_eig(const GCand &c, int n_pts) {
+    double *s = SM();
+    const double *X = s + C_X, *XQ = s + OFF_XQ, *E = s + OFF_EE;
+    const int tid = threadIdx.x;
+    for (int c0 = 0; c0 < n_pts; c0 += CHE) {
+      LogProd lp[CHE];
+#pragma unroll
+      for (int b = 0; b < CHE; ++b) lp[b].init();
+      for (int i = tid; i < c.nq; i += NT) {
+        const uint32_t mask = ((uint32_t)c.qsite[i] >> kSiteCodeShift) & 15u;
+        double y[K];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          double w4[4];
+          if (i < WS) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) w4[k] = s[OFF_W + (r * 4 + k) * WS + i];
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) w4[k] = __ldcs(c.wg + (int64_t)(r * 4 + k) * c.Lp + i);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            double t = w4[0] * X[k];
+#pragma unroll
+            for (int q = 1; q < 4; ++q) t = fma(w4[q], X[q * 4 + k], t);
+            y[r * 4 + k] = t * XQ[mask * 4 + k];
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < CHE; ++b) {
+          const double2 *Eb = reinterpret_cast<const double2 *>(E + min(c0 + b, n_pts - 1) * K);  // block-uniform: broadcast loads
+          double u0 = 0.0, u1 = 0.0;
+#pragma unroll
+          for (int j = 0; j < K / 2; ++j) { const double2 e = Eb[j]; u0 = fma(e.x, y[2 * j], u0); u1 = fma(e.y, y[2 * j + 1], u1); }
+          lp[b].mul(u0 + u1);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < CHE; ++b) {
+        const double v = warp_sum(lp[b].value());
+        if (lane_id() == 0 && c0 + b < n_pts) s[OFF_PARTE + warp_id() * NBE + c0 + b] = v;
+      }
+    }
+    __syncthreads();
+    if (warp_id() == 0) {
+      for (int b = lane_id(); b < n_pts; b += 32) {
+        double tot = 0.0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) tot += s[OFF_PARTE + g * NBE + b];
+        s[OFF_OUTE + b] = tot - rate_term + e_tot_ln2;
+      }
+      __syncwarp();
+    }
+  }
+
   // ---------------------------------------------------------------------------------------------
   // --pp on this engine: warp 0 runs TTDriver::calc_marg_prob (nested Brent / QNG, ordinary calls)
   // and every objective value it needs is a BLOCKING request: post the command, then execute it
@@ -530,6 +618,7 @@ struct TTGroup : TTDriver<TTGroup<R, G, TS, WS, RU>>, TTMachine<TTGroup<R, G, TS
       case CMD_PEND1_CACHED: pass_pend<1, false, 1>(c, OFF_PQ); break;
       case CMD_DIST_BATCH: pass_dist<NBD, 1>(c, OFF_PB); break;
       case CMD_PEND_BATCH_FUSED: pass_pend<NBP, true, 1>(c, OFF_PB); break;
+      case CMD_PEND_EIG: pass_pend_eig(c, JOB()[3]); break;
       default: pass_pend<NBP, false, 1>(c, OFF_PB); break;
     }
     return true;
@@ -578,6 +667,90 @@ struct TTGroup : TTDriver<TTGroup<R, G, TS, WS, RU>>, TTMachine<TTGroup<R, G, TS
     run_command(cand);
     hint_commit();
   }
+  // gsl_integration_qng (GSL integration/qng.c; TTDriver::qng) for the INNER integral, with every rule's integrand values
+  // produced by one batched evaluation (hint_flush: lanes write the abscissae, one or two passes, lanes take exp * prior)
+  // and the rule's sums then read from shared memory - the same values combined in the same order as TTDriver::qng,
+  // without a function call, a memo search and two exponentials on one thread per abscissa.
+  __device__ __noinline__ int qng_inner(double a, double b, double epsabs, double epsrel, double *result) {
+    double *s = SM();
+    const double half_length = 0.5 * (b - a), abs_half_length = fabs(half_length), center = 0.5 * (b + a);
+    auto announce = [&](const double *xs, int n_pairs, int at, bool with_center) {  // evaluation order: (center,) +x_k, -x_k ...
+      __syncwarp();
+      const int n = 2 * n_pairs + (with_center ? 1 : 0);
+      for (int t = lane_id(); t < n; t += 32) {
+        double x;
+        if (with_center && t == 0) x = center;
+        else { const int u = t - (with_center ? 1 : 0); const double ab = half_length * xs[u >> 1]; x = (u & 1) ? center - ab : center + ab; }
+        s[OFF_MX + at + t] = x; s[OFF_MA + at + t] = 0.0;
+      }
+      __syncwarp();
+      memo_pending = n;
+      hint_flush();
+      pend_bl = s[OFF_MX + at + n - 1]; pq_dirty = true;  // the last call's set_pend_bl
+    };
+    memo_clear(0);
+    {  // the 21-point rule: center, x1 pairs, x2 pairs (the first 21 slots)
+      __syncwarp();
+      for (int t = lane_id(); t < 21; t += 32) {
+        double x;
+        if (t == 0) x = center;
+        else { const int u = t - 1, k = u >> 1; const double ab = half_length * (k < 5 ? c_qng_x1[k] : c_qng_x2[k - 5]); x = (u & 1) ? center - ab : center + ab; }
+        s[OFF_MX + t] = x; s[OFF_MA + t] = 0.0;
+      }
+      __syncwarp();
+      memo_pending = 21;
+      hint_flush();
+      pend_bl = s[OFF_MX + 20]; pq_dirty = true;
+    }
+    const double *v = s + OFF_MI;
+    double fv1[5], fv2[5], fv3[5], fv4[5], savfun[21];
+    const double f_center = v[0];
+    if (epsabs <= 0.0 && (epsrel < 50.0 * kDblEps || epsrel < 0.5e-28)) { *result = 0.0; return ST_GSL_EBADTOL; }
+    double res10 = 0.0, res21 = c_qng_w21b[5] * f_center, resabs = c_qng_w21b[5] * fabs(f_center);
+    for (int k = 0; k < 5; ++k) {
+      const double f1 = v[1 + 2 * k], f2 = v[2 + 2 * k], fv = f1 + f2;
+      res10 += c_qng_w10[k] * fv;
+      res21 += c_qng_w21a[k] * fv;
+      resabs += c_qng_w21a[k] * (fabs(f1) + fabs(f2));
+      savfun[k] = fv; fv1[k] = f1; fv2[k] = f2;
+    }
+    for (int k = 0; k < 5; ++k) {
+      const double f1 = v[11 + 2 * k], f2 = v[12 + 2 * k], fv = f1 + f2;
+      res21 += c_qng_w21b[k] * fv;
+      resabs += c_qng_w21b[k] * (fabs(f1) + fabs(f2));
+      savfun[k + 5] = fv; fv3[k] = f1; fv4[k] = f2;
+    }
+    resabs *= abs_half_length;
+    const double mean = 0.5 * res21;
+    double resasc = c_qng_w21b[5] * fabs(f_center - mean);
+    for (int k = 0; k < 5; ++k)
+      resasc += (c_qng_w21a[k] * (fabs(fv1[k] - mean) + fabs(fv2[k] - mean)) +
+                 c_qng_w21b[k] * (fabs(fv3[k] - mean) + fabs(fv4[k] - mean)));
+    resasc *= abs_half_length;
+    double result_kronrod = res21 * half_length;
+    double err = Drv::rescale_error((res21 - res10) * half_length, resabs, resasc);
+    if (err < epsabs || err < epsrel * fabs(result_kronrod)) { *result = result_kronrod; return ST_OK; }
+    announce(c_qng_x3, 11, 21, false);
+    double res43 = c_qng_w43b[11] * f_center;
+    for (int k = 0; k < 10; ++k) res43 += savfun[k] * c_qng_w43a[k];
+    for (int k = 0; k < 11; ++k) {
+      const double fv = v[21 + 2 * k] + v[22 + 2 * k];
+      res43 += fv * c_qng_w43b[k];
+      savfun[k + 10] = fv;
+    }
+    result_kronrod = res43 * half_length;
+    err = Drv::rescale_error((res43 - res21) * half_length, resabs, resasc);
+    if (err < epsabs || err < epsrel * fabs(result_kronrod)) { *result = result_kronrod; return ST_OK; }
+    announce(c_qng_x4, 22, 43, false);
+    double res87 = c_qng_w87b[22] * f_center;
+    for (int k = 0; k < 21; ++k) res87 += savfun[k] * c_qng_w87a[k];
+    for (int k = 0; k < 22; ++k) res87 += c_qng_w87b[k] * (v[43 + 2 * k] + v[44 + 2 * k]);
+    result_kronrod = res87 * half_length;
+    err = Drv::rescale_error((res87 - res43) * half_length, resabs, resasc);
+    *result = result_kronrod;
+    if (err < epsabs || err < epsrel * fabs(result_kronrod)) return ST_OK;
+    return ST_GSL_ETOL;
+  }
   // QNG announces each rule's abscissae before evaluating them: six per pass
   __device__ void hint_begin() { memo_clear(0); }
   __device__ void hint_add(double x) {
@@ -591,17 +764,46 @@ struct TTGroup : TTDriver<TTGroup<R, G, TS, WS, RU>>, TTMachine<TTGroup<R, G, TS
   __device__ void hint_flush() {
     double *s = SM();
     while (memo_pending > 0) {
+      if (!w_stale) {  // the cached product is current: the rest of the rule in ONE eigenbasis pass
+        const int n = memo_pending < NBE ? memo_pending : NBE;
+        __syncwarp();
+        for (int t = lane_id(); t < n * K; t += 32) {
+          const int b = t / K, rk = t - b * K;
+          s[OFF_EE + t] = exp(s[C_RATES + (rk >> 2)] * s[OFF_MX + memo_n + b] * s[C_LAM + (rk & 3)]);
+        }
+        __syncwarp();
+        n_jobs = 0;
+        if (lane_id() == 0) { JOB()[0] = CMD_PEND_EIG; JOB()[1] = 0; JOB()[3] = n; }
+        __syncwarp();
+        run_command(cand);
+        __syncwarp();
+        for (int b = lane_id(); b < n; b += 32) {
+          const double f = s[OFF_OUTE + b];
+          s[OFF_MF + memo_n + b] = f;
+          s[OFF_MI + memo_n + b] = exp(f - this->base_ll) * this->prior(s[OFF_MX + memo_n + b]);
+        }
+        __syncwarp();
+        pend_bl = s[OFF_MX + memo_n + n - 1]; pq_dirty = true;  // as after the last of these calls (set_pend_bl)
+        memo_n += n;
+        memo_pending -= n;
+        continue;
+      }
       const int n = memo_pending < NBP ? memo_pending : NBP;
       n_jobs = 0;
       for (int b = 0; b < NBP; ++b) add_job(s[OFF_MX + memo_n + (b < n ? b : n - 1)], OFF_PB + b * PQS, 1);
       if (w_stale) { post(CMD_PEND_BATCH_FUSED, false, true); w_stale = false; } else post(CMD_PEND_BATCH_CACHED, false, false);
       run_command(cand);
       __syncwarp();
-      if (lane_id() < n) s[OFF_MF + memo_n + lane_id()] = s[OFF_OUT + lane_id()];
+      if (lane_id() < n) {
+        const double f = s[OFF_OUT + lane_id()];
+        s[OFF_MF + memo_n + lane_id()] = f;
+        s[OFF_MI + memo_n + lane_id()] = exp(f - this->base_ll) * this->prior(s[OFF_MX + memo_n + lane_id()]);
+      }
       __syncwarp();
       memo_n += n;
       memo_pending -= n;
     }
+    memo_integrand = true;
   }
 };
 
@@ -733,6 +935,11 @@ tt_group_pp_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__
   for (int i = threadIdx.x; i < 16; i += blockDim.x) { sm[TT::C_X + i] = m->x[i]; sm[TT::C_XIT + i] = m->xit[i]; }
   for (int i = threadIdx.x; i < R; i += blockDim.x) sm[TT::C_RATES + i] = m->rates[i];
   for (int i = threadIdx.x; i < 8; i += blockDim.x) sm[TT::OFF_BAD + i] = 0.0;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {  // xq[mask][k] = sum_{c in mask} xit[c][k]
+    double acc = 0.0;
+    for (int cc = 0; cc < 4; ++cc) if ((i >> 2) >> cc & 1) acc += m->xit[cc * 4 + (i & 3)];
+    sm[TT::OFF_XQ + i] = acc;
+  }
   TT &tt = *reinterpret_cast<TT *>(sm + TT::OFF_OBJ);  // warp 0 only
   int *job = TT::JOB();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
