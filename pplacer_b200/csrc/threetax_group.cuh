@@ -546,35 +546,60 @@ struct TTGroup : TTDriver<TTGroup<R, G, TS, WS, RU>>, TTMachine<TTGroup<R, G, TS
   // y[r,k] = (sum_s w[r,s] X[s,k]) * (sum_{c in code} Xit[c,k])  - no pendant table per point, 16 multiply-adds per
   // point and site against exponentials shared by the block (OFF_EE, computed by warp 0 before the pass is posted).
   // A whole QNG rule (21 / 22 / 44 abscissae, integration.ml:27-31) is one pass instead of four to eight.
+  // running product of site likelihoods as (mantissa product, exponent): the factor's exponent is split off BEFORE the
+  // multiplication, so the chain from site to site is one DMUL; special factors (zero, negative, NaN, inf, subnormal)
+  // go through log() into `sp` so that -inf / NaN propagate as in the reference's sum of logs (linear_c.c:418)
+  struct EigProd {
+    double m, sp;
+    int e;
+    __device__ __forceinline__ void init() { m = 1.0; sp = 0.0; e = 0; }
+    __device__ __forceinline__ void mul(double u) {
+      const int hi = __double2hiint(u);
+      const int ef = (hi >> 20) & 0x7ff;
+      if (hi < 0 || ef == 0 || ef == 0x7ff) { sp += log(u); return; }
+      e += ef - 1023;
+      m *= __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(u));
+    }
+    __device__ __forceinline__ void renorm() {
+      const int hi = __double2hiint(m);
+      e += ((hi >> 20) & 0x7ff) - 1023;
+      m = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(m));
+    }
+    __device__ __forceinline__ double value() { renorm(); return log(m) + (double)e * kLn2 + sp; }
+  };
+  __device__ __forceinline__ void eig_load_w(const GCand &c, int i, double (&w)[K]) const {
+    const double *s = SM();
+    if (i < WS) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) w[k] = s[OFF_W + k * WS + i];
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) w[k] = __ldcs(c.wg + (int64_t)k * c.Lp + i);
+    }
+  }
   __device__ __noinline__ void pass_pend_eig(const GCand &c, int n_pts) {
     double *s = SM();
     const double *X = s + C_X, *XQ = s + OFF_XQ, *E = s + OFF_EE;
     const int tid = threadIdx.x;
     for (int c0 = 0; c0 < n_pts; c0 += CHE) {
-      LogProd lp[CHE];
+      EigProd lp[CHE];
 #pragma unroll
       for (int b = 0; b < CHE; ++b) lp[b].init();
-      for (int i = tid; i < c.nq; i += NT) {
+      int iter = 0;
+      for (int i = tid; i < c.nq; i += NT, ++iter) {
+        double w[K];
+        eig_load_w(c, i, w);
         const uint32_t mask = ((uint32_t)c.qsite[i] >> kSiteCodeShift) & 15u;
         double y[K];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          double w4[4];
-          if (i < WS) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) w4[k] = s[OFF_W + (r * 4 + k) * WS + i];
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) w4[k] = __ldcs(c.wg + (int64_t)(r * 4 + k) * c.Lp + i);
-          }
+        for (int r = 0; r < R; ++r)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            double t = w4[0] * X[k];
+            double t = w[r * 4] * X[k];
 #pragma unroll
-            for (int q = 1; q < 4; ++q) t = fma(w4[q], X[q * 4 + k], t);
+            for (int q = 1; q < 4; ++q) t = fma(w[r * 4 + q], X[q * 4 + k], t);
             y[r * 4 + k] = t * XQ[mask * 4 + k];
           }
-        }
 #pragma unroll
         for (int b = 0; b < CHE; ++b) {
           const double2 *Eb = reinterpret_cast<const double2 *>(E + min(c0 + b, n_pts - 1) * K);  // block-uniform: broadcast loads
@@ -582,6 +607,10 @@ struct TTGroup : TTDriver<TTGroup<R, G, TS, WS, RU>>, TTMachine<TTGroup<R, G, TS
 #pragma unroll
           for (int j = 0; j < K / 2; ++j) { const double2 e = Eb[j]; u0 = fma(e.x, y[2 * j], u0); u1 = fma(e.y, y[2 * j + 1], u1); }
           lp[b].mul(u0 + u1);
+        }
+        if ((iter & 255) == 255) {
+#pragma unroll
+          for (int b = 0; b < CHE; ++b) lp[b].renorm();
         }
       }
 #pragma unroll
