@@ -47,6 +47,10 @@ WORKLOADS = {
     # here; shows what the prefilter does when most site maxima sit far below 1
     "c4_long": (10_000, 4, "C4 with mean branch length 0.05 (tree length ~1000: the reference's exponent pull stops, DESIGN.md 5b)",
                 "pplacer defaults", False, {}),
+    # donovan-test ar53 (the reference's own regression set): 3 bundled genomes + synthetic genomes made from reference
+    # rows (5 % substitutions), SURVEY.md 8d "Q=256 synthetic genomes".  Needs the git-ignored fixture tests/golden/_ar53.
+    "c3": (6968, 3, "C3: donovan-test ar53 GTDB archaeal protein set (WAG + Price-CAT 20, 6968 taxa, E=13933, 8035 columns, 54 GB of GLVs), bundled + synthetic genomes",
+           "pplacer defaults (keep_at_most 7, max_strikes 6, max_pitches 40)", False, {}),
     "c5": (800, 2, "C5: C2 shape in posterior-probability mode",
            "-p --keep-at-most 40 (calc_pp, keep_factor 0.001, max_strikes 20)", True, {"keep_at_most": 40}),
 }
@@ -121,6 +125,20 @@ def measured_peaks():
 def build_workload(name: str, Q: int, rank: int):
     from pplacer_b200 import synth
     from pplacer_b200.reference import build_problem
+    if name == "c3":
+        from pplacer_b200 import configs, models
+        if not configs.ar53_available():
+            raise SystemExit("bench.py --workload c3 needs tests/golden/_ar53 (tests/golden/make_fixtures.py /root/reference --ar53)")
+        import numpy as np
+        base = configs.ar53()
+        names = [n[0] for n in base.query_names]
+        # synthetic genomes: reference rows with 5 % substitutions (full length), seeded per rank
+        rng = np.random.default_rng(3000 + rank)
+        z = np.load(os.path.join(configs.GOLDEN, "_ar53", "msa.npz"))
+        rows = rng.choice(len(z["names"]), size=max(Q - 3, 0), replace=False)
+        aln = [(str(z["names"][i]), z["chars"][i].tobytes().decode("ascii")) for i in rows]
+        extra = [(n, s) for n, s in synth.perturbed_queries(aln, models.PROT_CODE, 3000 + rank) if n.endswith("_0")]
+        return configs.ar53(extra_queries=extra)
     taxa, seed = WORKLOADS[name][0], WORKLOADS[name][1]
     from pplacer_b200.configs import C4_MEAN_BL
     s = synth.simulate_reference(taxa, 1500, seed=seed, alpha=0.5, mean_bl=C4_MEAN_BL if name == "c4" else 0.05)
@@ -237,7 +255,7 @@ def run_ours(args):
         return float(t.item())
 
     wl = WORKLOADS[args.workload]
-    Q = args.queries if args.queries > 0 else (2000 if args.workload == "c5" else 10_000)
+    Q = args.queries if args.queries > 0 else {"c5": 2000, "c3": 256}.get(args.workload, 10_000)
     strong = args.scaling == "strong"
     if strong:
         # ONE fixed query set (the same on every rank: seeded), contiguous shards (pplacer_b200/shard.py) - what
@@ -259,7 +277,7 @@ def run_ours(args):
     K = prefs.keep_at_most
     stream = torch.cuda.Stream(device=dev)
     p.set_stream(stream.cuda_stream)
-    p.set_prefilter_kernel({"default": 0, "direct": 1, "table": 2, "staged": 4, "dmma": 5}[args.prefilter])
+    p.set_prefilter_kernel({"default": 0, "direct": 1, "table": 2, "staged": 4, "dmma": 5, "logtable": 6, "qlane": 7}[args.prefilter])
     p.set_three_tax_engine({"default": 0, "block": 1, "warp": 2, "group": 3, "eigen": 4}[args.tt_engine], args.tt_blocks_per_sm)
     n_figs = p.set_figs(cutoff=args.fig_cutoff) if args.fig_cutoff > 0 else 0
     fp64_peak = p.measure_fp64_peak()
@@ -359,13 +377,15 @@ def run_ours(args):
     sum_nq = float(inf.sum())
     R, S, E = p.R, p.S, p.n_nodes - 1
     share = {k: float(v) for k, v in zip(("prefilter", "rank", "optimise", "pp"), phases)}
-    pre_flops = 2.0 * R * S * E * sum_nq                 # 2RS flops per (query, edge, informative site)
+    pre_flops = 2.0 * (S if p.gcat else R * S) * E * sum_nq   # 2RS flops per (query, edge, informative site); Gcat: one category per site
     pre_ms = share["prefilter"]
     pre_tflops = pre_flops / (pre_ms * 1e-3) / 1e12 if pre_ms > 0 else 0.0
     used = p.prefilter_kernel_used()
-    kname = {1: "prefilter_direct_kernel", 2: "prefilter_table_kernel", 4: "prefilter_staged_kernel<MMA=false>", 5: "prefilter_staged_kernel<MMA=true>"}.get(used, "?")
+    kname = {1: "prefilter_direct_kernel", 2: "prefilter_table_kernel", 4: "prefilter_staged_kernel<MMA=false>", 5: "prefilter_staged_kernel<MMA=true>", 6: "prefilter_logtable_kernel", 7: "prefilter_qlane_kernel"}.get(used, "?")
     # compulsory HBM bytes: one pass over the prefilter copy of the supernodes + query codes + scores
     pre_bytes = (8.0 * (4 if used == 2 else R * S) + 4.0) * p.L * (E + 1) + Q * p.L + 8.0 * Q * (E + 1)
+    if args.workload == "c3":
+        kname = "prefilter_direct_kernel<S=20, Gcat>"
     roofline_prefilter = {
         "kernel": kname, "bound": "fp64", "achieved": pre_tflops, "peak": fp64_peak,
         "unit": "TFLOP/s", "frac": pre_tflops / fp64_peak if fp64_peak else None,
@@ -393,11 +413,27 @@ def run_ours(args):
             "note": "table form: one select + one multiply per (query, edge, site) unit; issue-bound, not FP64-bound - no FP64 "
                     "fraction is claimed for it; roofline.prefilter_direct carries the FMA form the FP64 roofline is defined on",
         })
+    if used == 7:
+        # query-lane log table: one shared-memory load (a broadcast request: <= 6 distinct words) and one DADD per
+        # (query, edge, site) unit, no FMAs - its roof is the shared-memory pipe, one warp request per clock per SM
+        lsu_peak = props.multi_processor_count * 32.0 * float(sm_mhz) * 1e6 / 1e9 if sm_mhz else None
+        ach = units / (pre_ms * 1e-3) / 1e9 if pre_ms > 0 else 0.0
+        roofline_prefilter.update({
+            "bound": "shared-memory requests", "achieved": ach, "unit": "G units/s", "peak": lsu_peak,
+            "frac": ach / lsu_peak if lsu_peak else None,
+            "peak_source": "SMs x 32 units per LDS request x SM clock (one shared-memory request per clock per SM); the DADD pipe allows twice that",
+            "algorithmic_tflops_equivalent": pre_tflops, "units_per_launch": units,
+            "note": "query-lane log-table form (prefilter_qlane.cuh): lane = query, warp = 32 queries x 32 edges, table tile streamed by TMA bulk copies; "
+                    "no FP64 fraction is claimed for it; roofline.prefilter_direct carries the FMA form the FP64 roofline is defined on",
+        })
+        roofline_prefilter["hbm"]["bytes_per_launch"] = 48.0 * p.L * (E + 1) + Q * p.L + 8.0 * Q * (E + 1)
+        roofline_prefilter["hbm"]["achieved"] = roofline_prefilter["hbm"]["bytes_per_launch"] / (pre_ms * 1e-3) / 1e9 if pre_ms > 0 else 0.0
+        roofline_prefilter["hbm"]["note"] = "compulsory bytes: one pass over the six-column log table + query codes + scores"
     # the graded prefilter form: K = R*S DFMAs per unit exactly as ten_masked_logdot_c writes them (linear_c.c:465),
     # timed on the same batch outside the step loop (pp_prefilter_time: CUDA events on the launching stream)
     roofline_direct = None
     other_forms = {}
-    if not args.no_direct_prefilter and world == 1:
+    if not args.no_direct_prefilter and world == 1 and S == 4 and not p.gcat and R == 4:
         try:
             forms = {"direct": (1, "prefilter_direct_kernel"), "staged": (4, "prefilter_staged_kernel<MMA=false> (TMA bulk copies + mbarrier ring, DFMA)"),
                      "dmma": (5, "prefilter_staged_kernel<MMA=true> (TMA bulk copies + mbarrier ring, DMMA m8n8k4)")}
@@ -414,7 +450,7 @@ def run_ours(args):
                 "algorithmic_flops_per_launch": pre_flops, "ms_per_launch": d_ms, "units_per_launch": units,
                 "hbm": {"achieved": ((8.0 * R * S + 4.0) * p.L * (E + 1) + Q * p.L + 8.0 * Q * (E + 1)) / (d_ms * 1e-3) / 1e9,
                         "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "peak_source": peaks_src},
-                "note": "one launch over the step's whole batch, not part of the timed step (the step uses the table form)",
+                "note": "one launch over the step's whole batch, not part of the timed step (the step uses a table form)",
             }
         except Exception as ex:   # e.g. a model without a direct/table split
             roofline_direct = {"error": str(ex)}
@@ -454,6 +490,16 @@ def run_ours(args):
             roofline_tt["traffic_note"] = "dram bytes per step (all second-stage launches), ncu capture r2f (profiles/traffic.json)"
     except Exception:
         pass
+    if args.workload == "c3":
+        # few queries against 17.9 GB of supernodes: the prefilter is bound by HBM - report it on that roof
+        hb = roofline_prefilter["hbm"]
+        n_rows = (Q + 63) // 64   # the supernodes stream once per 64-query block row (8 queries per warp x 8 warps)
+        hb["bytes_per_launch"] = (8.0 * (p.S if p.gcat else R * S) + 4.0) * p.L * (E + 1) * n_rows + Q * p.L + 8.0 * Q * (E + 1)
+        hb["achieved"] = hb["bytes_per_launch"] / (pre_ms * 1e-3) / 1e9 if pre_ms > 0 else 0.0
+        hb["note"] = "one pass over the supernodes (K=20 planes + exponents) per 64-query block row + query codes + scores"
+        roofline_prefilter.update({"bound": "hbm", "achieved": hb["achieved"], "peak": hb["peak"], "unit": "GB/s",
+                                   "frac": hb["achieved"] / hb["peak"] if hb["peak"] else None, "peak_source": hb["peak_source"],
+                                   "fp64": {"achieved": pre_tflops, "peak": fp64_peak, "unit": "TFLOP/s"}})
     dominant_tt = opt_ms >= pre_ms
     roofline = dict(roofline_tt if dominant_tt else roofline_prefilter)
     roofline["share_of_step_ms"] = share
@@ -508,7 +554,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = every rank places its own --queries; strong = one fixed set of --total-queries sharded over the ranks")
     ap.add_argument("--total-queries", type=int, default=0, help="--scaling strong: size of the fixed query set (default: --queries)")
-    ap.add_argument("--prefilter", default="default", choices=["default", "direct", "table", "staged", "dmma"],
+    ap.add_argument("--prefilter", default="default", choices=["default", "direct", "table", "staged", "dmma", "logtable", "qlane"],
                     help="prefilter kernel: library default, the FMA form, or the four-base table form")
     ap.add_argument("--tt-engine", default="default", choices=["default", "block", "warp", "group", "eigen"],
                     help="second-stage engine: library default (group), block-per-candidate, warp-per-candidate, block + shared-memory w")

@@ -24,6 +24,7 @@
 #include "precompute.cuh"
 #include "prefilter.cuh"
 #include "prefilter_staged.cuh"
+#include "prefilter_qlane.cuh"
 #include "query.cuh"
 #include "threetax.cuh"
 #include "threetax_warp.cuh"
@@ -102,6 +103,10 @@ struct pp_ctx {
   double mt_pend = -1.0;   // ... and the four-base table MT
   TqPrimary tqp;
   DevBuf<uint8_t> qc;
+  DevBuf<double> LTq;               // query-lane log table [Np/32][L][32][6]
+  DevBuf<uint32_t> qcol;            // column bytes of the sorted queries, four sites per word
+  DevBuf<int32_t> slow_flag;
+  double ltq_pend = -1.0;
   DevBuf<double> partial, MT, LT;  // LT: log-table form [L][5][Np]
   TqFive tq5;
   double lt_pend = -1.0;
@@ -206,7 +211,7 @@ extern "C" void pp_destroy(pp_ctx *c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (int w = 0; w < 3; ++w) { if (c->g.a[w]) cudaFree(c->g.a[w]); if (c->g.e[w]) cudaFree(c->g.e[w]); }
-  c->qc.release(); c->partial.release(); c->MT.release(); c->LT.release(); c->MTe.release();
+  c->qc.release(); c->partial.release(); c->MT.release(); c->LT.release(); c->LTq.release(); c->qcol.release(); c->slow_flag.release(); c->MTe.release();
   void *ptrs[] = {c->snT_a, c->snT_e, c->dm, c->d_bl, c->d_code_of_char, c->d_ref_codes, c->d_site_cat, c->d_child_ptr, c->d_child_idx, c->d_parent, c->d_leaf_row};
   for (void *p : ptrs) if (p) cudaFree(p);
   c->chars.release(); c->codes.release(); c->sort_tmp.release(); c->qsite.release(); c->nq.release();
@@ -560,7 +565,7 @@ extern "C" int pp_precompute(pp_ctx *c) {
     transpose_to_edge_major_kernel<double><<<grid, 256, 0, c->stream>>>(c->g.a[2], c->snT_a, c->n_nodes, c->K, c->L, c->Lp, c->Np, 1.0); LAUNCH_CHECK(c);
     dim3 grid_e((c->L + 31) / 32, (unsigned)(c->Np / 32), 1);
     transpose_to_edge_major_kernel<int32_t><<<grid_e, 256, 0, c->stream>>>(c->g.e[2], c->snT_e, c->n_nodes, 1, c->L, c->Lp, c->Np, 0); LAUNCH_CHECK(c);
-    c->tq_pend = c->mt_pend = c->lt_pend = -1.0;
+    c->tq_pend = c->mt_pend = c->lt_pend = c->ltq_pend = -1.0;
     c->rep_ready = false; c->rep_mt_pend = c->rep_lt_pend = -1.0;
   }
   cudaError_t e = cudaStreamSynchronize(c->stream);
@@ -751,6 +756,40 @@ static int launch_prefilter_logtable(pp_ctx *c, int64_t Q, double pend, int bloc
   return prefilter_finish(c, Q, g);
 }
 
+// r5a: C2 10.0 -> 3.8 ms, C4 122 -> 44.6 ms per 10k queries against the product-table form: the default for >= 256 queries (PPB_PF_QLANE=0 restores the table form)
+static const bool kQlaneDefault = [] { const char *e = std::getenv("PPB_PF_QLANE"); return !e || std::atoi(e) != 0; }();
+// query-lane log-table form (prefilter_qlane.cuh): lane = query, warp = 32 queries x 32 edges, TMA ring over the table tile
+template <int W, int SPS, int NS, int MINB>
+static int launch_prefilter_qlane(pp_ctx *c, int64_t Q, double pend, int blocks_per_sm) {
+  int rc;
+  using G = QlaneGeom<W, SPS, NS>;
+  SnT sn; sn.a = c->snT_a; sn.e = c->snT_e; sn.Np = c->Np; sn.L = c->L; sn.K = c->K; sn.n_nodes = c->n_nodes;
+  if (c->ltq_pend != pend) {  // once per (reference, pendant length)
+    if ((rc = c->LTq.ensure((size_t)c->L * c->Np * kQlCols))) return rc;
+    for (int s0 = 0; s0 < c->L; s0 += 65535) {
+      qlane_table_kernel<16><<<dim3((unsigned)((c->Np + 127) / 128), std::min(65535, c->L - s0)), 128, 0, c->stream>>>(sn, c->tq5, c->LTq.p, s0); LAUNCH_CHECK(c);
+    }
+    c->ltq_pend = pend;
+  }
+  const PreGeom g = prefilter_geometry(c, Q, 32, 1, W, blocks_per_sm);
+  const int n4 = (c->L + 3) / 4;
+  if ((rc = c->tile_lo.ensure(g.nqt)) || (rc = c->tile_hi.ensure(g.nqt)) || (rc = c->qcol.ensure((size_t)g.nqt * n4 * 32)) || (rc = c->slow_flag.ensure(Q))) return rc;
+  CK(cudaMemsetAsync(c->slow_flag.p, 0, sizeof(int32_t) * Q, c->stream));
+  tile_range_kernel<32><<<(g.nqt + 127) / 128, 128, 0, c->stream>>>(c->qsite.p, c->nq.p, c->qorder.p, (int)Q, g.nqt, c->Lp, c->tile_lo.p, c->tile_hi.p); LAUNCH_CHECK(c);
+  qlane_pack_kernel<<<dim3((n4 + 7) / 8, g.nqt), 256, 0, c->stream>>>(c->codes.p, c->qorder.p, c->qcol.p, (int)Q, c->L, c->Lp, g.nqt, c->slow_flag.p); LAUNCH_CHECK(c);
+  PreArgs A;
+  if ((rc = prefilter_args(c, Q, g, &A))) return rc;
+  const size_t sm = G::smem_bytes();
+  auto kern = prefilter_qlane_kernel<W, SPS, NS, MINB>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  kern<<<dim3(g.gx, g.gy, g.zs), (W + 1) * 32, sm, c->stream>>>(A, c->LTq.p, c->qcol.p); LAUNCH_CHECK(c);
+  c->prefilter_kernel_used = 7;
+  if ((rc = prefilter_finish(c, Q, g))) return rc;
+  A.out = c->scores.p;
+  prefilter_qlane_fix_kernel<<<dim3((unsigned)Q, (c->n_nodes + 127) / 128), 128, 0, c->stream>>>(A, c->qsite.p, c->Lp, c->slow_flag.p, c->scores.p); LAUNCH_CHECK(c);
+  return PP_OK;
+}
+
 // staged form (prefilter_staged.cuh): TMA bulk copies + mbarrier ring; MMA = the K-contraction on the FP64 tensor cores
 template <int W, int SPS, int NS, bool MMA, int MINB>
 static int launch_prefilter_staged(pp_ctx *c, int64_t Q, int blocks_per_sm) {
@@ -797,6 +836,13 @@ static int run_prefilter(pp_ctx *c, int64_t Q, int kernel_choice, double pend) {
     // log-table form: one load + one add per (query, edge, site); measured (r4f) 11.8 ms against 9.9 ms for the product
     // table on C2 - it executes half the instructions but one L1 request per (query, site) instead of 5 per site
     // (ncu r4g: l1tex 77 %, long_scoreboard 6.4 warps per issue) - so it is selectable (6), not the default
+    if (kernel_choice == 7 || (kernel_choice == 0 && kQlaneDefault && Q >= 256)) {
+      static const int qv = [] { const char *e = std::getenv("PPB_PFQ_VARIANT"); return e ? std::atoi(e) : 0; }();
+      if (qv == 1) return launch_prefilter_qlane<4, 16, 4, 2>(c, Q, pend, 2);
+      if (qv == 2) return launch_prefilter_qlane<8, 8, 6, 1>(c, Q, pend, 1);
+      if (qv == 3) return launch_prefilter_qlane<2, 8, 6, 3>(c, Q, pend, 3);
+      return launch_prefilter_qlane<4, 8, 6, 2>(c, Q, pend, 2);
+    }
     if (kernel_choice == 6) {
       if (few) return launch_prefilter_logtable<8, 1, 1>(c, Q, pend, 12);
       if (geom == 1) return launch_prefilter_logtable<4, 4, 8>(c, Q, pend, 8);
@@ -1407,7 +1453,7 @@ extern "C" int pp_set_stream(pp_ctx *c, void *cuda_stream) {
 }
 
 extern "C" int pp_set_prefilter_kernel(pp_ctx *c, int32_t kernel) {
-  if (!c || kernel < 0 || kernel > 6) return fail(PP_EINVAL, "pp_set_prefilter_kernel: kernel must be 0 ... 6");
+  if (!c || kernel < 0 || kernel > 7) return fail(PP_EINVAL, "pp_set_prefilter_kernel: kernel must be 0 ... 7");
   if ((kernel == 2 || kernel >= 4) && !(c->S == 4 && !c->gcat && c->K == 16)) return fail(PP_EINVAL, "pp_set_prefilter_kernel: the table and staged forms exist for the DNA Gamma-4 model only");
   c->prefilter_choice = kernel;
   return PP_OK;

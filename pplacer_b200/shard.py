@@ -21,10 +21,27 @@ def shard_range(Q: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+_bufs = {}
+
+
+def _buf(key, nbytes, device=None, pin=False):
+    """cached staging buffers: the gather runs every step, its buffers are allocated once"""
+    import torch
+    t = _bufs.get(key)
+    if t is None or t.numel() < nbytes:
+        if device is not None:
+            t = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        else:
+            t = torch.empty(nbytes, dtype=torch.uint8, pin_memory=pin)
+        _bufs[key] = t
+    return t[:nbytes]
+
+
 def gather_results(out: np.ndarray, n_out: np.ndarray, status: np.ndarray, Q: int, rank: int, world: int,
                    device: Optional[str] = None):
-    """Gather per-rank (results[Qr,K], n_out[Qr], status[Qr]) to rank 0 in query order.  Returns the
-    full arrays on rank 0 and None elsewhere.  Byte tensors carry the pp_result records."""
+    """Gather per-rank (results[Qr,K], n_out[Qr], status[Qr]) to rank 0 in query order: ONE collective
+    (torch.distributed gather: NCCL on GPUs, gloo in the CPU tests) of one byte row per rank - the pp_result records,
+    then the counts, then the status words.  Returns the full arrays on rank 0 and None elsewhere."""
     import torch
     import torch.distributed as dist
 
@@ -34,30 +51,40 @@ def gather_results(out: np.ndarray, n_out: np.ndarray, status: np.ndarray, Q: in
     sizes = [shard_range(Q, r, world)[1] - shard_range(Q, r, world)[0] for r in range(world)]
     cap = max(sizes)
     rec = _lib.RESULT_DTYPE.itemsize
-    buf = np.zeros(cap * (K * rec + 8), dtype=np.uint8)
+    row = (cap * (K * rec + 8) + 15) // 16 * 16
     n = out.shape[0]
-    buf[:n * K * rec] = np.frombuffer(out.tobytes(), dtype=np.uint8)
-    tail = buf[cap * K * rec:]
-    tail[:n * 4] = np.frombuffer(n_out.astype(np.int32).tobytes(), dtype=np.uint8)
-    tail[cap * 4:cap * 4 + n * 4] = np.frombuffer(status.astype(np.int32).tobytes(), dtype=np.uint8)
-    t = torch.from_numpy(buf)
-    if device is not None:
-        t = t.to(device)
-    gathered = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-    dist.gather(t, gathered, dst=0)
+    on_gpu = device is not None
+    send = _buf(("send", on_gpu), row, pin=on_gpu)
+    sv = send.numpy()
+    sv[:n * K * rec] = np.ascontiguousarray(out).view(np.uint8).reshape(-1)
+    sv[cap * K * rec:cap * K * rec + n * 4] = np.ascontiguousarray(n_out, dtype=np.int32).view(np.uint8)
+    sv[cap * K * rec + cap * 4:cap * K * rec + cap * 4 + n * 4] = np.ascontiguousarray(status, dtype=np.int32).view(np.uint8)
+    if on_gpu:
+        d_send = _buf(("d_send", str(device)), row, device=device)
+        d_send.copy_(send, non_blocking=True)
+    else:
+        d_send = send
+    recv = None
+    if rank == 0:
+        recv = _buf(("recv", str(device)), world * row, device=device) if on_gpu else _buf(("recv", None), world * row)
+    dist.gather(d_send, list(recv.view(world, row).unbind(0)) if rank == 0 else None, dst=0)
     if rank != 0:
         return None
+    if on_gpu:
+        host = _buf(("host", on_gpu), world * row, pin=True)
+        host.copy_(recv)                       # one device -> pinned-host copy for all ranks (synchronises)
+    else:
+        host = recv
+    hv = host.numpy().reshape(world, row)
     full = np.zeros((Q, K), dtype=_lib.RESULT_DTYPE)
     full_n = np.zeros(Q, dtype=np.int32)
     full_s = np.zeros(Q, dtype=np.int32)
     for r in range(world):
         lo, hi = shard_range(Q, r, world)
-        b = gathered[r].cpu().numpy()
         m = hi - lo
-        full[lo:hi] = np.frombuffer(b[:m * K * rec].tobytes(), dtype=_lib.RESULT_DTYPE).reshape(m, K)
-        tl = b[cap * K * rec:]
-        full_n[lo:hi] = np.frombuffer(tl[:m * 4].tobytes(), dtype=np.int32)
-        full_s[lo:hi] = np.frombuffer(tl[cap * 4:cap * 4 + m * 4].tobytes(), dtype=np.int32)
+        full[lo:hi] = hv[r, :m * K * rec].view(_lib.RESULT_DTYPE).reshape(m, K)
+        full_n[lo:hi] = hv[r, cap * K * rec:cap * K * rec + m * 4].view(np.int32)
+        full_s[lo:hi] = hv[r, cap * K * rec + cap * 4:cap * K * rec + cap * 4 + m * 4].view(np.int32)
     return full, full_n, full_s
 
 

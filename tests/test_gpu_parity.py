@@ -116,7 +116,7 @@ def test_prefilter_scores_and_ranking_match_oracle(oracle_binding, name):
             assert a == b or abs(w[q][a] - w[q][b]) <= 1e-9 * abs(w[q][a]), (q, a, b)
 
 
-@pytest.mark.parametrize("name,kernel", [(n, k) for n in ("c1_gtr", "synth", "zero_cat") for k in (1, 2, 3, 4, 5, 6)])
+@pytest.mark.parametrize("name,kernel", [(n, k) for n in ("c1_gtr", "synth", "zero_cat") for k in (1, 2, 3, 4, 5, 6, 7)])
 def test_prefilter_kernel_variants_match_oracle(oracle_binding, name, kernel):
     """The direct FMA form (1: evolved-query table in the constant bank, 3: in shared memory), the
     four-base table form (2) and the staged forms (TMA bulk copies + mbarrier ring; 4: FMA, 5: FP64 tensor
@@ -125,7 +125,7 @@ def test_prefilter_kernel_variants_match_oracle(oracle_binding, name, kernel):
     _, _, st, info = o.place(prob.query_chars, oracle_prefs(oracle_binding, prob), n_threads=4, debug=True)
     want = info["scores"]
     got = p.prefilter_scores(prob.query_chars, kernel=kernel)
-    assert p.prefilter_kernel_used() == {1: 1, 2: 2, 3: 1, 4: 4, 5: 5, 6: 6}[kernel]
+    assert p.prefilter_kernel_used() == {1: 1, 2: 2, 3: 1, 4: 4, 5: 5, 6: 6, 7: 7}[kernel]
     root = prob.tree.root
     keep = [i for i in range(prob.tree.n_nodes) if i != root]
     g, w = got[:, keep], want[:, keep]
@@ -140,7 +140,7 @@ def test_prefilter_many_queries_matches_few_query_kernels(oracle_binding):
     q = prob.query_chars
     big = np.concatenate([q, q, q[:17]], axis=0)
     assert big.shape[0] > 64
-    for kernel in (0, 1, 2, 3, 4, 5, 6):
+    for kernel in (0, 1, 2, 3, 4, 5, 6, 7):
         a = p.prefilter_scores(q, kernel=kernel)
         b = p.prefilter_scores(big, kernel=kernel)
         for lo in (0, q.shape[0]):
@@ -422,9 +422,9 @@ def test_c2_prefilter_forms_agree(c2_small):
     keep = np.array([i for i in range(prob.tree.n_nodes) if i != prob.tree.root])
     assert np.isfinite(ref[:, keep]).all() and np.isnan(ref[:, prob.tree.root]).all()
     assert p.prefilter_kernel_used() == 1
-    for kernel in (0, 6, 4, 5):
+    for kernel in (0, 2, 6, 7, 4, 5):
         got = p.prefilter_scores(q, kernel=kernel)
-        assert p.prefilter_kernel_used() == (2 if kernel == 0 else kernel)
+        assert p.prefilter_kernel_used() == (7 if kernel == 0 else kernel)   # >= 256 queries: the query-lane log table is the default
         assert np.isnan(got[:, prob.tree.root]).all()
         d = np.abs(got[:, keep] - ref[:, keep])
         assert np.all(d <= 1e-11 * np.abs(ref[:, keep])), (kernel, float((d / np.abs(ref[:, keep])).max()))
