@@ -213,10 +213,15 @@ int pp_emper_freq(int32_t S, const uint8_t *chars, int64_t n, double *out);
  * the context's own stream).  Lets the host time the path with CUDA events on the launching stream. */
 int pp_set_stream(pp_ctx *, void *cuda_stream);
 
-/* Which prefilter kernel pp_place uses: 0 = default (the four-base table form for the DNA Gamma-4
- * model, the direct FMA form otherwise), 1 = direct FMA form (K = rates*states DFMAs per query x edge
- * x site: ten_masked_logdot_c / mat_masked_logdot_c as written, linear_c.c:465,251), 2 = table form.
- * pp_prefilter_kernel_used reports what the last prefilter launch ran (1 or 2). */
+/* Which prefilter kernel pp_place uses (all forms give ten_masked_logdot_c / mat_masked_logdot_c, linear_c.c:465,251):
+ * 0 = default: DNA Gamma-4 model - the query-lane log table (7) for batches of >= 256 queries, the four-base product
+ *     table (2) below that; every other model - the direct FMA form (1);
+ * 1 = direct FMA form (K = rates*states DFMAs per query x edge x site, as the reference writes it; the form the FP64
+ *     roofline is defined on), 3 = the same with the evolved-query table in shared memory;
+ * 2 = four-base product table; 6 = log table, lanes walk edges; 7 = log table, lanes are queries (TMA-streamed tiles);
+ * 4 = direct form staged through shared memory by TMA bulk copies + an mbarrier ring (DFMA), 5 = the same with the
+ *     K contraction on the FP64 tensor cores (DMMA m8n8k4).  2 and 4-7 exist for the DNA Gamma-4 model only.
+ * pp_prefilter_kernel_used reports what the last prefilter launch ran (1, 2, 4, 5, 6 or 7). */
 int pp_set_prefilter_kernel(pp_ctx *, int32_t kernel);
 int pp_prefilter_kernel_used(pp_ctx *);
 

@@ -115,6 +115,9 @@ struct pp_ctx {
   int prefilter_kernel_used = 0;  // 1 direct, 2 table (last run_prefilter)
   // workspace
   DevBuf<uint8_t> chars, codes, sort_tmp;
+  DevBuf<int32_t> qsite_cat, nqc, cat_perm, cat_start;  // Gcat: site lists in (category, site) order for three_tax_kernel (query.cuh)
+  bool cat_perm_ready = false;
+  int64_t LpC = 0;
   DevBuf<int32_t> qsite, nq, prep_status, rank_in, rank_loc, seg_off, i32pool, n_out;
   DevBuf<double> Tq, scores, keys_in, keys_out, wbuf, f64pool;
   DevBuf<CandIn> cand;
@@ -211,7 +214,7 @@ extern "C" void pp_destroy(pp_ctx *c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (int w = 0; w < 3; ++w) { if (c->g.a[w]) cudaFree(c->g.a[w]); if (c->g.e[w]) cudaFree(c->g.e[w]); }
-  c->qc.release(); c->partial.release(); c->MT.release(); c->LT.release(); c->LTq.release(); c->qcol.release(); c->slow_flag.release(); c->MTe.release();
+  c->qsite_cat.release(); c->nqc.release(); c->cat_perm.release(); c->cat_start.release(); c->qc.release(); c->partial.release(); c->MT.release(); c->LT.release(); c->LTq.release(); c->qcol.release(); c->slow_flag.release(); c->MTe.release();
   void *ptrs[] = {c->snT_a, c->snT_e, c->dm, c->d_bl, c->d_code_of_char, c->d_ref_codes, c->d_site_cat, c->d_child_ptr, c->d_child_idx, c->d_parent, c->d_leaf_row};
   for (void *p : ptrs) if (p) cudaFree(p);
   c->chars.release(); c->codes.release(); c->sort_tmp.release(); c->qsite.release(); c->nq.release();
@@ -405,7 +408,9 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
     static const int tte = [] { const char *e = std::getenv("PPB_TTE_VARIANT"); return e ? std::atoi(e) : 0; }();
     c->tte_variant = tte;
   }
-  if ((rc = c->wbuf.ensure(w_slots * c->K * c->Lp)) != PP_OK) { pp_destroy(c); return rc; }
+  // Gcat: per block w + the compact distal / proximal copies, rows of LpC = the padded (category, site) list capacity
+  c->LpC = c->gcat ? ((c->Lp + 32 * (int64_t)c->R + 31) / 32) * 32 : c->Lp;
+  if ((rc = c->wbuf.ensure(c->gcat ? w_slots * 3 * c->K * c->LpC : w_slots * c->K * c->Lp)) != PP_OK) { pp_destroy(c); return rc; }
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaGetLastError());
   *out = c;
@@ -502,6 +507,7 @@ extern "C" int pp_refine_site_categories(pp_ctx *c, int32_t *site_cat_out, doubl
     CK(cudaStreamSynchronize(c->stream));
     if (h_bad > 0) return fail(PP_EINVAL, "pp_refine_site_categories: a site has zero likelihood (gcat_model.ml:368-369)");
     c->precomputed = false;  // the GLVs on the device are those of the last attempt
+    c->cat_perm_ready = false;
     return PP_OK;
   };
   rc = body();
@@ -612,6 +618,24 @@ static int prep_queries(pp_ctx *c, int64_t Q, const uint8_t *d_chars) {
   query_prep_kernel<<<(unsigned)Q, kPrepThreads, 0, c->stream>>>(d_chars, c->d_code_of_char, c->L, c->Lp, c->codes.p, c->qsite.p,
                                                                   c->nq.p, c->prep_status.p, PP_Q_BAD_CHAR, PP_Q_NO_INFORMATIVE);
   LAUNCH_CHECK(c);
+  if (c->gcat) {  // the second stage walks the sites category by category
+    if (!c->cat_perm_ready) {
+      std::vector<int32_t> cat(c->L), perm(c->L), start(c->R + 1, 0);
+      CK(cudaMemcpyAsync(cat.data(), c->d_site_cat, sizeof(int32_t) * c->L, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      for (int i = 0; i < c->L; ++i) { perm[i] = i; start[cat[i] + 1]++; }
+      for (int r = 0; r < c->R; ++r) start[r + 1] += start[r];
+      std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return cat[a] < cat[b]; });
+      if ((rc = c->cat_perm.ensure(c->L)) || (rc = c->cat_start.ensure(c->R + 1))) return rc;
+      CK(cudaMemcpyAsync(c->cat_perm.p, perm.data(), sizeof(int32_t) * c->L, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpyAsync(c->cat_start.p, start.data(), sizeof(int32_t) * (c->R + 1), cudaMemcpyHostToDevice, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      c->cat_perm_ready = true;
+    }
+    if ((rc = c->qsite_cat.ensure((size_t)Q * c->LpC)) || (rc = c->nqc.ensure(Q))) return rc;
+    qsite_by_category_kernel<<<(unsigned)Q, kPrepThreads, 0, c->stream>>>(c->codes.p, c->cat_perm.p, c->cat_start.p, c->R, c->Lp, c->LpC,
+                                                                         c->qsite_cat.p, c->nqc.p); LAUNCH_CHECK(c);
+  }
   // tile order of the prefilter: by the window of sites each query covers (library sort of Q keys: plumbing)
   if ((rc = c->win_keys.ensure(Q)) || (rc = c->win_keys2.ensure(Q)) || (rc = c->win_vals.ensure(Q)) || (rc = c->qorder.ensure(Q))) return rc;
   window_keys_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, c->stream>>>(c->qsite.p, c->nq.p, (int)Q, c->Lp, c->win_keys.p, c->win_vals.p); LAUNCH_CHECK(c);
@@ -989,8 +1013,8 @@ static int launch_three_tax(pp_ctx *c, const CandIn *in, CandOut *out, int n, co
   const int blocks = std::min(c->tt_blocks, n);
   DISPATCH_MODEL(c, {
     constexpr int TH = (S_ == 4) ? kTTThreadsDNA : kTTThreadsAA;
-    three_tax_kernel<S_, G_, TH><<<blocks, TH, c->tt_smem, c->stream>>>(c->dm, c->g, c->d_bl, c->d_site_cat, c->codes.p, c->qsite.p,
-                                                                        c->nq.p, in, out, n, prm, c->wbuf.p, c->counters.p);
+    three_tax_kernel<S_, G_, TH><<<blocks, TH, c->tt_smem, c->stream>>>(c->dm, c->g, c->d_bl, c->d_site_cat, c->codes.p, G_ ? c->qsite_cat.p : c->qsite.p,
+                                                                        c->nq.p, in, out, n, prm, c->wbuf.p, c->counters.p, c->nqc.p, c->LpC);
     LAUNCH_CHECK(c);
   });
   return PP_OK;

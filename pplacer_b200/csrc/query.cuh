@@ -57,6 +57,54 @@ query_prep_kernel(const uint8_t *__restrict__ chars, const uint8_t *__restrict__
   }
 }
 
+// Price-CAT models, second stage (three_tax_kernel): the query's informative sites ordered by (site category, site),
+// each category's segment padded with -1 to a multiple of 32, so that the 32 lanes of a warp always share the
+// category - the per-category rate matrices in shared memory are then read with broadcast loads (threetax.cuh).
+// perm = the alignment's sites in (category, site) order, cat_start[R + 1] = the segment bounds in perm (host-built
+// per category assignment).  Entries as in query_prep_kernel (site | code << 24); nqc[q] = padded length.
+__global__ void __launch_bounds__(kPrepThreads)
+qsite_by_category_kernel(const uint8_t *__restrict__ codes, const int32_t *__restrict__ perm, const int32_t *__restrict__ cat_start,
+                         int R, int Lp, int64_t LpC, int32_t *__restrict__ qsite_cat, int32_t *__restrict__ nqc) {
+  __shared__ int warp_tot[kPrepThreads / 32];
+  __shared__ int base_s;
+  const int64_t q = blockIdx.x;
+  const uint8_t *crow = codes + q * Lp;
+  int32_t *srow = qsite_cat + q * LpC;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = 0; c < R; ++c) {
+    const int j0 = cat_start[c], j1 = cat_start[c + 1];
+    for (int start = j0; start < j1; start += kPrepThreads) {
+      const int j = start + threadIdx.x;
+      int site = 0;
+      uint8_t code = 0xFF;
+      if (j < j1) { site = __ldg(perm + j); code = crow[site]; }
+      const bool inf = !(code & 0x80);
+      const unsigned bal = __ballot_sync(0xffffffffu, inf);
+      const int within = __popc(bal & ((1u << lane) - 1u));
+      if (lane == 0) warp_tot[warp] = __popc(bal);
+      __syncthreads();
+      int off = base_s;
+      for (int w = 0; w < warp; ++w) off += warp_tot[w];
+      if (inf) srow[off + within] = site | ((int)code << kSiteCodeShift);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < kPrepThreads / 32; ++w) t += warp_tot[w];
+        base_s += t;
+      }
+      __syncthreads();
+    }
+    const int end = base_s, padded = (end + 31) & ~31;
+    if (threadIdx.x < padded - end) srow[end + threadIdx.x] = -1;
+    __syncthreads();
+    if (threadIdx.x == 0) base_s = padded;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) nqc[q] = base_s;
+}
+
 // Evolved-query table for pendant length t: the reference evolves the full-length query GLV
 // (core.ml:137-141); an evolved indicator vector is a sum of columns of P_r(t), so it only depends
 // on the character:  Tq[(cat,) code][r*S+s] = sum_{j in states(code)} P_r(t)[s][j]  (j ascending,

@@ -534,14 +534,31 @@ struct TTMachine {
 
 };
 
+extern __shared__ double ppb_tt1_smem[];  // the general block engine's dynamic shared memory (ThreeTax)
+
 template <int S, bool GCAT, int THREADS>
 struct ThreeTax : TTDriver<ThreeTax<S, GCAT, THREADS>> {
   using Base = TTDriver<ThreeTax<S, GCAT, THREADS>>;
   using Base::pend_bl; using Base::dist_bl; using Base::prox_bl; using Base::calls;
-  static constexpr int RS = p_rstride<S, GCAT>();
+  static constexpr int RS = GCAT ? S * S : p_rstride<S, GCAT>();  // Gcat: a warp reads ONE category's matrix (broadcast, 16-byte rows): no padding
   // ---- shared memory views ----
-  double *statd, *lam, *x, *xit, *rates, *ex, *Pd, *Pp, *Pq, *Tp, *red;
-  uint32_t *mask_of_code;
+  // Offsets into the block's dynamic shared memory, turned into pointers by the accessors below: the object itself
+  // lives in local memory (its address goes to the non-inlined driver), and pointers loaded from there are GENERIC -
+  // every read of a rate matrix was an LD through the local/global path (ncu r5e: long_scoreboard / lg_throttle on
+  // them).  Derived from the __shared__ symbol they are LDS.
+  int o_statd, o_lam, o_x, o_xit, o_rates, o_ex, o_Pd, o_Pp, o_Pq, o_Tp, o_red, o_moc;
+  __device__ __forceinline__ double *statd() const { return ppb_tt1_smem + o_statd; }
+  __device__ __forceinline__ double *lam() const { return ppb_tt1_smem + o_lam; }
+  __device__ __forceinline__ double *x() const { return ppb_tt1_smem + o_x; }
+  __device__ __forceinline__ double *xit() const { return ppb_tt1_smem + o_xit; }
+  __device__ __forceinline__ double *rates() const { return ppb_tt1_smem + o_rates; }
+  __device__ __forceinline__ double *ex() const { return ppb_tt1_smem + o_ex; }
+  __device__ __forceinline__ double *Pd() const { return ppb_tt1_smem + o_Pd; }
+  __device__ __forceinline__ double *Pp() const { return ppb_tt1_smem + o_Pp; }
+  __device__ __forceinline__ double *Pq() const { return ppb_tt1_smem + o_Pq; }
+  __device__ __forceinline__ double *Tp() const { return ppb_tt1_smem + o_Tp; }
+  __device__ __forceinline__ double *red() const { return ppb_tt1_smem + o_red; }
+  __device__ __forceinline__ uint32_t *mask_of_code() const { return reinterpret_cast<uint32_t *>(ppb_tt1_smem + o_moc); }
   // ---- block-uniform state ----
   GlvArrays g;
   int R, Rt, Rg, K, nc;
@@ -551,12 +568,17 @@ struct ThreeTax : TTDriver<ThreeTax<S, GCAT, THREADS>> {
   double *w;
   int64_t wstride;
   int nq, loc;
+  // Gcat: the candidate's distal / proximal vectors gathered ONCE at the query's sites in (category, site) order,
+  // each category's segment padded to a multiple of 32 (query.cuh: qsite_by_category_kernel), cd/cp[s][i]
+  double *cd, *cp;
+  int nqc;
   double e_tot_ln2, rate_term;
 
   static __host__ __device__ size_t smem_doubles(int Rt, int nc) {
     size_t n = 0;
     n += S + S + 2 * S * S + Rt;              // statd lam x xit rates
     n += (size_t)Rt * S;                      // ex
+    n += 1;                                   // Pd starts on a 16-byte boundary (Gcat rows are read as double2)
     n += 2 * (size_t)Rt * RS;                 // Pd Pp
     n += (size_t)Rt * RS;                     // Pq (Gcat pendant tensor / Gmix scratch)
     n += GCAT ? 0 : (size_t)nc * Rt * S;      // Tp
@@ -567,33 +589,37 @@ struct ThreeTax : TTDriver<ThreeTax<S, GCAT, THREADS>> {
 
   __device__ void carve(double *sm, const DevModel *m) {
     R = m->R; Rt = m->R; Rg = GCAT ? 1 : m->R; K = Rg * S; nc = m->n_codes;
-    double *p = sm;
-    statd = p; p += S; lam = p; p += S; x = p; p += S * S; xit = p; p += S * S; rates = p; p += Rt;
-    ex = p; p += Rt * S;
-    Pd = p; p += Rt * RS; Pp = p; p += Rt * RS; Pq = p; p += Rt * RS;
-    Tp = p; p += GCAT ? 0 : nc * Rt * S;
-    red = p; p += 40;
-    mask_of_code = reinterpret_cast<uint32_t *>(p);
-    for (int i = threadIdx.x; i < S; i += THREADS) { statd[i] = m->statd[i]; lam[i] = m->lam[i]; }
-    for (int i = threadIdx.x; i < S * S; i += THREADS) { x[i] = m->x[i]; xit[i] = m->xit[i]; }
-    for (int i = threadIdx.x; i < Rt; i += THREADS) rates[i] = m->rates[i];
-    for (int i = threadIdx.x; i < kMaxCodesDev; i += THREADS) mask_of_code[i] = m->mask_of_code[i];
+    int o = 0;
+    o_statd = o; o += S; o_lam = o; o += S; o_x = o; o += S * S; o_xit = o; o += S * S; o_rates = o; o += Rt;
+    o_ex = o; o += Rt * S;
+    if (o & 1) ++o;
+    o_Pd = o; o += Rt * RS; o_Pp = o; o += Rt * RS; o_Pq = o; o += Rt * RS;
+    o_Tp = o; o += GCAT ? 0 : nc * Rt * S;
+    o_red = o; o += 40;
+    o_moc = o;
+    (void)sm;
+    for (int i = threadIdx.x; i < S; i += THREADS) { statd()[i] = m->statd[i]; lam()[i] = m->lam[i]; }
+    // xit is kept TRANSPOSED (xitT[k][j] = xit[j][k]): build_P's lanes walk j, so they read consecutive words
+    for (int i = threadIdx.x; i < S * S; i += THREADS) { x()[i] = m->x[i]; xit()[(i % S) * S + i / S] = m->xit[i]; }
+    for (int i = threadIdx.x; i < Rt; i += THREADS) rates()[i] = m->rates[i];
+    for (int i = threadIdx.x; i < kMaxCodesDev; i += THREADS) mask_of_code()[i] = m->mask_of_code[i];
     __syncthreads();
   }
 
   // Diagd.multi_exp for all Rt rates into dst (diagd.ml:79-98; linear_c.c:92-146)
-  __device__ __noinline__ void build_P(double *dst, double bl) {
+  __device__ __noinline__ void build_P(int o_dst, double bl) {
+    double *dst = ppb_tt1_smem + o_dst;
     __syncthreads();
     for (int t = threadIdx.x; t < Rt * S; t += THREADS) {
       const int r = t / S, k = t - r * S;
-      ex[t] = exp(rates[r] * bl * lam[k]);
+      ex()[t] = exp(rates()[r] * bl * lam()[k]);
     }
     __syncthreads();
     for (int t = threadIdx.x; t < Rt * S * S; t += THREADS) {
       const int r = t / (S * S), ij = t - r * S * S, i = ij / S, j = ij - i * S;
       double acc = 0.0;
 #pragma unroll
-      for (int k = 0; k < S; ++k) acc = fma(ex[r * S + k] * x[i * S + k], xit[j * S + k], acc);
+      for (int k = 0; k < S; ++k) acc = fma(ex()[r * S + k] * x()[i * S + k], xit()[k * S + j], acc);
       dst[r * RS + ij] = acc;
     }
     __syncthreads();
@@ -602,28 +628,28 @@ struct ThreeTax : TTDriver<ThreeTax<S, GCAT, THREADS>> {
   // evolved pendant GLV as a table (Gmix) or tensor (Gcat): Glv_edge.set_bl on pend (core.ml:234)
   __device__ __noinline__ void set_pend(double bl) {
     pend_bl = bl;
-    build_P(Pq, bl);
+    build_P(o_Pq, bl);
     if (!GCAT) {
       for (int idx = threadIdx.x; idx < nc * Rt * S; idx += THREADS) {
         const int code = idx / (Rt * S), rs = idx - code * (Rt * S), r = rs / S, s = rs - r * S;
-        uint32_t mask = mask_of_code[code];
+        uint32_t mask = mask_of_code()[code];
         double acc = 0.0;
-        while (mask) { const int j = __ffs(mask) - 1; mask &= mask - 1; acc += Pq[r * RS + s * S + j]; }
-        Tp[idx] = acc;
+        while (mask) { const int j = __ffs(mask) - 1; mask &= mask - 1; acc += Pq()[r * RS + s * S + j]; }
+        Tp()[idx] = acc;
       }
       __syncthreads();
     }
   }
   __device__ void set_dist_prox(double d, double p) {
     dist_bl = d; prox_bl = p;
-    build_P(Pd, d);
-    build_P(Pp, p);
+    build_P(o_Pd, d);
+    build_P(o_Pp, p);
   }
 
   __device__ __forceinline__ double pend_val(int cat, int code, int r, int s) const {
-    if (!GCAT) return Tp[code * (Rt * S) + r * S + s];
-    uint32_t mask = mask_of_code[code];
-    const double *row = Pq + cat * RS + s * S;
+    if (!GCAT) return Tp()[code * (Rt * S) + r * S + s];
+    uint32_t mask = mask_of_code()[code];
+    const double *row = Pq() + cat * RS + s * S;
     if ((mask & (mask - 1)) == 0) return row[__ffs(mask) - 1];
     double acc = 0.0;
     while (mask) { const int j = __ffs(mask) - 1; mask &= mask - 1; acc += row[j]; }
@@ -632,8 +658,49 @@ struct ThreeTax : TTDriver<ThreeTax<S, GCAT, THREADS>> {
 
   // Three_tax.log_like over all of the query's sites with the current P matrices; optionally
   // caches w[k][i] = (statd_s * prox_ev) * dist_ev for the pendant-only evaluations.
+  // Gcat: lanes of a warp share the site category, so the category's matrix rows are broadcast LDS.128 loads (the
+  // general loop below reads a different matrix per lane: one 8-byte shared-memory word per lane and FMA, bound by
+  // shared-memory bandwidth - r5a: 304 ms for 256 ar53 genomes); d / p come coalesced from the compact copies.
+  template <bool WRITE_W>
+  __device__ __forceinline__ double eval_full_gcat() {
+    LogProd lp;
+    lp.init();
+    for (int i = threadIdx.x; i < nqc; i += THREADS) {
+      const int pk = __ldg(qsite + i);
+      const bool valid = pk >= 0;
+      const int pk0 = __shfl_sync(0xffffffffu, pk, 0);  // a segment starts at a multiple of 32 with a real site
+      const int cat = site_cat[pk0 & kSiteMask];
+      const int code = (pk >> kSiteCodeShift) & 0x7f;
+      double d[S], p[S];
+#pragma unroll
+      for (int j = 0; j < S; ++j) { d[j] = __ldcg(cd + (int64_t)j * wstride + i); p[j] = __ldcg(cp + (int64_t)j * wstride + i); }
+      const double *Prd = Pd() + cat * RS, *Prp = Pp() + cat * RS;
+      const uint32_t mask = valid ? mask_of_code()[code] : 1u;
+      const bool single = __all_sync(0xffffffffu, (mask & (mask - 1)) == 0);
+      const double *col = Pq() + cat * RS + (__ffs(mask) - 1);
+      double u = 0.0;
+#pragma unroll 2
+      for (int s = 0; s < S; ++s) {
+        const double2 *rd = reinterpret_cast<const double2 *>(Prd + s * S), *rp = reinterpret_cast<const double2 *>(Prp + s * S);
+        double de0 = 0.0, de1 = 0.0, pe0 = 0.0, pe1 = 0.0;
+#pragma unroll
+        for (int j2 = 0; j2 < S / 2; ++j2) {
+          const double2 a = rd[j2], b = rp[j2];
+          de0 = fma(a.x, d[2 * j2], de0); de1 = fma(a.y, d[2 * j2 + 1], de1);
+          pe0 = fma(b.x, p[2 * j2], pe0); pe1 = fma(b.y, p[2 * j2 + 1], pe1);
+        }
+        const double ww = (statd()[s] * (pe0 + pe1)) * (de0 + de1);  // ((statd*x)*y) with x = prox, y = dist (three_tax.ml:31-36)
+        if (WRITE_W) w[(int64_t)s * wstride + i] = ww;
+        u = fma(ww, single ? col[s * S] : (valid ? pend_val(cat, code, 0, s) : 0.0), u);
+      }
+      if (valid) lp.mul(u);
+    }
+    return block_sum<THREADS>(lp.value(), red()) - rate_term + e_tot_ln2;
+  }
+
   template <bool WRITE_W>
   __device__ __forceinline__ double eval_full_impl() {
+    if (GCAT) return eval_full_gcat<WRITE_W>();
     LogProd lp;
     lp.init();
     const int64_t Lp = g.Lp;
@@ -645,7 +712,7 @@ struct ThreeTax : TTDriver<ThreeTax<S, GCAT, THREADS>> {
       const int cat = GCAT ? site_cat[site] : 0;
       double u = 0.0;
       for (int r = 0; r < Rg; ++r) {
-        const double *Prd = Pd + (GCAT ? cat : r) * RS, *Prp = Pp + (GCAT ? cat : r) * RS;
+        const double *Prd = Pd() + (GCAT ? cat : r) * RS, *Prp = Pp() + (GCAT ? cat : r) * RS;
         double d[S], p[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
@@ -657,14 +724,14 @@ struct ThreeTax : TTDriver<ThreeTax<S, GCAT, THREADS>> {
           double de = 0.0, pe = 0.0;
 #pragma unroll
           for (int j = 0; j < S; ++j) { de = fma(Prd[s * S + j], d[j], de); pe = fma(Prp[s * S + j], p[j], pe); }
-          const double ww = (statd[s] * pe) * de;  // ((statd*x)*y) with x = prox, y = dist (three_tax.ml:31-36)
+          const double ww = (statd()[s] * pe) * de;  // ((statd*x)*y) with x = prox, y = dist (three_tax.ml:31-36)
           if (WRITE_W) w[(int64_t)(r * S + s) * wstride + i] = ww;
           u = fma(ww, pend_val(cat, code, r, s), u);
         }
       }
       lp.mul(u);
     }
-    return block_sum<THREADS>(lp.value(), red) - rate_term + e_tot_ln2;
+    return block_sum<THREADS>(lp.value(), red()) - rate_term + e_tot_ln2;
   }
   __device__ __noinline__ double eval_full_cache() { return eval_full_impl<true>(); }
   __device__ __noinline__ double eval_full_plain() { return eval_full_impl<false>(); }
@@ -674,6 +741,54 @@ struct ThreeTax : TTDriver<ThreeTax<S, GCAT, THREADS>> {
   __device__ __noinline__ double eval_pend_cached() {
     LogProd lp;
     lp.init();
+    if (GCAT) {
+      // A thread takes PAIRS of adjacent list entries (16-byte loads: twice the bytes per load instruction in flight),
+      // TP pairs per trip, and requests all its S * TP loads of w before anything depends on them.  ncu r5e / r5g: this
+      // pass is bound by memory latency (63 % of the kernel's samples wait here at 8 % of the DRAM bandwidth).
+      // Lanes 0-15 of a warp cover one 32-entry group of the list, lanes 16-31 the next: the category is uniform per half-warp.
+      constexpr int TP = 2;
+      const int lane = threadIdx.x & 31;
+      const int npair = nqc >> 1;
+      for (int j0 = threadIdx.x; j0 < npair; j0 += TP * THREADS) {
+        double2 wv[TP][S];
+        int2 pk[TP];
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+          const int j = j0 + t * THREADS;
+          const bool in = j < npair;  // uniform per half-warp (nqc is a multiple of 32)
+          pk[t] = in ? __ldg(reinterpret_cast<const int2 *>(qsite) + j) : make_int2(-1, -1);
+#pragma unroll
+          for (int s = 0; s < S; ++s)
+            wv[t][s] = in ? __ldcg(reinterpret_cast<const double2 *>(w + (int64_t)s * wstride) + j) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+          const int pk0 = __shfl_sync(0xffffffffu, pk[t].x, lane & 16);  // a group starts with a real site
+          const int cat = pk0 >= 0 ? site_cat[pk0 & kSiteMask] : 0;
+          const bool va = pk[t].x >= 0, vb = pk[t].y >= 0;
+          const int ca = (pk[t].x >> kSiteCodeShift) & 0x7f, cb = (pk[t].y >> kSiteCodeShift) & 0x7f;
+          const uint32_t ma = va ? mask_of_code()[ca] : 1u, mb = vb ? mask_of_code()[cb] : 1u;
+          double ua0 = 0.0, ua1 = 0.0, ub0 = 0.0, ub1 = 0.0;
+          if (__all_sync(0xffffffffu, ((ma & (ma - 1)) | (mb & (mb - 1))) == 0)) {  // one state per site (the rule): columns of P_cat(pend)
+            const double *cola = Pq() + cat * RS + (__ffs(ma) - 1), *colb = Pq() + cat * RS + (__ffs(mb) - 1);
+#pragma unroll
+            for (int s = 0; s < S; s += 2) {
+              ua0 = fma(wv[t][s].x, cola[s * S], ua0); ua1 = fma(wv[t][s + 1].x, cola[(s + 1) * S], ua1);
+              ub0 = fma(wv[t][s].y, colb[s * S], ub0); ub1 = fma(wv[t][s + 1].y, colb[(s + 1) * S], ub1);
+            }
+          } else {
+#pragma unroll  // static indices: wv must stay in registers
+            for (int s = 0; s < S; ++s) {
+              ua0 = fma(wv[t][s].x, va ? pend_val(cat, ca, 0, s) : 0.0, ua0);
+              ub0 = fma(wv[t][s].y, vb ? pend_val(cat, cb, 0, s) : 0.0, ub0);
+            }
+          }
+          if (va) lp.mul(ua0 + ua1);
+          if (vb) lp.mul(ub0 + ub1);
+        }
+      }
+      return block_sum<THREADS>(lp.value(), red()) - rate_term + e_tot_ln2;
+    }
     for (int i = threadIdx.x; i < nq; i += THREADS) {
       const int site = qsite[i] & kSiteMask;
       const int code = qcode[site] & 0x7f;
@@ -684,18 +799,33 @@ struct ThreeTax : TTDriver<ThreeTax<S, GCAT, THREADS>> {
         for (int s = 0; s < S; ++s) u = fma(w[(int64_t)(r * S + s) * wstride + i], pend_val(cat, code, r, s), u);
       lp.mul(u);
     }
-    return block_sum<THREADS>(lp.value(), red) - rate_term + e_tot_ln2;
+    return block_sum<THREADS>(lp.value(), red()) - rate_term + e_tot_ln2;
   }
 
   // core.ml:225-239 set_tt_edges (without the gather): fix the candidate and its branch lengths
   __device__ void set_tt_edges(int loc_, double cut_bl, double pendant, double distal) {
     loc = loc_;
     long long es = 0;
+    if (GCAT) {
+      // one scattered pass over the candidate's planes; every later pass reads the compact copies coalesced
+      const double *dbase = g.a[0] + (int64_t)loc * g.a_stride, *pbase = g.a[1] + (int64_t)loc * g.a_stride;
+      __syncthreads();  // the previous candidate's passes are done with cd / cp
+      for (int i = threadIdx.x; i < nqc; i += THREADS) {
+        const int pk = __ldg(qsite + i);
+        const int site = pk & kSiteMask;
+        if (pk >= 0) es += (long long)g.e[0][(int64_t)loc * g.Lp + site] + (long long)g.e[1][(int64_t)loc * g.Lp + site];
+#pragma unroll 4
+        for (int j = 0; j < S; ++j) {
+          cd[(int64_t)j * wstride + i] = pk >= 0 ? __ldg(dbase + (int64_t)j * g.Lp + site) : 0.0;
+          cp[(int64_t)j * wstride + i] = pk >= 0 ? __ldg(pbase + (int64_t)j * g.Lp + site) : 0.0;
+        }
+      }
+    } else
     for (int i = threadIdx.x; i < nq; i += THREADS) {
       const int site = qsite[i] & kSiteMask;
       es += (long long)g.e[0][(int64_t)loc * g.Lp + site] + (long long)g.e[1][(int64_t)loc * g.Lp + site];
     }
-    es = block_sum_ll<THREADS>(es, reinterpret_cast<long long *>(red));
+    es = block_sum_ll<THREADS>(es, reinterpret_cast<long long *>(red()));
     e_tot_ln2 = kLn2 * (double)es;  // ln2 * (total_twoexp prox + total_twoexp dist), gstar_support.ml:43-49
     rate_term = GCAT ? 0.0 : (double)((float)nq) * log((double)((float)R));  // linear_c.c:421
     set_pend(pendant);
@@ -718,15 +848,19 @@ __global__ void __launch_bounds__(THREADS)
 three_tax_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__restrict__ bl,
                  const int32_t *__restrict__ site_cat, const uint8_t *__restrict__ codes,
                  const int32_t *__restrict__ qsite, const int32_t *__restrict__ nq, const CandIn *__restrict__ in,
-                 CandOut *__restrict__ out, int n, TTParams prm, double *__restrict__ wbuf, int *counter) {
-  extern __shared__ double sm[];
+                 CandOut *__restrict__ out, int n, TTParams prm, double *__restrict__ wbuf, int *counter,
+                 const int32_t *__restrict__ nqc, int64_t LpC) {
+  // Gcat: qsite = the (category, site)-ordered padded lists [Q][LpC], nqc = their padded lengths; wbuf holds w, cd, cp per block
+  double *sm = ppb_tt1_smem;
   __shared__ int s_idx;
   ThreeTax<S, GCAT, THREADS> tt;
   tt.g = g;
   tt.carve(sm, m);
   tt.site_cat = site_cat;
-  tt.wstride = g.Lp;
-  tt.w = wbuf + (int64_t)blockIdx.x * tt.K * g.Lp;
+  tt.wstride = GCAT ? LpC : g.Lp;
+  tt.w = wbuf + (int64_t)blockIdx.x * tt.K * tt.wstride * (GCAT ? 3 : 1);
+  tt.cd = tt.w + (int64_t)tt.K * tt.wstride;
+  tt.cp = tt.cd + (int64_t)tt.K * tt.wstride;
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) s_idx = atomicAdd(counter, 1);
@@ -734,9 +868,10 @@ three_tax_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__re
     const int idx = s_idx;
     if (idx >= n) break;
     const CandIn c = in[idx];
-    tt.qsite = qsite + (int64_t)c.q * g.Lp;
+    tt.qsite = qsite + (int64_t)c.q * (GCAT ? LpC : g.Lp);
     tt.qcode = codes + (int64_t)c.q * g.Lp;
     tt.nq = nq[c.q];
+    tt.nqc = GCAT ? nqc[c.q] : 0;
     tt.calls = 0;
     const double cut_bl = bl[c.loc];
     CandOut o;

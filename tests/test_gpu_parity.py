@@ -396,11 +396,15 @@ def test_c4_shape_matches_oracle(oracle_binding):
         assert p.rank_fallbacks() == 0
         direct = p.prefilter_scores(prob.query_chars[:8], kernel=1)
         staged = [p.prefilter_scores(prob.query_chars[:8], kernel=k) for k in (6, 4, 5)]
+        qlane = p.prefilter_scores(prob.query_chars, kernel=7)   # the form large batches use (313 edge tiles, 720 MB table)
+        assert p.prefilter_kernel_used() == 7
     root = prob.tree.root
     keep = np.array([i for i in range(prob.tree.n_nodes) if i != root])
     g, w = gi["scores"][:, keep], oi["scores"][:, keep]
     assert np.isfinite(w).all()
     assert np.all(np.abs(g - w) <= 1e-10 * np.abs(w)), np.abs((g - w) / w).max()
+    assert np.isnan(qlane[:, root]).all()
+    assert np.all(np.abs(qlane[:, keep] - w) <= 1e-10 * np.abs(w)), np.abs((qlane[:, keep] - w) / w).max()
     for d in [direct] + staged:
         d = d[:, keep]
         assert np.all(np.abs(d - w[:8]) <= 1e-10 * np.abs(w[:8])), np.abs((d - w[:8]) / w[:8]).max()
