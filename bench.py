@@ -384,7 +384,7 @@ def run_ours(args):
     kname = {1: "prefilter_direct_kernel", 2: "prefilter_table_kernel", 4: "prefilter_staged_kernel<MMA=false>", 5: "prefilter_staged_kernel<MMA=true>", 6: "prefilter_logtable_kernel", 7: "prefilter_qlane_kernel"}.get(used, "?")
     # compulsory HBM bytes: one pass over the prefilter copy of the supernodes + query codes + scores
     pre_bytes = (8.0 * (4 if used == 2 else R * S) + 4.0) * p.L * (E + 1) + Q * p.L + 8.0 * Q * (E + 1)
-    if args.workload == "c3":
+    if args.workload == "c3" and used == 1:
         kname = "prefilter_direct_kernel<S=20, Gcat>"
     roofline_prefilter = {
         "kernel": kname, "bound": "fp64", "achieved": pre_tflops, "peak": fp64_peak,
@@ -426,9 +426,11 @@ def run_ours(args):
             "note": "query-lane log-table form (prefilter_qlane.cuh): lane = query, warp = 32 queries x 32 edges, table tile streamed by TMA bulk copies; "
                     "no FP64 fraction is claimed for it; roofline.prefilter_direct carries the FMA form the FP64 roofline is defined on",
         })
-        roofline_prefilter["hbm"]["bytes_per_launch"] = 48.0 * p.L * (E + 1) + Q * p.L + 8.0 * Q * (E + 1)
+        ncols = 6 if S == 4 else S + 2
+        roofline_prefilter["kernel"] = "prefilter_qlane_kernel" if S == 4 else "prefilter_qlane_kernel<NC=%d>" % ncols
+        roofline_prefilter["hbm"]["bytes_per_launch"] = 8.0 * ncols * p.L * (E + 1) + Q * p.L + 8.0 * Q * (E + 1)
         roofline_prefilter["hbm"]["achieved"] = roofline_prefilter["hbm"]["bytes_per_launch"] / (pre_ms * 1e-3) / 1e9 if pre_ms > 0 else 0.0
-        roofline_prefilter["hbm"]["note"] = "compulsory bytes: one pass over the six-column log table + query codes + scores"
+        roofline_prefilter["hbm"]["note"] = "compulsory bytes: one pass over the log table (6 columns DNA, 22 columns proteins) + query codes + scores"
     # the graded prefilter form: K = R*S DFMAs per unit exactly as ten_masked_logdot_c writes them (linear_c.c:465),
     # timed on the same batch outside the step loop (pp_prefilter_time: CUDA events on the launching stream)
     roofline_direct = None
@@ -484,13 +486,13 @@ def run_ours(args):
             tr = json.load(fh).get(args.workload, {})
         if roofline_prefilter["kernel"] in tr:
             roofline_prefilter["traffic"] = tr[roofline_prefilter["kernel"]]["dram_bytes"]
-            roofline_prefilter["traffic_note"] = "dram bytes per launch, ncu capture r2f (profiles/traffic.json)"
+            roofline_prefilter["traffic_note"] = "dram bytes per launch, ncu capture %s (profiles/traffic.json)" % tr[roofline_prefilter["kernel"]].get("capture", "r2f")
         if roofline_tt["kernel"] in tr and Q == 10_000:
             roofline_tt["traffic"] = tr[roofline_tt["kernel"]]["dram_bytes"]
-            roofline_tt["traffic_note"] = "dram bytes per step (all second-stage launches), ncu capture r2f (profiles/traffic.json)"
+            roofline_tt["traffic_note"] = "dram bytes per step (all second-stage launches), ncu capture %s (profiles/traffic.json)" % tr[roofline_tt["kernel"]].get("capture", "r2f")
     except Exception:
         pass
-    if args.workload == "c3":
+    if args.workload == "c3" and used == 1:
         # few queries against 17.9 GB of supernodes: the prefilter is bound by HBM - report it on that roof
         hb = roofline_prefilter["hbm"]
         n_rows = (Q + 63) // 64   # the supernodes stream once per 64-query block row (8 queries per warp x 8 warps)

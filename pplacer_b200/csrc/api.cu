@@ -149,14 +149,14 @@ struct pp_ctx {
   // figs (fig.cuh): host CSR, device copies, the representatives' supernode columns in prefilter layout
   std::vector<int32_t> fig_rep, fig_ptr, fig_idx;
   DevBuf<int32_t> d_fig_rep, d_fig_ptr, d_fig_idx, rep_e, fig_order, fig_i32, fig_pair_q, fig_pair_e, fig_pair_e2, fig_seg;
-  DevBuf<double> rep_a, rep_scores, rep_MT, rep_LT;
+  DevBuf<double> rep_a, rep_scores, rep_MT, rep_LT, rep_LTq;
   DevBuf<int32_t> rep_MTe;
   DevBuf<uint32_t> fig_bits;
   DevBuf<unsigned long long> fig_keys, fig_keys2;
   DevBuf<uint8_t> fig_tmp;
   int64_t rep_Np = 0;
   bool rep_ready = false;
-  double rep_mt_pend = -1.0, rep_lt_pend = -1.0;
+  double rep_mt_pend = -1.0, rep_lt_pend = -1.0, rep_ltq_pend = -1.0;
   // prefilter tiling: queries sorted by the window of sites they cover (prefilter.cuh window_keys_kernel)
   DevBuf<unsigned long long> win_keys, win_keys2;
   DevBuf<int32_t> win_vals, qorder, tile_lo, tile_hi;
@@ -223,7 +223,7 @@ extern "C" void pp_destroy(pp_ctx *c) {
   c->ord_keys.release(); c->ord_vals.release(); c->ord_keys2.release(); c->ord_vals2.release(); c->ord_tmp.release();
   c->d_fig_rep.release(); c->d_fig_ptr.release(); c->d_fig_idx.release(); c->rep_e.release(); c->fig_order.release(); c->fig_i32.release();
   c->fig_pair_q.release(); c->fig_pair_e.release(); c->fig_pair_e2.release(); c->fig_seg.release(); c->rep_a.release(); c->rep_scores.release();
-  c->rep_MT.release(); c->rep_LT.release(); c->rep_MTe.release(); c->fig_bits.release(); c->fig_keys.release(); c->fig_keys2.release(); c->fig_tmp.release();
+  c->rep_MT.release(); c->rep_LT.release(); c->rep_LTq.release(); c->rep_MTe.release(); c->fig_bits.release(); c->fig_keys.release(); c->fig_keys2.release(); c->fig_tmp.release();
   c->win_keys.release(); c->win_keys2.release(); c->win_vals.release(); c->qorder.release(); c->tile_lo.release(); c->tile_hi.release(); c->win_tmp.release();
   c->wbuf.release(); c->f64pool.release(); c->cand.release(); c->cand_out.release(); c->pp_out.release();
   c->place_out.release(); c->n_calls.release(); c->counters.release(); c->tt_work.release();
@@ -572,7 +572,7 @@ extern "C" int pp_precompute(pp_ctx *c) {
     dim3 grid_e((c->L + 31) / 32, (unsigned)(c->Np / 32), 1);
     transpose_to_edge_major_kernel<int32_t><<<grid_e, 256, 0, c->stream>>>(c->g.e[2], c->snT_e, c->n_nodes, 1, c->L, c->Lp, c->Np, 0); LAUNCH_CHECK(c);
     c->tq_pend = c->mt_pend = c->lt_pend = c->ltq_pend = -1.0;
-    c->rep_ready = false; c->rep_mt_pend = c->rep_lt_pend = -1.0;
+    c->rep_ready = false; c->rep_mt_pend = c->rep_lt_pend = c->rep_ltq_pend = -1.0;
   }
   cudaError_t e = cudaStreamSynchronize(c->stream);
   cudaFree(Pfull); cudaFree(Phalf); cudaFree(d_levels);
@@ -814,6 +814,47 @@ static int launch_prefilter_qlane(pp_ctx *c, int64_t Q, double pend, int blocks_
   return PP_OK;
 }
 
+// the same form for the 20-state models (Gamma mixtures and Price-CAT): 22 columns (prefilter_qlane.cuh, second half)
+template <int S, bool G, int W, int SPS, int NS, int MINB>
+static int launch_prefilter_qlane_generic(pp_ctx *c, int64_t Q, double pend, int blocks_per_sm) {
+  int rc;
+  constexpr int NC = S + 2;
+  using Geo = QlaneGeom<W, SPS, NS, NC>;
+  QlColMap map;
+  std::memset(&map, 0, sizeof map);
+  for (int code = 0; code < kMaxCodesDev; ++code) {
+    const uint32_t m = code < c->al.n_codes ? c->al.mask_of_code[code] : 0u;
+    map.col[code] = 255;
+    if (m && !(m & (m - 1))) { int st = 0; while (!((m >> st) & 1u)) ++st; map.col[code] = (uint8_t)st; map.code_of_state[st] = (uint8_t)code; }
+  }
+  SnT sn; sn.a = c->snT_a; sn.e = c->snT_e; sn.Np = c->Np; sn.L = c->L; sn.K = c->K; sn.n_nodes = c->n_nodes;
+  if (c->ltq_pend != pend) {  // once per (reference, pendant length): 19.7 GB for ar53
+    if ((rc = c->LTq.ensure((size_t)c->L * c->Np * NC))) return rc;
+    for (int s0 = 0; s0 < c->L; s0 += 65535) {
+      qlane_table_generic_kernel<S, G, NC><<<dim3((unsigned)((c->Np + 127) / 128), std::min(65535, c->L - s0)), 128, 0, c->stream>>>(
+          sn, c->Tq.p, c->d_site_cat, c->al.n_codes, c->Rg, map, c->LTq.p, s0); LAUNCH_CHECK(c);
+    }
+    c->ltq_pend = pend;
+  }
+  const PreGeom g = prefilter_geometry(c, Q, 32, 1, W, blocks_per_sm);
+  const int n4 = (c->L + 3) / 4;
+  if ((rc = c->tile_lo.ensure(g.nqt)) || (rc = c->tile_hi.ensure(g.nqt)) || (rc = c->qcol.ensure((size_t)g.nqt * n4 * 32)) || (rc = c->slow_flag.ensure(Q))) return rc;
+  CK(cudaMemsetAsync(c->slow_flag.p, 0, sizeof(int32_t) * Q, c->stream));
+  tile_range_kernel<32><<<(g.nqt + 127) / 128, 128, 0, c->stream>>>(c->qsite.p, c->nq.p, c->qorder.p, (int)Q, g.nqt, c->Lp, c->tile_lo.p, c->tile_hi.p); LAUNCH_CHECK(c);
+  qlane_pack_generic_kernel<<<dim3((n4 + 7) / 8, g.nqt), 256, 0, c->stream>>>(c->codes.p, c->qorder.p, c->qcol.p, (int)Q, c->L, c->Lp, g.nqt, map, (unsigned)S, c->slow_flag.p); LAUNCH_CHECK(c);
+  PreArgs A;
+  if ((rc = prefilter_args(c, Q, g, &A))) return rc;
+  const size_t sm = Geo::smem_bytes();
+  auto kern = prefilter_qlane_kernel<W, SPS, NS, MINB, NC, G>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  kern<<<dim3(g.gx, g.gy, g.zs), (W + 1) * 32, sm, c->stream>>>(A, c->LTq.p, c->qcol.p); LAUNCH_CHECK(c);
+  c->prefilter_kernel_used = 7;
+  if ((rc = prefilter_finish(c, Q, g))) return rc;
+  A.out = c->scores.p;
+  prefilter_qlane_fix_generic_kernel<S, G><<<dim3((unsigned)Q, (c->n_nodes + 127) / 128), 128, 0, c->stream>>>(A, c->qsite.p, c->Lp, map, c->Rg, c->slow_flag.p, c->scores.p); LAUNCH_CHECK(c);
+  return PP_OK;
+}
+
 // staged form (prefilter_staged.cuh): TMA bulk copies + mbarrier ring; MMA = the K-contraction on the FP64 tensor cores
 template <int W, int SPS, int NS, bool MMA, int MINB>
 static int launch_prefilter_staged(pp_ctx *c, int64_t Q, int blocks_per_sm) {
@@ -880,6 +921,12 @@ static int run_prefilter(pp_ctx *c, int64_t Q, int kernel_choice, double pend) {
     return few ? launch_prefilter_table<2, 8, 1, 1>(c, Q, pend, 12) : launch_prefilter_table<2, 4, 4, 8>(c, Q, pend, 8);
   }
   if (kernel_choice == 2) return fail(PP_EINVAL, "prefilter: the table form exists for the DNA Gamma-4 model only");
+  if (c->S == 20 && (kernel_choice == 7 || (kernel_choice == 0 && kQlaneDefault && Q >= 64))) {
+    // proteins: 22-column query-lane log table; from one full warp of queries on it beats the direct form, which has to
+    // run S (Price-CAT) or R*S DFMAs per unit (C3, 256 genomes: 101 ms direct)
+    rc = c->gcat ? launch_prefilter_qlane_generic<20, true, 8, 4, 4, 1>(c, Q, pend, 1) : launch_prefilter_qlane_generic<20, false, 8, 4, 4, 1>(c, Q, pend, 1);
+    if (!(rc == PP_ENOMEM && kernel_choice == 0)) return rc;  // no room for the table: the direct form below needs none
+  }
   if (c->gcat) {
     if (c->S == 4) return few ? launch_prefilter_direct<4, true, 1, 2, 8, 1, TQ_GLOBAL>(c, Q, 12) : launch_prefilter_direct<4, true, 1, 2, 16, 8, TQ_GLOBAL>(c, Q, 2);
     return few ? launch_prefilter_direct<20, true, 1, 2, 4, 1, TQ_GLOBAL>(c, Q, 12) : launch_prefilter_direct<20, true, 1, 2, 8, 4, TQ_GLOBAL>(c, Q, 3);
@@ -1063,7 +1110,7 @@ extern "C" int pp_set_figs(pp_ctx *c, int32_t n_figs, const int32_t *rep, const 
   if (!c || n_figs < 0) return fail(PP_EINVAL, "pp_set_figs: bad arguments");
   CK(cudaSetDevice(c->device));
   c->fig_rep.clear(); c->fig_ptr.clear(); c->fig_idx.clear();
-  c->rep_ready = false; c->rep_mt_pend = c->rep_lt_pend = -1.0;
+  c->rep_ready = false; c->rep_mt_pend = c->rep_lt_pend = c->rep_ltq_pend = -1.0;
   if (n_figs == 0) return PP_OK;  // Fig.Dummy: the plain ranking of every non-root edge
   if (!rep || !ptr || !idx || ptr[0] != 0) return fail(PP_EINVAL, "pp_set_figs: bad arguments");
   for (int f = 0; f < n_figs; ++f) {
@@ -1095,15 +1142,15 @@ static int run_prefilter_reps(pp_ctx *c, int64_t Q, int kernel_choice, double pe
   }
   // view swap: the prefilter launchers read the supernode arrays, the table caches and the score buffer from the context
   std::swap(c->snT_a, c->rep_a.p); std::swap(c->snT_e, c->rep_e.p); std::swap(c->Np, c->rep_Np);
-  std::swap(c->scores, c->rep_scores); std::swap(c->MT, c->rep_MT); std::swap(c->MTe, c->rep_MTe); std::swap(c->LT, c->rep_LT);
-  std::swap(c->mt_pend, c->rep_mt_pend); std::swap(c->lt_pend, c->rep_lt_pend);
+  std::swap(c->scores, c->rep_scores); std::swap(c->MT, c->rep_MT); std::swap(c->MTe, c->rep_MTe); std::swap(c->LT, c->rep_LT); std::swap(c->LTq, c->rep_LTq);
+  std::swap(c->mt_pend, c->rep_mt_pend); std::swap(c->lt_pend, c->rep_lt_pend); std::swap(c->ltq_pend, c->rep_ltq_pend);
   const int nn = c->n_nodes, root = c->root_id;
   c->n_nodes = m; c->root_id = -1;
   rc = run_prefilter(c, Q, kernel_choice, pend);
   c->n_nodes = nn; c->root_id = root;
   std::swap(c->snT_a, c->rep_a.p); std::swap(c->snT_e, c->rep_e.p); std::swap(c->Np, c->rep_Np);
-  std::swap(c->scores, c->rep_scores); std::swap(c->MT, c->rep_MT); std::swap(c->MTe, c->rep_MTe); std::swap(c->LT, c->rep_LT);
-  std::swap(c->mt_pend, c->rep_mt_pend); std::swap(c->lt_pend, c->rep_lt_pend);
+  std::swap(c->scores, c->rep_scores); std::swap(c->MT, c->rep_MT); std::swap(c->MTe, c->rep_MTe); std::swap(c->LT, c->rep_LT); std::swap(c->LTq, c->rep_LTq);
+  std::swap(c->mt_pend, c->rep_mt_pend); std::swap(c->lt_pend, c->rep_lt_pend); std::swap(c->ltq_pend, c->rep_ltq_pend);
   return rc;
 }
 
@@ -1478,7 +1525,9 @@ extern "C" int pp_set_stream(pp_ctx *c, void *cuda_stream) {
 
 extern "C" int pp_set_prefilter_kernel(pp_ctx *c, int32_t kernel) {
   if (!c || kernel < 0 || kernel > 7) return fail(PP_EINVAL, "pp_set_prefilter_kernel: kernel must be 0 ... 7");
-  if ((kernel == 2 || kernel >= 4) && !(c->S == 4 && !c->gcat && c->K == 16)) return fail(PP_EINVAL, "pp_set_prefilter_kernel: the table and staged forms exist for the DNA Gamma-4 model only");
+  const bool dna4 = c->S == 4 && !c->gcat && c->K == 16;
+  if ((kernel == 2 || (kernel >= 4 && kernel <= 6)) && !dna4) return fail(PP_EINVAL, "pp_set_prefilter_kernel: the table and staged forms exist for the DNA Gamma-4 model only");
+  if (kernel == 7 && !dna4 && c->S != 20) return fail(PP_EINVAL, "pp_set_prefilter_kernel: the query-lane form exists for the DNA Gamma-4 model and the 20-state models");
   c->prefilter_choice = kernel;
   return PP_OK;
 }

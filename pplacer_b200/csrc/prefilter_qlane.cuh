@@ -80,9 +80,9 @@ qlane_pack_kernel(const uint8_t *__restrict__ codes, const int32_t *__restrict__
   qcol[((int64_t)grp * n4 + s4) * 32 + lane] = w;
 }
 
-template <int W, int SPS, int NS>
+template <int W, int SPS, int NS, int NC = kQlCols>
 struct QlaneGeom {
-  static constexpr int SITE_BYTES = kQlEdges * kQlCols * 8;  // 1536
+  static constexpr int SITE_BYTES = kQlEdges * NC * 8;  // 1536 (DNA, six columns); 5632 (proteins, 22 columns)
   static constexpr int STAGE_BYTES = SPS * SITE_BYTES;
   static constexpr int OFF_BAR = NS * STAGE_BYTES;
   static constexpr int OFF_TR = OFF_BAR + 2 * NS * 8 + 16;    // per-warp [32][33] transpose tile for the coalesced store
@@ -90,10 +90,10 @@ struct QlaneGeom {
   static_assert(SPS % 4 == 0, "the column words hold four sites");
 };
 
-template <int W, int SPS, int NS, int MINB>
+template <int W, int SPS, int NS, int MINB, int NC = kQlCols, bool GCAT = false>
 __global__ void __launch_bounds__((W + 1) * 32, MINB)
 prefilter_qlane_kernel(const PreArgs A, const double *__restrict__ LT, const uint32_t *__restrict__ qcol) {
-  using G = QlaneGeom<W, SPS, NS>;
+  using G = QlaneGeom<W, SPS, NS, NC>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + G::OFF_BAR);
   uint64_t *empty = full + NS;
@@ -113,7 +113,7 @@ prefilter_qlane_kernel(const PreArgs A, const double *__restrict__ LT, const uin
   }
   __syncthreads();
   const int et = blockIdx.y;
-  const double *tile = LT + (int64_t)et * L * (kQlEdges * kQlCols);
+  const double *tile = LT + (int64_t)et * L * (kQlEdges * NC);
 
   if (warp == W) {  // ---- producer: one bulk copy per stage (the tile is contiguous over sites) ----
     if (lane == 0)
@@ -123,7 +123,7 @@ prefilter_qlane_kernel(const PreArgs A, const double *__restrict__ LT, const uin
         const int sb = blo + st * SPS;
         const uint32_t bytes = (uint32_t)min(SPS, L - sb) * G::SITE_BYTES;
         stg::mbar_expect_tx(full + slot, bytes);
-        stg::bulk_g2s(smem_raw + (size_t)slot * G::STAGE_BYTES, tile + (int64_t)sb * (kQlEdges * kQlCols), bytes, full + slot);
+        stg::bulk_g2s(smem_raw + (size_t)slot * G::STAGE_BYTES, tile + (int64_t)sb * (kQlEdges * NC), bytes, full + slot);
       }
     return;
   }
@@ -145,7 +145,7 @@ prefilter_qlane_kernel(const PreArgs A, const double *__restrict__ LT, const uin
 #pragma unroll
     for (int j = 0; j < SPS / 4; ++j) {
       const int s4 = (sb >> 2) + j;
-      cw[j] = (live && s4 < n4) ? __ldg(qc + (int64_t)s4 * 32) : 0x05050505u;
+      cw[j] = (live && s4 < n4) ? __ldg(qc + (int64_t)s4 * 32) : 0x01010101u * (unsigned)(GCAT || NC != kQlCols ? NC - 2 : 5);
     }
     stg::mbar_wait(full + slot, (st / NS) & 1);
     const double *stage = reinterpret_cast<const double *>(smem_raw + (size_t)slot * G::STAGE_BYTES);
@@ -157,9 +157,9 @@ prefilter_qlane_kernel(const PreArgs A, const double *__restrict__ LT, const uin
           const int site = sb + 4 * j + b;
           if (site < wlo || site >= whi) continue;  // warp-uniform: outside this z-slice / the warp's windows (or past the alignment)
           const unsigned c = (cw[j] >> (8 * b)) & 0xffu;
-          const double *row = stage + (size_t)(4 * j + b) * (kQlEdges * kQlCols) + c;
+          const double *row = stage + (size_t)(4 * j + b) * (kQlEdges * NC) + c;
 #pragma unroll
-          for (int e = 0; e < kQlEdges; ++e) acc[e] += row[e * kQlCols];
+          for (int e = 0; e < kQlEdges; ++e) acc[e] += row[e * NC];
         }
       }
     }
@@ -180,7 +180,7 @@ prefilter_qlane_kernel(const PreArgs A, const double *__restrict__ LT, const uin
     const int q = __ldg(A.order + slot);
     if (e < A.sn.n_nodes) {
       double v = tr[r * 33 + lane];
-      if (blockIdx.z == 0) v -= (double)((float)__ldg(A.nq + q)) * log((double)((float)A.R));  // linear_c.c:536
+      if (blockIdx.z == 0 && !GCAT) v -= (double)((float)__ldg(A.nq + q)) * log((double)((float)A.R));  // linear_c.c:536 (no such term in mat_masked_logdot_c)
       if (A.zs == 1 && e == A.root_id) v = __longlong_as_double(0x7ff8000000000000LL);
       outz[(int64_t)q * A.sn.n_nodes + e] = v;
     }
@@ -203,6 +203,109 @@ prefilter_qlane_fix_kernel(const PreArgs A, const int32_t *__restrict__ qsite, i
     const int pk = qs[i];
     const unsigned code = ((unsigned)pk >> kSiteCodeShift) & 15u;
     if (((unsigned)(kLogColOfCode >> (4 * code)) & 15u) == 15u) add += slow_log_term(A, pk & kSiteMask, code, e);
+  }
+  scores[(int64_t)q * A.sn.n_nodes + e] += add;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same form for any alphabet and model class (proteins: S = 20, Gamma mixtures and Price-CAT): NC = S + 2
+// columns - one per state, then a zero column (uninformative sites, pad lanes, multi-state codes) and a pad.
+// mat_masked_logdot_c (linear_c.c:251-296) / ten_masked_logdot_c (:465-539).
+// ---------------------------------------------------------------------------------------------------------------
+struct QlColMap {
+  uint8_t col[kMaxCodesDev];    // table column of an alphabet code (255 = multi-state: exact term in the fix kernel)
+  uint8_t code_of_state[32];    // the alphabet code whose mask is exactly state s
+};
+
+// LTq[et][site][e][NC]; one thread per (site, edge), the S column sums run as S independent chains over (rate, state)
+template <int S, bool GCAT, int NC>
+__global__ void __launch_bounds__(128)
+qlane_table_generic_kernel(const SnT sn, const double *__restrict__ Tq, const int32_t *__restrict__ site_cat, int nc, int Rg,
+                           const QlColMap map, double *__restrict__ LT, int site0) {
+  const int64_t Np = sn.Np;
+  const int e = blockIdx.x * 128 + threadIdx.x;
+  const int site = site0 + blockIdx.y;
+  if (e >= Np) return;
+  const int K = Rg * S;
+  const double *col = sn.a + ((int64_t)site * K) * Np + e;
+  const int cat = GCAT ? __ldg(site_cat + site) : 0;
+  double dot[S];
+#pragma unroll
+  for (int c = 0; c < S; ++c) dot[c] = 0.0;
+  for (int r = 0; r < Rg; ++r) {
+    double v[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) v[s] = __ldg(col + (int64_t)(r * S + s) * Np);
+#pragma unroll
+    for (int c = 0; c < S; ++c) {
+      const double *tq = GCAT ? Tq + ((int64_t)cat * nc + map.code_of_state[c]) * S : Tq + (int64_t)map.code_of_state[c] * K + r * S;
+#pragma unroll
+      for (int s = 0; s < S; ++s) dot[c] = fma(__ldg(tq + s), v[s], dot[c]);
+    }
+  }
+  const double ex = kLn2 * (double)__ldg(sn.e + (int64_t)site * Np + e);
+  double *dst = LT + (((int64_t)(e / kQlEdges) * sn.L + site) * kQlEdges + (e % kQlEdges)) * NC;
+#pragma unroll
+  for (int c = 0; c < S; ++c) dst[c] = log(dot[c]) + ex;
+#pragma unroll
+  for (int c = S; c < NC; ++c) dst[c] = 0.0;
+}
+
+__global__ void __launch_bounds__(256)
+qlane_pack_generic_kernel(const uint8_t *__restrict__ codes, const int32_t *__restrict__ order, uint32_t *__restrict__ qcol, int Q, int L,
+                          int64_t Lp, int n_groups, const QlColMap map, unsigned zero_col, int32_t *__restrict__ slow_flag) {
+  const int s4 = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, grp = blockIdx.y;
+  const int n4 = (L + 3) / 4;
+  if (s4 >= n4) return;
+  const int slot = grp * 32 + lane;
+  uint32_t w = 0x01010101u * zero_col;
+  if (slot < Q) {
+    const int q = order[slot];
+    const uint8_t *row = codes + (int64_t)q * Lp;
+    w = 0;
+    bool slow = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int site = s4 * 4 + j;
+      unsigned c = zero_col;
+      if (site < L) {
+        const unsigned code = row[site];
+        if (!(code & 0x80u)) {
+          c = map.col[code & (kMaxCodesDev - 1)];
+          if (c == 255u) { c = zero_col; slow = true; }
+        }
+      }
+      w |= c << (8 * j);
+    }
+    if (slow) slow_flag[q] = 1;
+  }
+  qcol[((int64_t)grp * n4 + s4) * 32 + lane] = w;
+}
+
+// exact terms of the multi-state codes for the flagged queries: one thread per (query, edge), sites in order
+template <int S, bool GCAT>
+__global__ void __launch_bounds__(128)
+prefilter_qlane_fix_generic_kernel(const PreArgs A, const int32_t *__restrict__ qsite, int64_t Lp, const QlColMap map, int Rg,
+                                   const int32_t *__restrict__ slow_flag, double *__restrict__ scores) {
+  const int q = blockIdx.x;
+  if (!slow_flag[q]) return;
+  const int e = blockIdx.y * blockDim.x + threadIdx.x;
+  if (e >= A.sn.n_nodes || e == A.root_id) return;
+  const int n = A.nq[q];
+  const int32_t *qs = qsite + (int64_t)q * Lp;
+  const int K = Rg * S;
+  double add = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const int pk = qs[i];
+    const unsigned code = ((unsigned)pk >> kSiteCodeShift) & 0x7fu;
+    if (map.col[code & (kMaxCodesDev - 1)] != 255u) continue;
+    const int site = pk & kSiteMask;
+    const double *tq = GCAT ? A.Tq + ((int64_t)A.site_cat[site] * A.nc + code) * S : A.Tq + (int64_t)code * K;
+    const double *col = A.sn.a + ((int64_t)site * K) * A.sn.Np + e;
+    double dot = 0.0;
+    for (int k = 0; k < K; ++k) dot = fma(tq[k], col[(int64_t)k * A.sn.Np], dot);
+    add += log(dot) + kLn2 * (double)A.sn.e[(int64_t)site * A.sn.Np + e];
   }
   scores[(int64_t)q * A.sn.n_nodes + e] += add;
 }

@@ -749,13 +749,13 @@ struct ThreeTax : TTDriver<ThreeTax<S, GCAT, THREADS>> {
       constexpr int TP = 2;
       const int lane = threadIdx.x & 31;
       const int npair = nqc >> 1;
-      for (int j0 = threadIdx.x; j0 < npair; j0 += TP * THREADS) {
+      for (int base = 0; base < npair; base += TP * THREADS) {  // block-uniform trip count: every lane reaches the warp-wide shuffles and votes
         double2 wv[TP][S];
         int2 pk[TP];
 #pragma unroll
         for (int t = 0; t < TP; ++t) {
-          const int j = j0 + t * THREADS;
-          const bool in = j < npair;  // uniform per half-warp (nqc is a multiple of 32)
+          const int j = base + t * THREADS + threadIdx.x;
+          const bool in = j < npair;  // uniform per HALF-warp only (npair is a multiple of 16)
           pk[t] = in ? __ldg(reinterpret_cast<const int2 *>(qsite) + j) : make_int2(-1, -1);
 #pragma unroll
           for (int s = 0; s < S; ++s)

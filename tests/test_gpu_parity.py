@@ -133,6 +133,27 @@ def test_prefilter_kernel_variants_match_oracle(oracle_binding, name, kernel):
     assert np.all(np.abs(g - w) <= 1e-10 * np.abs(w)), np.abs((g - w) / w).max()
 
 
+@pytest.mark.parametrize("name", ["wag", "gcat_aa"])
+def test_protein_query_lane_prefilter_matches_oracle(oracle_binding, name):
+    """The 22-column query-lane log table of the 20-state models (Gamma mixture and Price-CAT), with the two-state
+    ambiguity codes B / Z (exact terms added by the fix kernel), X and gaps (uninformative), on more queries than one
+    warp holds: same scores as mat_masked_logdot_c / ten_masked_logdot_c."""
+    prob, o, p = setup(name, oracle_binding)
+    q = np.concatenate([prob.query_chars] * 5, axis=0)[:70].copy()
+    q[1, ::7] = ord("B"); q[2, 3::11] = ord("Z"); q[3, ::5] = ord("X"); q[4, 1::9] = ord("-")
+    _, _, st, info = o.place(q, oracle_prefs(oracle_binding, prob), n_threads=4, debug=True)
+    want = info["scores"]
+    got = p.prefilter_scores(q, kernel=7)
+    assert p.prefilter_kernel_used() == 7
+    direct = p.prefilter_scores(q, kernel=1)
+    root = prob.tree.root
+    keep = [i for i in range(prob.tree.n_nodes) if i != root]
+    assert np.isnan(got[:, root]).all()
+    for g in (got[:, keep], direct[:, keep]):
+        w = want[:, keep]
+        assert np.all(np.abs(g - w) <= 1e-10 * np.abs(w)), np.abs((g - w) / w).max()
+
+
 def test_prefilter_many_queries_matches_few_query_kernels(oracle_binding):
     """Q > 64 takes the multi-warp tiles (W = 4/8, QT = 16), Q <= 64 the one-warp blocks with the site
     range split over blockIdx.z: same scores for the same queries either way, for every kernel form."""
