@@ -133,14 +133,15 @@ def test_prefilter_kernel_variants_match_oracle(oracle_binding, name, kernel):
     assert np.all(np.abs(g - w) <= 1e-10 * np.abs(w)), np.abs((g - w) / w).max()
 
 
-@pytest.mark.parametrize("name", ["wag", "gcat_aa"])
-def test_protein_query_lane_prefilter_matches_oracle(oracle_binding, name):
-    """The 22-column query-lane log table of the 20-state models (Gamma mixture and Price-CAT), with the two-state
-    ambiguity codes B / Z (exact terms added by the fix kernel), X and gaps (uninformative), on more queries than one
-    warp holds: same scores as mat_masked_logdot_c / ten_masked_logdot_c."""
+@pytest.mark.parametrize("name", ["wag", "gcat_aa", "gcat_dna"])
+def test_generic_query_lane_prefilter_matches_oracle(oracle_binding, name):
+    """The generic query-lane log table (S + 2 columns: 20-state Gamma mixture and Price-CAT, DNA Price-CAT), with
+    two-state ambiguity codes (exact terms added by the fix kernel), the any-state code X / N (its own column) and gaps
+    (uninformative), on more queries than one warp holds: same scores as mat_masked_logdot_c / ten_masked_logdot_c."""
     prob, o, p = setup(name, oracle_binding)
     q = np.concatenate([prob.query_chars] * 5, axis=0)[:70].copy()
-    q[1, ::7] = ord("B"); q[2, 3::11] = ord("Z"); q[3, ::5] = ord("X"); q[4, 1::9] = ord("-")
+    two_a, two_b, any_c = ("R", "Y", "N") if name == "gcat_dna" else ("B", "Z", "X")
+    q[1, ::7] = ord(two_a); q[2, 3::11] = ord(two_b); q[3, ::5] = ord(any_c); q[4, 1::9] = ord("-")
     _, _, st, info = o.place(q, oracle_prefs(oracle_binding, prob), n_threads=4, debug=True)
     want = info["scores"]
     got = p.prefilter_scores(q, kernel=7)
@@ -687,7 +688,7 @@ def test_fig_ranking_at_the_c2_shape(c2_small, oracle_binding):
     from pplacer_b200 import fig
     prob, p = c2_small
     figs = fig.figs_of_tree(0.1, prob.tree)
-    q = prob.query_chars[:96]
+    q = prob.query_chars[:288]   # >= 256 queries: the representatives go through the query-lane table on the fig view
     o = oracle_binding.Oracle(prob)
     o.precompute()
     o.set_figs(figs)
@@ -698,7 +699,8 @@ def test_fig_ranking_at_the_c2_shape(c2_small, oracle_binding):
         got, n_got, st_got, gi = p.place(q, p.prefs(), debug=True)
     finally:
         p.set_figs(None)
+    assert p.prefilter_kernel_used() == 7
     near = assert_placements_match(got, n_got, st_got, exp, n_exp, st_exp, near_tie_ll=1e-3)
-    assert len(near_queries(near)) <= 2, near
+    assert len(near_queries(near)) <= 5, near
     assert (np.isfinite(gi["scores"]) == np.isfinite(oi["scores"])).all(axis=1).mean() >= 0.97
     assert np.isfinite(oi["scores"]).sum(axis=1).mean() < 0.5 * prob.tree.n_nodes
