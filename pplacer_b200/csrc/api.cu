@@ -827,6 +827,7 @@ static int launch_prefilter_qlane_generic(pp_ctx *c, int64_t Q, double pend, int
     const uint32_t m = code < c->al.n_codes ? c->al.mask_of_code[code] : 0u;
     map.col[code] = 255;
     if (m && !(m & (m - 1))) { int st = 0; while (!((m >> st) & 1u)) ++st; map.col[code] = (uint8_t)st; map.code_of_state[st] = (uint8_t)code; }
+    else if (m == (S == 32 ? 0xffffffffu : (1u << S) - 1u)) { map.col[code] = (uint8_t)S; map.code_of_state[S] = (uint8_t)code; }  // X / N
   }
   SnT sn; sn.a = c->snT_a; sn.e = c->snT_e; sn.Np = c->Np; sn.L = c->L; sn.K = c->K; sn.n_nodes = c->n_nodes;
   if (c->ltq_pend != pend) {  // once per (reference, pendant length): 19.7 GB for ar53
@@ -842,7 +843,7 @@ static int launch_prefilter_qlane_generic(pp_ctx *c, int64_t Q, double pend, int
   if ((rc = c->tile_lo.ensure(g.nqt)) || (rc = c->tile_hi.ensure(g.nqt)) || (rc = c->qcol.ensure((size_t)g.nqt * n4 * 32)) || (rc = c->slow_flag.ensure(Q))) return rc;
   CK(cudaMemsetAsync(c->slow_flag.p, 0, sizeof(int32_t) * Q, c->stream));
   tile_range_kernel<32><<<(g.nqt + 127) / 128, 128, 0, c->stream>>>(c->qsite.p, c->nq.p, c->qorder.p, (int)Q, g.nqt, c->Lp, c->tile_lo.p, c->tile_hi.p); LAUNCH_CHECK(c);
-  qlane_pack_generic_kernel<<<dim3((n4 + 7) / 8, g.nqt), 256, 0, c->stream>>>(c->codes.p, c->qorder.p, c->qcol.p, (int)Q, c->L, c->Lp, g.nqt, map, (unsigned)S, c->slow_flag.p); LAUNCH_CHECK(c);
+  qlane_pack_generic_kernel<<<dim3((n4 + 7) / 8, g.nqt), 256, 0, c->stream>>>(c->codes.p, c->qorder.p, c->qcol.p, (int)Q, c->L, c->Lp, g.nqt, map, (unsigned)(S + 1), c->slow_flag.p); LAUNCH_CHECK(c);
   PreArgs A;
   if ((rc = prefilter_args(c, Q, g, &A))) return rc;
   const size_t sm = Geo::smem_bytes();
@@ -922,6 +923,11 @@ static int run_prefilter(pp_ctx *c, int64_t Q, int kernel_choice, double pend) {
     return few ? launch_prefilter_table<2, 8, 1, 1>(c, Q, pend, 12) : launch_prefilter_table<2, 4, 4, 8>(c, Q, pend, 8);
   }
   if (kernel_choice == 2) return fail(PP_EINVAL, "prefilter: the table form exists for the DNA Gamma-4 model only");
+  if (c->S == 4 && (kernel_choice == 7 || (kernel_choice == 0 && kQlaneDefault && Q >= 256))) {
+    // DNA with Price-CAT (FastTree reference trees) or a Gamma mixture other than four rates: six-column generic table
+    rc = c->gcat ? launch_prefilter_qlane_generic<4, true, 4, 8, 6, 2>(c, Q, pend, 2) : launch_prefilter_qlane_generic<4, false, 4, 8, 6, 2>(c, Q, pend, 2);
+    if (!(rc == PP_ENOMEM && kernel_choice == 0)) return rc;
+  }
   if (c->S == 20 && (kernel_choice == 7 || (kernel_choice == 0 && kQlaneDefault && Q >= 64))) {
     // proteins: 22-column query-lane log table; from one full warp of queries on it beats the direct form, which has to
     // run S (Price-CAT) or R*S DFMAs per unit (C3, 256 genomes: 101 ms direct)
@@ -1534,7 +1540,7 @@ extern "C" int pp_set_prefilter_kernel(pp_ctx *c, int32_t kernel) {
   if (!c || kernel < 0 || kernel > 7) return fail(PP_EINVAL, "pp_set_prefilter_kernel: kernel must be 0 ... 7");
   const bool dna4 = c->S == 4 && !c->gcat && c->K == 16;
   if ((kernel == 2 || (kernel >= 4 && kernel <= 6)) && !dna4) return fail(PP_EINVAL, "pp_set_prefilter_kernel: the table and staged forms exist for the DNA Gamma-4 model only");
-  if (kernel == 7 && !dna4 && c->S != 20) return fail(PP_EINVAL, "pp_set_prefilter_kernel: the query-lane form exists for the DNA Gamma-4 model and the 20-state models");
+
   c->prefilter_choice = kernel;
   return PP_OK;
 }

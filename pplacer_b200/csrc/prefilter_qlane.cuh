@@ -145,7 +145,7 @@ prefilter_qlane_kernel(const PreArgs A, const double *__restrict__ LT, const uin
 #pragma unroll
     for (int j = 0; j < SPS / 4; ++j) {
       const int s4 = (sb >> 2) + j;
-      cw[j] = (live && s4 < n4) ? __ldg(qc + (int64_t)s4 * 32) : 0x01010101u * (unsigned)(GCAT || NC != kQlCols ? NC - 2 : 5);
+      cw[j] = (live && s4 < n4) ? __ldg(qc + (int64_t)s4 * 32) : 0x01010101u * (unsigned)(NC - 1);  // the zero column is the last one in both layouts
     }
     stg::mbar_wait(full + slot, (st / NS) & 1);
     const double *stage = reinterpret_cast<const double *>(smem_raw + (size_t)slot * G::STAGE_BYTES);
@@ -209,13 +209,14 @@ prefilter_qlane_fix_kernel(const PreArgs A, const int32_t *__restrict__ qsite, i
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// The same form for any alphabet and model class (proteins: S = 20, Gamma mixtures and Price-CAT): NC = S + 2
-// columns - one per state, then a zero column (uninformative sites, pad lanes, multi-state codes) and a pad.
+// The same form for any alphabet and model class (proteins, DNA with Price-CAT or a Gamma mixture other than four
+// rates): NC = S + 2 columns - one per state, one for the "any" code (X / N: informative in the reference,
+// alignment.ml:235), and a zero column (uninformative sites, pad lanes, the other multi-state codes).
 // mat_masked_logdot_c (linear_c.c:251-296) / ten_masked_logdot_c (:465-539).
 // ---------------------------------------------------------------------------------------------------------------
 struct QlColMap {
-  uint8_t col[kMaxCodesDev];    // table column of an alphabet code (255 = multi-state: exact term in the fix kernel)
-  uint8_t code_of_state[32];    // the alphabet code whose mask is exactly state s
+  uint8_t col[kMaxCodesDev];    // table column of an alphabet code (255 = two- / three-state code: exact term in the fix kernel)
+  uint8_t code_of_state[32];    // the alphabet code whose mask is exactly state s; [S] = the "any" code
 };
 
 // LTq[et][site][e][NC]; one thread per (site, edge), the S column sums run as S independent chains over (rate, state)
@@ -230,15 +231,16 @@ qlane_table_generic_kernel(const SnT sn, const double *__restrict__ Tq, const in
   const int K = Rg * S;
   const double *col = sn.a + ((int64_t)site * K) * Np + e;
   const int cat = GCAT ? __ldg(site_cat + site) : 0;
-  double dot[S];
+  constexpr int NCOL = S + 1;  // the states and the "any" code
+  double dot[NCOL];
 #pragma unroll
-  for (int c = 0; c < S; ++c) dot[c] = 0.0;
+  for (int c = 0; c < NCOL; ++c) dot[c] = 0.0;
   for (int r = 0; r < Rg; ++r) {
     double v[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) v[s] = __ldg(col + (int64_t)(r * S + s) * Np);
 #pragma unroll
-    for (int c = 0; c < S; ++c) {
+    for (int c = 0; c < NCOL; ++c) {
       const double *tq = GCAT ? Tq + ((int64_t)cat * nc + map.code_of_state[c]) * S : Tq + (int64_t)map.code_of_state[c] * K + r * S;
 #pragma unroll
       for (int s = 0; s < S; ++s) dot[c] = fma(__ldg(tq + s), v[s], dot[c]);
@@ -247,9 +249,9 @@ qlane_table_generic_kernel(const SnT sn, const double *__restrict__ Tq, const in
   const double ex = kLn2 * (double)__ldg(sn.e + (int64_t)site * Np + e);
   double *dst = LT + (((int64_t)(e / kQlEdges) * sn.L + site) * kQlEdges + (e % kQlEdges)) * NC;
 #pragma unroll
-  for (int c = 0; c < S; ++c) dst[c] = log(dot[c]) + ex;
+  for (int c = 0; c < NCOL; ++c) dst[c] = log(dot[c]) + ex;
 #pragma unroll
-  for (int c = S; c < NC; ++c) dst[c] = 0.0;
+  for (int c = NCOL; c < NC; ++c) dst[c] = 0.0;
 }
 
 __global__ void __launch_bounds__(256)
