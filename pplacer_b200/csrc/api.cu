@@ -215,6 +215,7 @@ extern "C" void pp_destroy(pp_ctx *c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (int w = 0; w < 3; ++w) { if (c->g.a[w]) cudaFree(c->g.a[w]); if (c->g.e[w]) cudaFree(c->g.e[w]); }
+  for (int w = 0; w < 2; ++w) if (c->g.ea[w]) cudaFree(c->g.ea[w]);
   c->qsite_cat.release(); c->nqc.release(); c->cat_perm.release(); c->cat_start.release(); c->qc.release(); c->partial.release(); c->MT.release(); c->LT.release(); c->LTq.release(); c->qcol.release(); c->slow_flag.release(); c->MTe.release();
   void *ptrs[] = {c->snT_a, c->snT_e, c->dm, c->d_bl, c->d_code_of_char, c->d_ref_codes, c->d_site_cat, c->d_child_ptr, c->d_child_idx, c->d_parent, c->d_leaf_row};
   for (void *p : ptrs) if (p) cudaFree(p);
@@ -574,6 +575,19 @@ extern "C" int pp_precompute(pp_ctx *c) {
     transpose_to_edge_major_kernel<int32_t><<<grid_e, 256, 0, c->stream>>>(c->g.e[2], c->snT_e, c->n_nodes, 1, c->L, c->Lp, c->Np, 0); LAUNCH_CHECK(c);
     c->tq_pend = c->mt_pend = c->lt_pend = c->ltq_pend = -1.0;
     c->rep_ready = false; c->rep_mt_pend = c->rep_lt_pend = c->rep_ltq_pend = -1.0;
+  }
+  if (rc == PP_OK && ttw_supported(c) && c->eig_ok) {
+    // engine 4 reads darr / parr in the eigenbasis of the rate matrix (threetax_eigen.cuh); without room for the two
+    // copies the second stage falls back to engine 3
+    const size_t bytes = sizeof(double) * (size_t)c->g.a_stride * c->n_nodes;
+    for (int w = 0; w < 2 && c->eig_ok; ++w)
+      if (!c->g.ea[w] && cudaMalloc(&c->g.ea[w], bytes) != cudaSuccess) { cudaGetLastError(); c->g.ea[w] = nullptr; c->eig_ok = false; }
+    if (c->eig_ok) {
+      XitMat xm;
+      std::memcpy(xm.v, c->em4.xit, sizeof xm.v);
+      const dim3 grid((unsigned)((c->Lp + 255) / 256), (unsigned)std::min<int64_t>((int64_t)c->n_nodes * c->R, 32768));
+      for (int w = 0; w < 2; ++w) { eigen_glv_kernel<<<grid, 256, 0, c->stream>>>(c->g.a[w], c->g.ea[w], (int64_t)c->n_nodes * c->R, c->Lp, xm); LAUNCH_CHECK(c); }
+    }
   }
   cudaError_t e = cudaStreamSynchronize(c->stream);
   cudaFree(Pfull); cudaFree(Phalf); cudaFree(d_levels);

@@ -31,6 +31,7 @@ struct DevModel {
 
 struct GlvArrays {
   double *a[3];   // darr, parr, snodes : [n_nodes][K][Lp]
+  double *ea[2];  // DNA Gamma-4 second stage (threetax_eigen.cuh): darr, parr in the eigenbasis of the rate matrix, same layout
   int32_t *e[3];  // [n_nodes][Lp]
   int64_t a_stride;  // K * Lp
   int L, Lp, K, n_nodes;

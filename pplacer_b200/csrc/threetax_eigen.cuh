@@ -15,6 +15,17 @@
 // no rate-matrix build, no dediagonalize, no per-lane table lookups, no global memory: y (3R+1 doubles per
 // site) lives in the block's shared memory for the first WS sites of the query (global overflow beyond).
 //
+// The passes that gather the candidate's distal / proximal vectors read them IN THE EIGENBASIS too (r5m): pp_precompute
+// keeps alpha = Xit^T d and beta = Xit^T p per (node, rate, site) beside darr / parr, so that
+//     P_r(t) d = X (exp(rho_r t Lambda) .* alpha)
+// needs four exponentials per rate instead of a 4x4 matrix from shared memory (the X entries are immediates from the
+// constant bank), and a distal evaluation contracts directly in the eigenbasis:
+//     u_i = sum_r a_r^T M_r[code_i] b_r,   a = E(dist) .* alpha,  b = E(prox) .* beta,
+//     M_r[code][k][k'] = sum_s statd_s q_r,s(code) X[s,k] X[s,k']          (q = the evolved pendant vector of the code)
+// - 28 FP64 operations per (site, rate, point) instead of 44, and M (built once per pendant length) is shared by
+// the four points of a batched pass.  M and the batch's exponentials live in the head of y, which is dead while
+// the distal length moves.
+//
 // Division of labour, per objective call:
 //   thread 0    copies the scalar optimiser state (TTMachine, threetax.cuh) from shared memory into registers,
 //               advances it to the next call that needs a pass (memo hits cost nothing), posts a COMMAND;
@@ -51,6 +62,7 @@ template <int R, int NW, int WS>
 struct TTEig {
   static constexpr int NT = 32 * NW, K = 4 * R, PM = 16 * R, NE = 3 * R, NY = NE + 1, NEP = (NE + 1) & ~1;
   static constexpr int NBP = 5, NBD = 4, MEMO = 24, MAXJOBS = 10, NPT = 8;
+  static constexpr int MSTR = 18;  // doubles per (rate, code) block of M: 16 + 2, so that the four base codes fall into different banks
   static constexpr unsigned FULL = 0xffffffffu;
   enum : int { CMD_DONE = 0, CMD_PEND, CMD_BUILD_PEND, CMD_DIST1, CMD_DIST4 };
   enum : int { JOB_P = 0, JOB_Q = 1 };
@@ -75,9 +87,11 @@ struct TTEig {
   static constexpr int OBJ_DOUBLES = 64;
   static constexpr int OFF_QS = OFF_OBJ + OBJ_DOUBLES;                // int32 [WS]: site | code << 24 of the candidate's query
   static constexpr int OFF_Y = OFF_QS + WS / 2;                       // y[NY][WS]
-  static constexpr int OFF_PB = OFF_Y;                                // distal batch matrices [NBD][2][PM]: y is dead while the distal length moves
+  static constexpr int OFF_PB = OFF_Y;                                // distal batch exponentials [NBD][2][K]: y is dead while the distal length moves
+  static constexpr int OFF_M = OFF_PB + NBD * 2 * K;                  // M[R][16 codes][MSTR]: also in the dead head of y
   static_assert(WS % 32 == 0, "a warp's sites are all in shared memory or all in the global overflow");
-  static_assert(NBD * 2 * PM <= NY * WS, "the distal batch matrices alias the head of y");
+  static_assert(NBD * 2 * K + R * 16 * MSTR <= NY * WS, "the distal batch exponentials and M alias the head of y");
+  static_assert((OFF_M % 2) == 0 && (MSTR % 2) == 0, "16-byte alignment of the M rows");
   static_assert((OFF_PD % 2) == 0 && (OFF_E % 2) == 0 && (OFF_Y % 2) == 0 && (PM % 2) == 0, "16-byte alignment of the matrix sets");
   static_assert(NBP <= NPT && NBD <= NPT, "points per pass");
 
@@ -134,7 +148,7 @@ struct TTEig {
         memo_pending = 4;
         w_stale = 1;  // the batch matrices overwrite the head of y
 #pragma unroll
-        for (int b = 0; b < 4; ++b) { add_job(JOB_P, bx[b], OFF_PB + 2 * b * PM); add_job(JOB_P, bp[b], OFF_PB + (2 * b + 1) * PM); }
+        for (int b = 0; b < 4; ++b) { add_job(JOB_P, bx[b], OFF_PB + 2 * b * K); add_job(JOB_P, bp[b], OFF_PB + (2 * b + 1) * K); }
       } else {
         memo_clear(0);
         const double mid = 0.5 * (left + right);
@@ -160,10 +174,10 @@ struct TTEig {
     }
     __device__ __forceinline__ void post(int cmd, int points) { JOB()[0] = cmd; JOB()[1] = n_jobs; JOB()[3] = points; }
     __device__ __forceinline__ void need_pd() {
-      if (pd_dirty) { add_job(JOB_P, dist_bl, OFF_PD); add_job(JOB_P, prox_bl, OFF_PD + PM); pd_dirty = 0; }
+      if (pd_dirty) { add_job(JOB_P, dist_bl, OFF_PD); add_job(JOB_P, prox_bl, OFF_PD + K); pd_dirty = 0; }
     }
     __device__ __forceinline__ void post_pend(int points) {  // the points are in OFF_PT
-      if (w_stale) { need_pd(); w_stale = 0; post(CMD_BUILD_PEND, points); } else post(CMD_PEND, points);
+      if (w_stale) { need_pd(); w_stale = 0; pq_dirty = 1; post(CMD_BUILD_PEND, points); } else post(CMD_PEND, points);  // writing y overwrites M
     }
     __device__ __forceinline__ void post_dist(bool batch) {
       if (pq_dirty) { add_job(JOB_Q, pend_bl, OFF_PQ); pq_dirty = 0; }
@@ -236,31 +250,22 @@ struct TTEig {
   };
   static_assert(sizeof(Scalar) <= OBJ_DOUBLES * sizeof(double), "scalar state does not fit its shared slot");
 
-  // ---- all threads: Diagd.multi_exp (diagd.ml:79-98; linear_c.c:92-146) for the posted jobs ----
-  // A rate-matrix job belongs to ONE warp (exponentials, then entries, with a warp-level sync between), the pendant
-  // table is split over all warps (each computes the job's K exponentials for itself): one block barrier in all.
+  // ---- all threads: the posted jobs.  JOB_P: the K exponentials exp(rho_r bl lambda_k) of a branch length (what is
+  // left of Diagd.multi_exp, diagd.ml:79-98, when the vectors are already in the eigenbasis), one warp per job.
+  // JOB_Q: the evolved pendant vectors q[rs][mask] of the sixteen codes (lv_of_nuc, nuc_models.ml:49-54 through
+  // gemmish_c, linear_c.c:29-90), then M[r][mask][k][k'] = sum_s statd_s q[rs][mask] X[s,k] X[s,k'] ----
   __device__ __forceinline__ static void build_jobs(const EigModel<R> &em, int n) {
     double *s = SM();
     const int *job = JOB();
     const int w = warp_id(), l = lane_id();
+    bool has_q = false;
     for (int j = w; j < n; j += NW) {
       if (job[4 + MAXJOBS + j] != JOB_P) continue;
-      double *ex = s + OFF_EX + j * K;
-      for (int t = l; t < K; t += 32) ex[t] = exp(em.rates[t >> 2] * s[OFF_JBL + j] * em.lam[t & 3]);
-      __syncwarp();
-      double *dst = s + job[4 + j];
-      for (int e = l; e < PM; e += 32) {
-        const int r = e >> 4, i = (e >> 2) & 3, c = e & 3;
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) acc = fma(ex[r * 4 + k] * em.x[i * 4 + k], em.xit[c * 4 + k], acc);
-        dst[e] = acc;
-      }
+      if (l < K) s[job[4 + j] + l] = exp(em.rates[l >> 2] * s[OFF_JBL + j] * em.lam[l & 3]);
     }
     for (int j = 0; j < n; ++j) {
       if (job[4 + MAXJOBS + j] != JOB_Q) continue;
-      // q[rs][mask]: the evolved indicator vector of a code is the sum of the selected columns of P in
-      // ascending state order (lv_of_nuc, nuc_models.ml:49-54 through gemmish_c, linear_c.c:29-90)
+      has_q = true;
       double *ex = s + OFF_EXQ + w * K;
       for (int t = l; t < K; t += 32) ex[t] = exp(em.rates[t >> 2] * s[OFF_JBL + j] * em.lam[t & 3]);
       __syncwarp();
@@ -279,23 +284,16 @@ struct TTEig {
       }
     }
     __syncthreads();
-  }
-
-  template <int T>
-  __device__ __forceinline__ static void site_w(const double *Pd, const double *Pp, const double (&d)[T][4], const double (&p)[T][4],
-                                                const EigModel<R> &em, double (&ww)[T][4]) {
-    const double2 *Pd2 = reinterpret_cast<const double2 *>(Pd), *Pp2 = reinterpret_cast<const double2 *>(Pp);
+    if (has_q) {  // block-uniform
+      const double *q = s + OFF_PQ;
+      for (int e = threadIdx.x; e < R * 16 * 16; e += NT) {
+        const int r = e >> 8, mask = (e >> 4) & 15, k = (e >> 2) & 3, k2 = e & 3;
+        double acc = 0.0;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const double2 a0 = Pd2[s * 2], a1 = Pd2[s * 2 + 1], b0 = Pp2[s * 2], b1 = Pp2[s * 2 + 1];
-#pragma unroll
-      for (int t = 0; t < T; ++t) {
-        double de = fma(a0.x, d[t][0], 0.0), pe = fma(b0.x, p[t][0], 0.0);
-        de = fma(a0.y, d[t][1], de); pe = fma(b0.y, p[t][1], pe);
-        de = fma(a1.x, d[t][2], de); pe = fma(b1.x, p[t][2], pe);
-        de = fma(a1.y, d[t][3], de); pe = fma(b1.y, p[t][3], pe);
-        ww[t][s] = (em.statd[s] * pe) * de;  // ((statd*x)*y), x = prox, y = dist (three_tax.ml:31-36)
+        for (int i = 0; i < 4; ++i) acc = fma((em.statd[i] * q[(r * 4 + i) * 16 + mask]) * em.x[i * 4 + k], em.x[i * 4 + k2], acc);
+        s[OFF_M + (r * 16 + mask) * MSTR + k * 4 + k2] = acc;
       }
+      __syncthreads();
     }
   }
 
@@ -391,11 +389,11 @@ struct TTEig {
   //   BUILD = true : y of every site from the current distal / proximal matrices (header) -> shared memory, global beyond WS
   // T sites per thread per iteration.  The loads of step (iteration, rate) + 1 are issued before step (iteration, rate) is
   // computed and the site list runs two iterations ahead, so one L2 latency is exposed per pass instead of one per step
-  // (r3d: long_scoreboard on the first FMA of site_w was the top stall of the straightforward loop).
+  // (r3d: long_scoreboard on the first FMA of the site body was the top stall of the straightforward loop).
   template <bool BUILD, int NB, int T>
   __device__ __forceinline__ static void pass_gather(const EigModel<R> &em, const ECand &c, int pm_off) {
     double *s = SM();
-    const double *Pm = s + pm_off, *PQ = s + OFF_PQ;
+    const double *EV = s + pm_off, *MT = s + OFF_M;  // EV: per point the K exponentials of the distal, then of the proximal length
     double *bad = s + OFF_BAD;
     SiteProd lp[NB];
 #pragma unroll
@@ -438,23 +436,45 @@ struct TTEig {
           load_dp<T>(c, pks, last ? 0 : r + 1, dn, pn);
         }
         if (!BUILD) {
-          double q[T][4];
+          double m[T][16];
 #pragma unroll
-          for (int t = 0; t < T; ++t)
+          for (int t = 0; t < T; ++t) {
+            const double2 *mp = reinterpret_cast<const double2 *>(MT + (r * 16 + ((pk[t] >> kSiteCodeShift) & 15)) * MSTR);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) q[t][k] = PQ[(r * 4 + k) * 16 + ((pk[t] >> kSiteCodeShift) & 15)];
+            for (int i = 0; i < 8; ++i) { const double2 v = mp[i]; m[t][2 * i] = v.x; m[t][2 * i + 1] = v.y; }
+          }
 #pragma unroll
           for (int b = 0; b < NB; ++b) {
-            double ww[T][4];
-            site_w<T>(Pm + b * 2 * PM + r * 16, Pm + b * 2 * PM + PM + r * 16, d, p, em, ww);
+            const double2 *ed = reinterpret_cast<const double2 *>(EV + b * 2 * K + r * 4), *ep = reinterpret_cast<const double2 *>(EV + b * 2 * K + K + r * 4);
+            const double2 e0 = ed[0], e1 = ed[1], f0 = ep[0], f1 = ep[1];
 #pragma unroll
-            for (int t = 0; t < T; ++t)
-#pragma unroll
-              for (int k = 0; k < 4; ++k) u[t][b] = fma(ww[t][k], q[t][k], u[t][b]);
+            for (int t = 0; t < T; ++t) {
+              const double a0 = e0.x * d[t][0], a1 = e0.y * d[t][1], a2 = e1.x * d[t][2], a3 = e1.y * d[t][3];
+              const double b0 = f0.x * p[t][0], b1 = f0.y * p[t][1], b2 = f1.x * p[t][2], b3 = f1.y * p[t][3];
+              const double t0 = fma(m[t][3], b3, fma(m[t][2], b2, fma(m[t][1], b1, m[t][0] * b0)));
+              const double t1 = fma(m[t][7], b3, fma(m[t][6], b2, fma(m[t][5], b1, m[t][4] * b0)));
+              const double t2 = fma(m[t][11], b3, fma(m[t][10], b2, fma(m[t][9], b1, m[t][8] * b0)));
+              const double t3 = fma(m[t][15], b3, fma(m[t][14], b2, fma(m[t][13], b1, m[t][12] * b0)));
+              u[t][b] = fma(a3, t3, fma(a2, t2, fma(a1, t1, fma(a0, t0, u[t][b]))));
+            }
           }
         } else {
           double ww[T][4];
-          site_w<T>(Pm + r * 16, Pm + PM + r * 16, d, p, em, ww);
+          {
+            const double2 *ed = reinterpret_cast<const double2 *>(EV + r * 4), *ep = reinterpret_cast<const double2 *>(EV + K + r * 4);
+            const double2 e0 = ed[0], e1 = ed[1], f0 = ep[0], f1 = ep[1];
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              const double a0 = e0.x * d[t][0], a1 = e0.y * d[t][1], a2 = e1.x * d[t][2], a3 = e1.y * d[t][3];
+              const double b0 = f0.x * p[t][0], b1 = f0.y * p[t][1], b2 = f1.x * p[t][2], b3 = f1.y * p[t][3];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const double de = fma(em.x[i * 4 + 3], a3, fma(em.x[i * 4 + 2], a2, fma(em.x[i * 4 + 1], a1, em.x[i * 4] * a0)));
+                const double pe = fma(em.x[i * 4 + 3], b3, fma(em.x[i * 4 + 2], b2, fma(em.x[i * 4 + 1], b1, em.x[i * 4] * b0)));
+                ww[t][i] = (em.statd[i] * pe) * de;  // ((statd*x)*y), x = prox, y = dist (three_tax.ml:31-36)
+              }
+            }
+          }
 #pragma unroll
           for (int t = 0; t < T; ++t) {
             double t0 = ww[t][0] * em.xz[0];
@@ -592,6 +612,22 @@ struct TTEig {
   }
 };
 
+// alpha[node][r*4 + k][site] = sum_c Xit[c][k] * glv[node][r*4 + c][site]: darr / parr in the eigenbasis of the rate matrix
+// (exponents unchanged - the transform is linear per site and rate).  One thread per (node, rate, site).
+struct XitMat { double v[16]; };
+__global__ void __launch_bounds__(256)
+eigen_glv_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t n_planes4 /* nodes * R */, int64_t Lp, const XitMat xit) {
+  const int64_t site = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (site >= Lp) return;
+  for (int64_t pl = blockIdx.y; pl < n_planes4; pl += gridDim.y) {
+    const double *a = src + pl * 4 * Lp + site;
+    const double d0 = __ldg(a), d1 = __ldg(a + Lp), d2 = __ldg(a + 2 * Lp), d3 = __ldg(a + 3 * Lp);
+    double *o = dst + pl * 4 * Lp + site;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[(int64_t)k * Lp] = fma(xit.v[12 + k], d3, fma(xit.v[8 + k], d2, fma(xit.v[4 + k], d1, xit.v[k] * d0)));
+  }
+}
+
 // Persistent kernel: every BLOCK pulls candidates (in `order`: length class, then edge) until n are done.
 template <int R, int NW, int MINB, int WS>
 __global__ void __launch_bounds__(NW * 32, MINB)
@@ -623,8 +659,8 @@ tt_eigen_kernel(const __grid_constant__ EigModel<R> em, GlvArrays g, const doubl
     ECand c;
     c.qsite = qsite + (int64_t)cin.q * g.Lp;
     c.nq = nq[cin.q];
-    c.dbase = g.a[0] + (int64_t)cin.loc * g.a_stride;
-    c.pbase = g.a[1] + (int64_t)cin.loc * g.a_stride;
+    c.dbase = g.ea[0] + (int64_t)cin.loc * g.a_stride;  // the eigenbasis copies of darr / parr (eigen_glv_kernel)
+    c.pbase = g.ea[1] + (int64_t)cin.loc * g.a_stride;
     c.Lp = g.Lp;
     c.wg = wbuf + (int64_t)blockIdx.x * TT::K * g.Lp;
     {  // the query's site list into shared memory; total_twoexp of the distal and proximal GLVs over it (gstar_support.ml:43-49)
