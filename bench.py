@@ -416,12 +416,14 @@ def run_ours(args):
     if used == 7:
         # query-lane log table: one shared-memory load (a broadcast request: <= 6 distinct words) and one DADD per
         # (query, edge, site) unit, no FMAs - its roof is the shared-memory pipe, one warp request per clock per SM
-        lsu_peak = props.multi_processor_count * 32.0 * float(sm_mhz) * 1e6 / 1e9 if sm_mhz else None
+        # a warp-wide 8-byte shared-memory load is two 128-byte wavefronts, and the pipe moves one wavefront per clock
+        # per SM: 16 units per clock per SM (ncu r5b / r5o: l1tex throughput 88 % at 0.78 of this figure)
+        lsu_peak = props.multi_processor_count * 16.0 * float(sm_mhz) * 1e6 / 1e9 if sm_mhz else None
         ach = units / (pre_ms * 1e-3) / 1e9 if pre_ms > 0 else 0.0
         roofline_prefilter.update({
-            "bound": "shared-memory requests", "achieved": ach, "unit": "G units/s", "peak": lsu_peak,
+            "bound": "shared-memory bandwidth", "achieved": ach, "unit": "G units/s", "peak": lsu_peak,
             "frac": ach / lsu_peak if lsu_peak else None,
-            "peak_source": "SMs x 32 units per LDS request x SM clock (one shared-memory request per clock per SM); the DADD pipe allows twice that",
+            "peak_source": "SMs x 16 units per clock x SM clock: one 128-byte shared-memory wavefront per clock per SM, two wavefronts per warp-wide 8-byte load (one unit per lane); the DADD pipe allows four times that",
             "algorithmic_tflops_equivalent": pre_tflops, "units_per_launch": units,
             "note": "query-lane log-table form (prefilter_qlane.cuh): lane = query, warp = 32 queries x 32 edges, table tile streamed by TMA bulk copies; "
                     "no FP64 fraction is claimed for it; roofline.prefilter_direct carries the FMA form the FP64 roofline is defined on",

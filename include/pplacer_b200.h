@@ -145,6 +145,12 @@ int pp_precompute(pp_ctx *);
 int pp_refine_site_categories(pp_ctx *, int32_t *site_cat_out, double *site_ll_out);
 /* --check-like (pplacer_run.ml:344-377): out [n_nodes x 2] = (tree_likelihood, supernode_like) seen from every edge. */
 int pp_check_like(pp_ctx *, double *out);
+/* Maximum a posteriori states on the proximal side of internal nodes, what --map-mrca / --map-identity read
+ * (Map_seq.of_map, map_seq.ml:17-37 -> Seq_post.get_summary Proximal, seq_post.ml:14-31): out [n_ids x L] receives
+ * per site the index of the most likely state of statd .* evolve(darr[id], bl[id]) .* parr[id] summed over the rates,
+ * or -1 when its posterior share is below `cutoff` (Prefs.map_cutoff).  The MRCA bookkeeping around it
+ * (Refpkg.get_mrcam, Map_seq.mrca_map_seq_map) needs the refpkg taxonomy and stays with the host. */
+int pp_map_states(pp_ctx *, int32_t n_ids, const int32_t *ids, double cutoff, int8_t *out);
 /* Copy GLVs [node_begin, node_end) of darr (which=0) / parr (1) / snodes (2) back in the REFERENCE
  * layout: Gmix a[R][L][S], Gcat a[L][S] per node (linear_c.c:5-12); e[L] as int64 per node. */
 int pp_export_glvs(pp_ctx *, int32_t which, int32_t node_begin, int32_t node_end, double *a, int64_t *e);

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "pp_kernel_launches", "pp_phase_times_ms", "pp_measure_fp64_peak", "pp_set_stream",
     "pp_set_prefilter_kernel", "pp_prefilter_kernel_used", "pp_set_three_tax_engine", "pp_three_tax_engine_used", "pp_three_tax_work", "pp_three_tax_profile", "pp_set_rank_mode", "pp_rank_fallbacks",
     "pp_create_multi", "pp_destroy_multi", "pp_multi_precompute", "pp_multi_place", "pp_multi_n_devices", "pp_multi_ctx",
-    "pp_multi_last_counts", "pp_refine_site_categories", "pp_check_like", "pp_set_figs", "pp_n_figs",
+    "pp_multi_last_counts", "pp_refine_site_categories", "pp_check_like", "pp_map_states", "pp_set_figs", "pp_n_figs",
 ]
 
 
@@ -119,6 +119,7 @@ def load():
     L.pp_n_figs.argtypes = [C.c_void_p]
     L.pp_refine_site_categories.argtypes = [C.c_void_p, c_i32_p, c_double_p]
     L.pp_check_like.argtypes = [C.c_void_p, c_double_p]
+    L.pp_map_states.argtypes = [C.c_void_p, C.c_int32, c_i32_p, C.c_double, C.POINTER(C.c_int8)]
     L.pp_create_multi.argtypes = [C.POINTER(Model), C.POINTER(Tree), c_u8_p, C.c_int32, C.c_int32, C.c_int32, c_i32_p,
                                   C.POINTER(C.c_void_p)]
     L.pp_destroy_multi.argtypes = [C.c_void_p]

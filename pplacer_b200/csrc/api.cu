@@ -1730,6 +1730,72 @@ extern "C" int pp_multi_last_counts(pp_multi *m, int64_t *per_device) {
 // other and across nodes.  An all-ones query (N / X) evolves to the unit vector for any pendant length (rows of P sum
 // to one), so the two columns are Three_tax.log_like and the prefilter score of that query.  out: n_nodes x 2
 // (tree_likelihood, supernode_like); the supernode column is NaN at the root.
+// Seq_post.get_summary Proximal (seq_post.ml:14-31) with Map_seq.of_map's bounded_max_index (map_seq.ml:22-25) and
+// Glv.summarize_post (gmix_model.ml:241-256 / gcat_model.ml): per site the most likely state of
+//   statd .* evolve(darr[id], bl[id]) .* parr[id]   summed over the rates,
+// or -1 when its share of the total is below the cutoff.  One block per node.
+template <int S, bool GCAT>
+__global__ void __launch_bounds__(128)
+map_states_kernel(const DevModel *__restrict__ m, GlvArrays g, const double *__restrict__ bl, const int32_t *__restrict__ site_cat,
+                  const int32_t *__restrict__ ids, double cutoff, int Rt, int8_t *__restrict__ out) {
+  extern __shared__ double sm_map[];
+  constexpr int RS = S * S;
+  double *ex = sm_map, *P = sm_map + Rt * S;
+  const int id = ids[blockIdx.x];
+  block_build_P<S>(m, Rt, bl[id], P, RS, ex);
+  const double *dbase = g.a[0] + (int64_t)id * g.a_stride, *pbase = g.a[1] + (int64_t)id * g.a_stride;
+  for (int site = threadIdx.x; site < g.L; site += blockDim.x) {
+    double u[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) u[s] = 0.0;
+    const int cat = GCAT ? site_cat[site] : 0;
+    for (int r = 0; r < (GCAT ? 1 : Rt); ++r) {
+      const double *Pr = P + (GCAT ? cat : r) * RS;
+      double d[S];
+#pragma unroll
+      for (int j = 0; j < S; ++j) d[j] = dbase[(int64_t)(r * S + j) * g.Lp + site];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        double ev = 0.0;
+#pragma unroll
+        for (int j = 0; j < S; ++j) ev = fma(Pr[s * S + j], d[j], ev);
+        u[s] += (m->statd[s] * ev) * pbase[(int64_t)(r * S + s) * g.Lp + site];  // statd_pairwise_prod, linear_c.c:148-206
+      }
+    }
+    int best = 0;
+    double tot = fabs(u[0]);
+#pragma unroll
+    for (int s = 1; s < S; ++s) { if (u[s] > u[best]) best = s; tot += fabs(u[s]); }  // Gsl.Vector.max_index: the first maximum
+    out[(int64_t)blockIdx.x * g.L + site] = (u[best] / tot < cutoff) ? (int8_t)-1 : (int8_t)best;
+  }
+}
+
+extern "C" int pp_map_states(pp_ctx *c, int32_t n_ids, const int32_t *ids, double cutoff, int8_t *out) {
+  if (!c || !ids || !out || n_ids < 1) return fail(PP_EINVAL, "pp_map_states: bad arguments");
+  if (!c->precomputed) return fail(PP_ESTATE, "pp_map_states: call pp_precompute first");
+  for (int i = 0; i < n_ids; ++i)
+    if (ids[i] < 0 || ids[i] >= c->n_nodes || ids[i] == c->root_id) return fail(PP_EINVAL, "pp_map_states: node id out of range (or the root, which has no proximal side)");
+  CK(cudaSetDevice(c->device));
+  int rc;
+  DevBuf<int32_t> d_ids;
+  DevBuf<int8_t> d_out;
+  if ((rc = d_ids.ensure(n_ids)) || (rc = d_out.ensure((size_t)n_ids * c->L))) { d_ids.release(); d_out.release(); return rc; }
+  cudaMemcpyAsync(d_ids.p, ids, sizeof(int32_t) * n_ids, cudaMemcpyHostToDevice, c->stream);
+  const size_t smb = (size_t)(c->R * c->S + c->R * c->S * c->S) * sizeof(double);
+  cudaError_t e = cudaSuccess;
+  DISPATCH_MODEL(c, {
+    e = cudaFuncSetAttribute(map_states_kernel<S_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+    if (e == cudaSuccess) map_states_kernel<S_, G_><<<n_ids, 128, smb, c->stream>>>(c->dm, c->g, c->d_bl, c->d_site_cat, d_ids.p, cutoff, c->R, d_out.p);
+  });
+  c->launches += 1;
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out.p, (size_t)n_ids * c->L, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  d_ids.release(); d_out.release();
+  if (e != cudaSuccess) return fail(PP_ECUDA, std::string("pp_map_states: ") + cudaGetErrorString(e));
+  return PP_OK;
+}
+
 extern "C" int pp_check_like(pp_ctx *c, double *out) {
   if (!c || !out) return fail(PP_EINVAL, "pp_check_like: bad arguments");
   if (!c->precomputed) return fail(PP_ESTATE, "pp_check_like: call pp_precompute first");

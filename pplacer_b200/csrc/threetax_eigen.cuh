@@ -297,31 +297,36 @@ struct TTEig {
     }
   }
 
-  // Running product of per-site likelihoods as (mantissa product, exponent sum).  Unlike WarpProd (threetax_warp.cuh)
-  // the factor's exponent is split off BEFORE the multiplication, so the chain from site to site is ONE DMUL
-  // (8 cycles, tools/micro/lat.cu) and the running mantissa product only grows: renorm() every <= 512 factors.
+  // Running product of per-site likelihoods as (product, exponent sum).  A factor inside [2^-120, 2^120) - every
+  // factor of a well-conditioned problem - is multiplied in as it is: one integer range test and ONE DMUL per factor
+  // (the chain from site to site is 8 cycles, tools/micro/lat.cu); the callers renorm() at least every 8 factors, so
+  // the product stays inside the double range.  Anything else takes the exact path below.
   struct SiteProd {
     double m;
     int e;
     __device__ __forceinline__ void init() { m = 1.0; e = 0; }
     __device__ __forceinline__ void mul(double u, double *bad_slot) {
       int hi = __double2hiint(u);
-      int ef = (hi >> 20) & 0x7ff;
-      if (hi < 0 || ef == 0 || ef == 0x7ff) {
-        // zero / negative / NaN / inf / subnormal factor (rare; inline - a call here would spill every value that is live
-        // across the site loop): subnormals are rescaled exactly, the rest add log(u) = -inf / NaN / +inf to the point's
-        // shared slot (linear_c.c:418 sums log(util)) and leave the product alone
-        if (u > 0.0 && u < 2.2250738585072014e-308) { u *= 0x1p600; e -= 600; }
-        else {
-          const double inf = __longlong_as_double(0x7ff0000000000000LL);
-          atomicAdd(bad_slot, u == 0.0 ? -inf : (u == inf ? inf : __longlong_as_double(0x7ff8000000000000LL)));
-          u = 1.0;
+      if ((unsigned)(hi - ((1023 - 120) << 20)) >= (unsigned)(240 << 20)) {
+        // zero / negative / NaN / inf / subnormal / far-out-of-range factor (rare; inline - a call here would spill every
+        // value that is live across the site loop): subnormals are rescaled exactly, zero / negative / non-finite values
+        // add log(u) = -inf / NaN / +inf to the point's shared slot (linear_c.c:418 sums log(util)) and leave the product
+        // alone; what remains is a normal number, whose exponent is split off exactly
+        int ef = (hi >> 20) & 0x7ff;
+        if (hi < 0 || ef == 0 || ef == 0x7ff) {
+          if (u > 0.0 && u < 2.2250738585072014e-308) { u *= 0x1p600; e -= 600; }
+          else {
+            const double inf = __longlong_as_double(0x7ff0000000000000LL);
+            atomicAdd(bad_slot, u == 0.0 ? -inf : (u == inf ? inf : __longlong_as_double(0x7ff8000000000000LL)));
+            u = 1.0;
+          }
+          hi = __double2hiint(u);
+          ef = (hi >> 20) & 0x7ff;
         }
-        hi = __double2hiint(u);
-        ef = (hi >> 20) & 0x7ff;
+        e += ef - 1023;
+        u = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(u));
       }
-      e += ef - 1023;
-      m *= __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(u));
+      m *= u;
     }
     __device__ __forceinline__ void renorm() {
       const int hi = __double2hiint(m);
@@ -517,7 +522,7 @@ struct TTEig {
         }
         pk[t] = pk1[t]; pk1[t] = pk2[t];
       }
-      if (!BUILD && (iter & 255) == 255) {
+      if (!BUILD && (iter & (8 / T - 1)) == 8 / T - 1) {  // every 8 factors (SiteProd)
 #pragma unroll
         for (int b = 0; b < NB; ++b) lp[b].renorm();
       }
@@ -577,7 +582,15 @@ struct TTEig {
 #pragma unroll
     for (int j = 0; j < NE; ++j) E1[j] = NB == 1 ? s[OFF_E + j] : 0.0;
     const int n_sm = min(c.nq, WS);
-    int i = tid;
+    int i = tid, nf = 0;  // nf: factors since the last renorm (SiteProd: at most 8)
+    auto tick = [&](int k) {
+      nf += k;
+      if (nf >= 7) {
+        nf = 0;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) lp[b].renorm();
+      }
+    };
     if (NB == 1) {
       for (; i + NT < n_sm; i += 2 * NT) {  // two sites per trip: independent chains
         double ya[NY], yb[NY];
@@ -585,6 +598,7 @@ struct TTEig {
         for (int j = 0; j < NY; ++j) { ya[j] = Y[j * WS + i]; yb[j] = Y[j * WS + i + NT]; }
         pend_site<NB>(ya, E1, lp, bad);
         pend_site<NB>(yb, E1, lp, bad);
+        tick(2);
       }
     }
     for (; i < n_sm; i += NT) {
@@ -592,21 +606,18 @@ struct TTEig {
 #pragma unroll
       for (int j = 0; j < NY; ++j) y[j] = Y[j * WS + i];
       pend_site<NB>(y, E1, lp, bad);
+      tick(1);
     }
 #pragma unroll
     for (int o = 0; o < PF; ++o)
-      if (io + o * NT < c.nq) pend_site<NB>(yo[o], E1, lp, bad);
-    int iter = 0;
-    for (int i2 = io + PF * NT; i2 < c.nq; i2 += NT, ++iter) {
+      if (io + o * NT < c.nq) { pend_site<NB>(yo[o], E1, lp, bad); tick(1); }
+    for (int i2 = io + PF * NT; i2 < c.nq; i2 += NT) {
       double y[NY];
       const double *yp = c.wg + i2;
 #pragma unroll
       for (int j = 0; j < NY; ++j) y[j] = __ldcg(yp + (int64_t)j * c.Lp);
       pend_site<NB>(y, E1, lp, bad);
-      if ((iter & 255) == 255) {
-#pragma unroll
-        for (int b = 0; b < NB; ++b) lp[b].renorm();
-      }
+      tick(1);
     }
     pass_end<NB>(lp);
   }

@@ -183,6 +183,15 @@ class Placer:
         _lib.check(_lib.load().pp_check_like(self.ctx, _lib.dp(out)))
         return out
 
+    def map_states(self, node_ids, cutoff: float = 0.8) -> np.ndarray:
+        """Map_seq.of_map (map_seq.ml:17-37): int8[len(node_ids), L], per site the MAP state on the proximal side of
+        each node or -1 below `cutoff` (Prefs.map_cutoff, 0.8) - what --map-mrca / --map-identity read."""
+        ids = np.ascontiguousarray(node_ids, dtype=np.int32)
+        out = np.zeros((len(ids), self.L), dtype=np.int8)
+        _lib.check(_lib.load().pp_map_states(self.ctx, len(ids), ids.ctypes.data_as(_lib.c_i32_p), float(cutoff),
+                                             out.ctypes.data_as(_lib.C.POINTER(_lib.C.c_int8))))
+        return out
+
     def model_numerics(self):
         S, R = self.S, self.R
         statd, x, lam, xit, rates = np.zeros(S), np.zeros((S, S)), np.zeros(S), np.zeros((S, S)), np.zeros(R)

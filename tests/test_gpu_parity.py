@@ -653,6 +653,39 @@ def test_check_like_table(name):
 # ---------------------------------------------------------------------------------------------
 # fig ranking (--fig-cutoff)
 # ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["c1_gtr", "wag", "gcat_dna", "gcat_aa"])
+def test_map_states_match_the_posterior_of_the_oracle_glvs(oracle_binding, name):
+    """pp_map_states (Map_seq.of_map, map_seq.ml:17-37; Seq_post.get_summary Proximal, seq_post.ml:14-31) against a numpy
+    restatement on the ORACLE's darr / parr: statd .* evolve(darr[id], bl[id]) .* parr[id], summed over the rates,
+    arg-max per site, -1 below the cutoff."""
+    prob, o, p = setup(name, oracle_binding)
+    mn = p.model_numerics()
+    t = prob.tree
+    ids = [i for i in t.nonroot_ids()][:: max(1, len(t.nonroot_ids()) // 6)][:6]
+    cutoff = 0.8
+    got = p.map_states(ids, cutoff)
+    gcat = prob.model.model_class == 1
+    for row, nid in zip(got, ids):
+        ad, _ = o.glv(0, nid)
+        ap, _ = o.glv(1, nid)
+        P = oracle_binding.multi_exp(mn["x"], mn["lam"], mn["xit"], mn["rates"], float(t.bl[nid]))
+        if gcat:
+            ev = np.einsum("lsj,lj->ls", P[prob.site_cat], ad)
+            u = mn["statd"][None, :] * ev * ap
+        else:
+            ev = np.einsum("rsj,rlj->rls", P, ad)
+            u = (mn["statd"][None, None, :] * ev * ap).sum(axis=0)
+        best = u.argmax(axis=1)
+        share = u.max(axis=1) / np.abs(u).sum(axis=1)
+        want = np.where(share < cutoff, -1, best)
+        srt = np.sort(u, axis=1)
+        clear = (np.abs(share - cutoff) > 1e-9) & ((srt[:, -1] - srt[:, -2]) > 1e-12 * np.abs(srt[:, -1]))
+        assert clear.mean() > 0.9
+        assert np.array_equal(row[clear], want[clear]), (name, nid, int((row[clear] != want[clear]).sum()))
+        assert (row >= -1).all() and (row < p.S).all()
+
+
 @pytest.mark.parametrize("name,cutoffs", [("c1_gtr", (0.05, 0.3)), ("synth", (0.05, 0.2, 1.0)), ("gcat_aa", (0.2,)), ("wag", (0.3,))])
 def test_fig_ranking_matches_oracle(oracle_binding, name, cutoffs):
     """Fig._enum_by_score on the device (fig.cuh): representatives scored for every query, groups of figs expanded and
