@@ -38,10 +38,12 @@ def _buf(key, nbytes, device=None, pin=False):
 
 
 def gather_results(out: np.ndarray, n_out: np.ndarray, status: np.ndarray, Q: int, rank: int, world: int,
-                   device: Optional[str] = None):
+                   device: Optional[str] = None, reuse: bool = False):
     """Gather per-rank (results[Qr,K], n_out[Qr], status[Qr]) to rank 0 in query order: ONE collective
     (torch.distributed gather: NCCL on GPUs, gloo in the CPU tests) of one byte row per rank - the pp_result records,
-    then the counts, then the status words.  Returns the full arrays on rank 0 and None elsewhere."""
+    then the counts, then the status words.  Returns the full arrays on rank 0 and None elsewhere.
+    reuse=True hands back arrays that the NEXT call overwrites (a loop that gathers every step need not pay for
+    fresh 4 MB-per-rank allocations and their page faults each time)."""
     import torch
     import torch.distributed as dist
 
@@ -76,9 +78,15 @@ def gather_results(out: np.ndarray, n_out: np.ndarray, status: np.ndarray, Q: in
     else:
         host = recv
     hv = host.numpy().reshape(world, row)
-    full = np.zeros((Q, K), dtype=_lib.RESULT_DTYPE)
-    full_n = np.zeros(Q, dtype=np.int32)
-    full_s = np.zeros(Q, dtype=np.int32)
+    if reuse:
+        key = ("full", Q, K)
+        if key not in _bufs:
+            _bufs[key] = (np.zeros((Q, K), dtype=_lib.RESULT_DTYPE), np.zeros(Q, dtype=np.int32), np.zeros(Q, dtype=np.int32))
+        full, full_n, full_s = _bufs[key]
+    else:
+        full = np.zeros((Q, K), dtype=_lib.RESULT_DTYPE)
+        full_n = np.zeros(Q, dtype=np.int32)
+        full_s = np.zeros(Q, dtype=np.int32)
     for r in range(world):
         lo, hi = shard_range(Q, r, world)
         m = hi - lo
