@@ -74,6 +74,21 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+// scope guards: a failing CK(...) returns from the middle of a function; what was allocated before it is released here
+struct DevFree {
+  void **pp;
+  explicit DevFree(void **p) : pp(p) {}
+  ~DevFree() { if (*pp) { cudaFree(*pp); *pp = nullptr; } }
+  DevFree(const DevFree &) = delete;
+};
+struct CtxGuard {  // pp_create: destroys the half-built context unless release() was reached
+  pp_ctx *c;
+  explicit CtxGuard(pp_ctx *c_) : c(c_) {}
+  ~CtxGuard();
+  void release() { c = nullptr; }
+  CtxGuard(const CtxGuard &) = delete;
+};
+
 constexpr int kTTThreadsDNA = 128;
 constexpr int kTTThreadsAA = 256;
 
@@ -236,6 +251,8 @@ extern "C" void pp_destroy(pp_ctx *c) {
   delete c;
 }
 
+CtxGuard::~CtxGuard() { if (c) pp_destroy(c); }
+
 extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref_chars, int32_t n_leaves, int32_t L,
                          int32_t device, pp_ctx **out) {
   if (!m || !t || !ref_chars || !out) return fail(PP_EINVAL, "pp_create: null argument");
@@ -257,6 +274,7 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
   if (device < 0 || device >= ndev) return fail(PP_EINVAL, "pp_create: bad device index");
   CK(cudaSetDevice(device));
   pp_ctx *c = new pp_ctx();
+  CtxGuard guard(c);  // every early return below destroys the half-built context
   c->device = device;
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   c->S = m->n_states; c->gcat = m->model_class ? 1 : 0; c->R = m->n_rates; c->Rg = c->gcat ? 1 : c->R; c->K = c->Rg * c->S;
@@ -268,8 +286,8 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
   hm.S = c->S; hm.R = c->R; hm.Rg = c->Rg; hm.K = c->K; hm.gcat = c->gcat; hm.n_codes = c->al.n_codes; hm.any_code = c->al.any_code;
   if (m->statd) std::memcpy(hm.statd, m->statd, sizeof(double) * c->S);
   else {
-    if (!m->statd_chars) { delete c; return fail(PP_EINVAL, "pp_create: neither statd nor statd_chars given"); }
-    if (!emper_freq(c->S, m->statd_chars, m->n_statd_chars, hm.statd)) { delete c; return fail(PP_EINVAL, "pp_create: unknown base in reference alignment"); }
+    if (!m->statd_chars) return fail(PP_EINVAL, "pp_create: neither statd nor statd_chars given");
+    if (!emper_freq(c->S, m->statd_chars, m->n_statd_chars, hm.statd)) return fail(PP_EINVAL, "pp_create: unknown base in reference alignment");
   }
   diagd_normed(c->S, m->exch, hm.statd, hm.x, hm.lam, hm.xit);
   if (m->rates) std::memcpy(hm.rates, m->rates, sizeof(double) * c->R);
@@ -284,7 +302,7 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
   for (int i = 0; i < t->n_nodes; ++i)
     for (int k = c->child_ptr[i]; k < c->child_ptr[i + 1]; ++k) {
       const int ch = c->child_idx[k];
-      if (ch < 0 || ch >= t->n_nodes || c->parent[ch] != -1 || ch == t->root_id) { delete c; return fail(PP_EINVAL, "pp_create: malformed tree"); }
+      if (ch < 0 || ch >= t->n_nodes || c->parent[ch] != -1 || ch == t->root_id) return fail(PP_EINVAL, "pp_create: malformed tree");
       c->parent[ch] = i;
     }
   c->depth.assign(t->n_nodes, -1);
@@ -296,28 +314,28 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
       const int v = stack.back(); stack.pop_back(); ++seen;
       for (int k = c->child_ptr[v]; k < c->child_ptr[v + 1]; ++k) { c->depth[c->child_idx[k]] = c->depth[v] + 1; stack.push_back(c->child_idx[k]); }
     }
-    if ((int)seen != t->n_nodes) { delete c; return fail(PP_EINVAL, "pp_create: tree is not connected"); }
+    if ((int)seen != t->n_nodes) return fail(PP_EINVAL, "pp_create: tree is not connected");
   }
   for (int i = 0; i < t->n_nodes; ++i) {
     const bool leaf = c->child_ptr[i] == c->child_ptr[i + 1];
-    if (leaf && (c->leaf_row[i] < 0 || c->leaf_row[i] >= n_leaves)) { delete c; return fail(PP_EINVAL, "pp_create: leaf without alignment row"); }
+    if (leaf && (c->leaf_row[i] < 0 || c->leaf_row[i] >= n_leaves)) return fail(PP_EINVAL, "pp_create: leaf without alignment row");
   }
   // ---- reference alignment -> codes ----
   std::vector<uint8_t> codes((size_t)n_leaves * c->Lp, (uint8_t)(c->al.any_code | kGapBit));
   for (int r = 0; r < n_leaves; ++r)
     for (int s = 0; s < L; ++s) {
       const uint8_t code = c->al.code_of_char[ref_chars[(size_t)r * L + s]];
-      if (code == kBadCode) { delete c; return fail(PP_EINVAL, std::string("pp_create: '") + (char)ref_chars[(size_t)r * L + s] + "' is not a known base in the reference alignment"); }
+      if (code == kBadCode) return fail(PP_EINVAL, std::string("pp_create: '") + (char)ref_chars[(size_t)r * L + s] + "' is not a known base in the reference alignment");
       codes[(size_t)r * c->Lp + s] = code;
     }
   std::vector<int32_t> cat(c->Lp, 0);
   if (c->gcat)
     for (int s = 0; s < L; ++s) {
-      if (m->site_cat[s] < 0 || m->site_cat[s] >= c->R) { delete c; return fail(PP_EINVAL, "pp_create: site category out of range"); }
+      if (m->site_cat[s] < 0 || m->site_cat[s] >= c->R) return fail(PP_EINVAL, "pp_create: site category out of range");
       cat[s] = m->site_cat[s];
     }
   int rc;
-#define UP(dst, src, n) if ((rc = upload(&(dst), (src), (n))) != PP_OK) { pp_destroy(c); return rc; }
+#define UP(dst, src, n) if ((rc = upload(&(dst), (src), (n))) != PP_OK) return rc;
   CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   CK(cudaEventCreate(&c->ev[0]));
@@ -336,7 +354,7 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
   for (int w = 0; w < 3; ++w) {
     cudaError_t e1 = cudaMalloc(&c->g.a[w], sizeof(double) * (size_t)c->g.a_stride * c->n_nodes);
     cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(&c->g.e[w], sizeof(int32_t) * (size_t)c->Lp * c->n_nodes) : e1;
-    if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaGetLastError(); pp_destroy(c); return fail(PP_ENOMEM, "pp_create: not enough device memory for darr/parr/snodes"); }
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaGetLastError(); return fail(PP_ENOMEM, "pp_create: not enough device memory for darr/parr/snodes"); }
     cudaMemsetAsync(c->g.a[w], 0, sizeof(double) * (size_t)c->g.a_stride * c->n_nodes, c->stream);
     cudaMemsetAsync(c->g.e[w], 0, sizeof(int32_t) * (size_t)c->Lp * c->n_nodes, c->stream);
   }
@@ -344,12 +362,12 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
   {
     cudaError_t e1 = cudaMalloc(&c->snT_a, sizeof(double) * (size_t)c->L * c->K * c->Np);
     cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(&c->snT_e, sizeof(int32_t) * (size_t)c->L * c->Np) : e1;
-    if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaGetLastError(); pp_destroy(c); return fail(PP_ENOMEM, "pp_create: not enough device memory for the prefilter copy of the supernodes"); }
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaGetLastError(); return fail(PP_ENOMEM, "pp_create: not enough device memory for the prefilter copy of the supernodes"); }
   }
   c->t.child_ptr = c->d_child_ptr; c->t.child_idx = c->d_child_idx; c->t.parent = c->d_parent; c->t.leaf_row = c->d_leaf_row;
   c->t.ref_codes = c->d_ref_codes; c->t.site_cat = c->d_site_cat;
   CK(cudaMallocHost(&c->h_counters, 8 * sizeof(int)));
-  if ((rc = c->counters.ensure(8)) != PP_OK || (rc = c->tt_work.ensure(32)) != PP_OK) { pp_destroy(c); return rc; }
+  if ((rc = c->counters.ensure(8)) != PP_OK || (rc = c->tt_work.ensure(32)) != PP_OK) return rc;
   CK(cudaMemsetAsync(c->tt_work.p, 0, 32 * sizeof(unsigned long long), c->stream));
   // QNG tables -> constant memory
   cudaMemcpyToSymbol(c_qng_x1, ppb_qng_x1, sizeof ppb_qng_x1); cudaMemcpyToSymbol(c_qng_w10, ppb_qng_w10, sizeof ppb_qng_w10);
@@ -363,7 +381,7 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
     c->tt_smem = tt_smem_bytes<S_, G_>(c);
     constexpr int TH = (S_ == 4) ? kTTThreadsDNA : kTTThreadsAA;
     auto kern = three_tax_kernel<S_, G_, TH>;
-    if (c->tt_smem > 227 * 1024) { pp_destroy(c); return fail(PP_EINVAL, "pp_create: model too large for shared memory (rates x states^2)"); }
+    if (c->tt_smem > 227 * 1024) return fail(PP_EINVAL, "pp_create: model too large for shared memory (rates x states^2)");
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tt_smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TH, c->tt_smem));
@@ -412,9 +430,10 @@ extern "C" int pp_create(const pp_model *m, const pp_tree *t, const uint8_t *ref
   }
   // Gcat: per block w + the compact distal / proximal copies, rows of LpC = the padded (category, site) list capacity
   c->LpC = c->gcat ? ((c->Lp + 32 * (int64_t)c->R + 31) / 32) * 32 : c->Lp;
-  if ((rc = c->wbuf.ensure(c->gcat ? w_slots * 3 * c->K * c->LpC : w_slots * c->K * c->Lp)) != PP_OK) { pp_destroy(c); return rc; }
+  if ((rc = c->wbuf.ensure(c->gcat ? w_slots * 3 * c->K * c->LpC : w_slots * c->K * c->Lp)) != PP_OK) return rc;
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaGetLastError());
+  guard.release();
   *out = c;
   return PP_OK;
 }
@@ -523,6 +542,8 @@ extern "C" int pp_precompute(pp_ctx *c) {
   const int Rt = c->R;
   const size_t pm = (size_t)c->n_nodes * Rt * c->S * c->S;
   double *Pfull = nullptr, *Phalf = nullptr;
+  int32_t *d_levels = nullptr;
+  DevFree g_pfull(reinterpret_cast<void **>(&Pfull)), g_phalf(reinterpret_cast<void **>(&Phalf)), g_levels(reinterpret_cast<void **>(&d_levels));
   CK(cudaMalloc(&Pfull, pm * sizeof(double)));
   CK(cudaMalloc(&Phalf, pm * sizeof(double)));
   // level lists
@@ -533,7 +554,6 @@ extern "C" int pp_precompute(pp_ctx *c) {
   std::vector<int32_t> flat; std::vector<int> off(max_depth + 2, 0);
   for (int d = 0; d <= max_depth; ++d) { off[d] = (int)flat.size(); flat.insert(flat.end(), levels[d].begin(), levels[d].end()); }
   off[max_depth + 1] = (int)flat.size();
-  int32_t *d_levels = nullptr;
   CK(cudaMalloc(&d_levels, flat.size() * sizeof(int32_t)));
   CK(cudaMemcpyAsync(d_levels, flat.data(), flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   const int tiles = (c->L + kPreThreads - 1) / kPreThreads;
@@ -590,7 +610,7 @@ extern "C" int pp_precompute(pp_ctx *c) {
     }
   }
   cudaError_t e = cudaStreamSynchronize(c->stream);
-  cudaFree(Pfull); cudaFree(Phalf); cudaFree(d_levels);
+  // Pfull, Phalf, d_levels: released by their guards
   if (e != cudaSuccess) return fail(PP_ECUDA, std::string("pp_precompute: ") + cudaGetErrorString(e));
   if (rc != PP_OK) return rc;
   c->precomputed = true;
@@ -1523,6 +1543,7 @@ extern "C" int pp_evolve(pp_ctx *c, const double *src_a, const int64_t *src_e, i
     for (int site = 0; site < n; ++site)
       for (int s = 0; s < c->S; ++s) h[(size_t)(r * c->S + s) * np + site] = src_a[((size_t)r * n + site) * c->S + s];
   double *d_src = nullptr, *d_dst = nullptr;
+  DevFree g_src(reinterpret_cast<void **>(&d_src)), g_dst(reinterpret_cast<void **>(&d_dst));
   CK(cudaMalloc(&d_src, h.size() * sizeof(double)));
   CK(cudaMalloc(&d_dst, h.size() * sizeof(double)));
   CK(cudaMemcpy(d_src, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -1534,7 +1555,6 @@ extern "C" int pp_evolve(pp_ctx *c, const double *src_a, const int64_t *src_e, i
   });
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaMemcpy(h.data(), d_dst, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  cudaFree(d_src); cudaFree(d_dst);
   for (int r = 0; r < c->Rg; ++r)
     for (int site = 0; site < n; ++site)
       for (int s = 0; s < c->S; ++s) dst_a[((size_t)r * n + site) * c->S + s] = h[(size_t)(r * c->S + s) * np + site];
