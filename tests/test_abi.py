@@ -89,3 +89,18 @@ def test_product_does_not_touch_oracle():
     for path in glob.glob(os.path.join(ROOT, "pplacer_b200", "**", "*"), recursive=True):
         if os.path.isfile(path) and path.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
             assert not pat.search(open(path, errors="replace").read()), path
+
+
+def test_library_is_sm100a_with_tensor_core_and_tma_instructions():
+    """The shipped binary is sm_100a SASS and holds what DESIGN.md 3.2 claims for the staged prefilter forms and the
+    query-lane table: FP64 tensor-core MMAs (DMMA), TMA bulk copies (UBLKCP = cp.async.bulk) and mbarrier waits (SYNCS)."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    lib = _lib.lib_path()
+    arch = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in arch, arch
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout   # ~10 s
+    assert "prefilter_staged_kernel" in sass and "prefilter_qlane_kernel" in sass and "tt_eigen_kernel" in sass
+    assert "DMMA.8x8x4" in sass and "UBLKCP" in sass and "SYNCS" in sass
