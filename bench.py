@@ -277,7 +277,7 @@ def run_ours(args):
     K = prefs.keep_at_most
     stream = torch.cuda.Stream(device=dev)
     p.set_stream(stream.cuda_stream)
-    p.set_prefilter_kernel({"default": 0, "direct": 1, "table": 2, "staged": 4, "dmma": 5, "logtable": 6, "qlane": 7}[args.prefilter])
+    p.set_prefilter_kernel({"default": 0, "direct": 1, "table": 2, "staged": 4, "dmma": 5, "logtable": 6, "qlane": 7, "pairs": 8}[args.prefilter])
     p.set_three_tax_engine({"default": 0, "block": 1, "warp": 2, "group": 3, "eigen": 4}[args.tt_engine], args.tt_blocks_per_sm)
     n_figs = p.set_figs(cutoff=args.fig_cutoff) if args.fig_cutoff > 0 else 0
     fp64_peak = p.measure_fp64_peak()
@@ -381,7 +381,7 @@ def run_ours(args):
     pre_ms = share["prefilter"]
     pre_tflops = pre_flops / (pre_ms * 1e-3) / 1e12 if pre_ms > 0 else 0.0
     used = p.prefilter_kernel_used()
-    kname = {1: "prefilter_direct_kernel", 2: "prefilter_table_kernel", 4: "prefilter_staged_kernel<MMA=false>", 5: "prefilter_staged_kernel<MMA=true>", 6: "prefilter_logtable_kernel", 7: "prefilter_qlane_kernel"}.get(used, "?")
+    kname = {1: "prefilter_direct_kernel", 2: "prefilter_table_kernel", 4: "prefilter_staged_kernel<MMA=false>", 5: "prefilter_staged_kernel<MMA=true>", 6: "prefilter_logtable_kernel", 7: "prefilter_qlane_kernel", 8: "prefilter_qlane_kernel<NC=36> (pair-of-sites table)"}.get(used, "?")
     # compulsory HBM bytes: one pass over the prefilter copy of the supernodes + query codes + scores
     pre_bytes = (8.0 * (4 if used == 2 else R * S) + 4.0) * p.L * (E + 1) + Q * p.L + 8.0 * Q * (E + 1)
     if args.workload == "c3" and used == 1:
@@ -413,12 +413,12 @@ def run_ours(args):
             "note": "table form: one select + one multiply per (query, edge, site) unit; issue-bound, not FP64-bound - no FP64 "
                     "fraction is claimed for it; roofline.prefilter_direct carries the FMA form the FP64 roofline is defined on",
         })
-    if used == 7:
+    if used in (7, 8):
         # query-lane log table: one shared-memory load (a broadcast request: <= 6 distinct words) and one DADD per
         # (query, edge, site) unit, no FMAs - its roof is the shared-memory pipe, one warp request per clock per SM
         # a warp-wide 8-byte shared-memory load is two 128-byte wavefronts, and the pipe moves one wavefront per clock
         # per SM: 16 units per clock per SM (ncu r5b / r5o: l1tex throughput 88 % at 0.78 of this figure)
-        lsu_peak = props.multi_processor_count * 16.0 * float(sm_mhz) * 1e6 / 1e9 if sm_mhz else None
+        lsu_peak = props.multi_processor_count * (32.0 if used == 8 else 16.0) * float(sm_mhz) * 1e6 / 1e9 if sm_mhz else None   # pair table: one word per TWO units
         ach = units / (pre_ms * 1e-3) / 1e9 if pre_ms > 0 else 0.0
         roofline_prefilter.update({
             "bound": "shared-memory bandwidth", "achieved": ach, "unit": "G units/s", "peak": lsu_peak,
@@ -428,8 +428,8 @@ def run_ours(args):
             "note": "query-lane log-table form (prefilter_qlane.cuh): lane = query, warp = 32 queries x 32 edges, table tile streamed by TMA bulk copies; "
                     "no FP64 fraction is claimed for it; roofline.prefilter_direct carries the FMA form the FP64 roofline is defined on",
         })
-        ncols = 6 if S == 4 else S + 2
-        roofline_prefilter["kernel"] = "prefilter_qlane_kernel" if S == 4 else "prefilter_qlane_kernel<NC=%d>" % ncols
+        ncols = (18 if used == 8 else 6) if S == 4 else S + 2   # columns per site
+        roofline_prefilter["kernel"] = kname if S == 4 else "prefilter_qlane_kernel<NC=%d>" % ncols
         roofline_prefilter["hbm"]["bytes_per_launch"] = 8.0 * ncols * p.L * (E + 1) + Q * p.L + 8.0 * Q * (E + 1)
         roofline_prefilter["hbm"]["achieved"] = roofline_prefilter["hbm"]["bytes_per_launch"] / (pre_ms * 1e-3) / 1e9 if pre_ms > 0 else 0.0
         roofline_prefilter["hbm"]["note"] = "compulsory bytes: one pass over the log table (6 columns DNA, 22 columns proteins) + query codes + scores"
@@ -558,7 +558,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = every rank places its own --queries; strong = one fixed set of --total-queries sharded over the ranks")
     ap.add_argument("--total-queries", type=int, default=0, help="--scaling strong: size of the fixed query set (default: --queries)")
-    ap.add_argument("--prefilter", default="default", choices=["default", "direct", "table", "staged", "dmma", "logtable", "qlane"],
+    ap.add_argument("--prefilter", default="default", choices=["default", "direct", "table", "staged", "dmma", "logtable", "qlane", "pairs"],
                     help="prefilter kernel: library default, the FMA form, or the four-base table form")
     ap.add_argument("--tt-engine", default="default", choices=["default", "block", "warp", "group", "eigen"],
                     help="second-stage engine: library default (group), block-per-candidate, warp-per-candidate, block + shared-memory w")

@@ -220,14 +220,16 @@ int pp_emper_freq(int32_t S, const uint8_t *chars, int64_t n, double *out);
 int pp_set_stream(pp_ctx *, void *cuda_stream);
 
 /* Which prefilter kernel pp_place uses (all forms give ten_masked_logdot_c / mat_masked_logdot_c, linear_c.c:465,251):
- * 0 = default: DNA Gamma-4 model - the query-lane log table (7) for batches of >= 256 queries, the four-base product
- *     table (2) below that; every other model - the direct FMA form (1);
+ * 0 = default: DNA Gamma-4 model - the pair-of-sites query-lane log table (8) for batches of >= 256 queries, the
+ *     four-base product table (2) below that; 20-state models and the other DNA models - the generic query-lane table (7)
+ *     for large batches, the direct FMA form (1) otherwise;
  * 1 = direct FMA form (K = rates*states DFMAs per query x edge x site, as the reference writes it; the form the FP64
  *     roofline is defined on), 3 = the same with the evolved-query table in shared memory;
  * 2 = four-base product table; 6 = log table, lanes walk edges; 7 = log table, lanes are queries (TMA-streamed tiles);
+ * 8 = the same with one table word per PAIR of adjacent sites (36 columns);
  * 4 = direct form staged through shared memory by TMA bulk copies + an mbarrier ring (DFMA), 5 = the same with the
- *     K contraction on the FP64 tensor cores (DMMA m8n8k4).  2 and 4-7 exist for the DNA Gamma-4 model only.
- * pp_prefilter_kernel_used reports what the last prefilter launch ran (1, 2, 4, 5, 6 or 7). */
+ *     K contraction on the FP64 tensor cores (DMMA m8n8k4).  2, 4-6 and 8 exist for the DNA Gamma-4 model only.
+ * pp_prefilter_kernel_used reports what the last prefilter launch ran (1, 2, 4, 5, 6, 7 or 8). */
 int pp_set_prefilter_kernel(pp_ctx *, int32_t kernel);
 int pp_prefilter_kernel_used(pp_ctx *);
 

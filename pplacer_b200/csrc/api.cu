@@ -119,6 +119,9 @@ struct pp_ctx {
   TqPrimary tqp;
   DevBuf<uint8_t> qc;
   DevBuf<double> LTq;               // query-lane log table [Np/32][L][32][6]
+  DevBuf<double> LTq2;              // pair-of-sites table [Np/32][ceil(L/2)][32][36]
+  DevBuf<int32_t> tile_lo2, tile_hi2;
+  double ltq2_pend = -1.0;
   DevBuf<uint32_t> qcol;            // column bytes of the sorted queries, four sites per word
   DevBuf<int32_t> slow_flag;
   double ltq_pend = -1.0;
@@ -165,14 +168,14 @@ struct pp_ctx {
   // figs (fig.cuh): host CSR, device copies, the representatives' supernode columns in prefilter layout
   std::vector<int32_t> fig_rep, fig_ptr, fig_idx;
   DevBuf<int32_t> d_fig_rep, d_fig_ptr, d_fig_idx, rep_e, fig_order, fig_i32, fig_pair_q, fig_pair_e, fig_pair_e2, fig_seg;
-  DevBuf<double> rep_a, rep_scores, rep_MT, rep_LT, rep_LTq;
+  DevBuf<double> rep_a, rep_scores, rep_MT, rep_LT, rep_LTq, rep_LTq2;
   DevBuf<int32_t> rep_MTe;
   DevBuf<uint32_t> fig_bits;
   DevBuf<unsigned long long> fig_keys, fig_keys2;
   DevBuf<uint8_t> fig_tmp;
   int64_t rep_Np = 0;
   bool rep_ready = false;
-  double rep_mt_pend = -1.0, rep_lt_pend = -1.0, rep_ltq_pend = -1.0;
+  double rep_mt_pend = -1.0, rep_lt_pend = -1.0, rep_ltq_pend = -1.0, rep_ltq2_pend = -1.0;
   // prefilter tiling: queries sorted by the window of sites they cover (prefilter.cuh window_keys_kernel)
   DevBuf<unsigned long long> win_keys, win_keys2;
   DevBuf<int32_t> win_vals, qorder, tile_lo, tile_hi;
@@ -231,7 +234,7 @@ extern "C" void pp_destroy(pp_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (int w = 0; w < 3; ++w) { if (c->g.a[w]) cudaFree(c->g.a[w]); if (c->g.e[w]) cudaFree(c->g.e[w]); }
   for (int w = 0; w < 2; ++w) if (c->g.ea[w]) cudaFree(c->g.ea[w]);
-  c->qsite_cat.release(); c->nqc.release(); c->cat_perm.release(); c->cat_start.release(); c->qc.release(); c->partial.release(); c->MT.release(); c->LT.release(); c->LTq.release(); c->qcol.release(); c->slow_flag.release(); c->MTe.release();
+  c->qsite_cat.release(); c->nqc.release(); c->cat_perm.release(); c->cat_start.release(); c->qc.release(); c->partial.release(); c->MT.release(); c->LT.release(); c->LTq.release(); c->LTq2.release(); c->tile_lo2.release(); c->tile_hi2.release(); c->qcol.release(); c->slow_flag.release(); c->MTe.release();
   void *ptrs[] = {c->snT_a, c->snT_e, c->dm, c->d_bl, c->d_code_of_char, c->d_ref_codes, c->d_site_cat, c->d_child_ptr, c->d_child_idx, c->d_parent, c->d_leaf_row};
   for (void *p : ptrs) if (p) cudaFree(p);
   c->chars.release(); c->codes.release(); c->sort_tmp.release(); c->qsite.release(); c->nq.release();
@@ -240,7 +243,7 @@ extern "C" void pp_destroy(pp_ctx *c) {
   c->ord_keys.release(); c->ord_vals.release(); c->ord_keys2.release(); c->ord_vals2.release(); c->ord_tmp.release();
   c->d_fig_rep.release(); c->d_fig_ptr.release(); c->d_fig_idx.release(); c->rep_e.release(); c->fig_order.release(); c->fig_i32.release();
   c->fig_pair_q.release(); c->fig_pair_e.release(); c->fig_pair_e2.release(); c->fig_seg.release(); c->rep_a.release(); c->rep_scores.release();
-  c->rep_MT.release(); c->rep_LT.release(); c->rep_LTq.release(); c->rep_MTe.release(); c->fig_bits.release(); c->fig_keys.release(); c->fig_keys2.release(); c->fig_tmp.release();
+  c->rep_MT.release(); c->rep_LT.release(); c->rep_LTq.release(); c->rep_LTq2.release(); c->rep_MTe.release(); c->fig_bits.release(); c->fig_keys.release(); c->fig_keys2.release(); c->fig_tmp.release();
   c->win_keys.release(); c->win_keys2.release(); c->win_vals.release(); c->qorder.release(); c->tile_lo.release(); c->tile_hi.release(); c->win_tmp.release();
   c->wbuf.release(); c->f64pool.release(); c->cand.release(); c->cand_out.release(); c->pp_out.release();
   c->place_out.release(); c->n_calls.release(); c->counters.release(); c->tt_work.release();
@@ -593,8 +596,8 @@ extern "C" int pp_precompute(pp_ctx *c) {
     transpose_to_edge_major_kernel<double><<<grid, 256, 0, c->stream>>>(c->g.a[2], c->snT_a, c->n_nodes, c->K, c->L, c->Lp, c->Np, 1.0); LAUNCH_CHECK(c);
     dim3 grid_e((c->L + 31) / 32, (unsigned)(c->Np / 32), 1);
     transpose_to_edge_major_kernel<int32_t><<<grid_e, 256, 0, c->stream>>>(c->g.e[2], c->snT_e, c->n_nodes, 1, c->L, c->Lp, c->Np, 0); LAUNCH_CHECK(c);
-    c->tq_pend = c->mt_pend = c->lt_pend = c->ltq_pend = -1.0;
-    c->rep_ready = false; c->rep_mt_pend = c->rep_lt_pend = c->rep_ltq_pend = -1.0;
+    c->tq_pend = c->mt_pend = c->lt_pend = c->ltq_pend = c->ltq2_pend = -1.0;
+    c->rep_ready = false; c->rep_mt_pend = c->rep_lt_pend = c->rep_ltq_pend = c->rep_ltq2_pend = -1.0;
   }
   if (rc == PP_OK && ttw_supported(c) && c->eig_ok) {
     // engine 4 reads darr / parr in the eigenbasis of the rate matrix (threetax_eigen.cuh); without room for the two
@@ -849,6 +852,47 @@ static int launch_prefilter_qlane(pp_ctx *c, int64_t Q, double pend, int blocks_
   return PP_OK;
 }
 
+// pair-of-sites table (prefilter_qlane.cuh): the query-lane kernel with NC = 36 walking pairs of sites
+template <int W, int SPS, int NS, int MINB>
+static int launch_prefilter_qlane_pairs(pp_ctx *c, int64_t Q, double pend, int blocks_per_sm) {
+  int rc;
+  constexpr int NC = kQlPairCols;
+  using G = QlaneGeom<W, SPS, NS, NC>;
+  const int L2 = (c->L + 1) / 2;
+  SnT sn; sn.a = c->snT_a; sn.e = c->snT_e; sn.Np = c->Np; sn.L = c->L; sn.K = c->K; sn.n_nodes = c->n_nodes;
+  if (c->ltq2_pend != pend) {  // once per (reference, pendant length)
+    if ((rc = c->LTq2.ensure((size_t)L2 * c->Np * NC))) return rc;
+    for (int p0 = 0; p0 < L2; p0 += 65535) {
+      qlane_pair_table_kernel<16><<<dim3((unsigned)((c->Np + 127) / 128), std::min(65535, L2 - p0)), 128, 0, c->stream>>>(sn, c->tq5, c->LTq2.p, p0); LAUNCH_CHECK(c);
+    }
+    c->ltq2_pend = pend;
+  }
+  PreGeom g = prefilter_geometry(c, Q, 32, 1, W, blocks_per_sm);
+  g.sites_per_z = (L2 + g.zs - 1) / g.zs;             // the kernel's "sites" are pairs
+  g.zs = (L2 + g.sites_per_z - 1) / g.sites_per_z;
+  const int n4 = (L2 + 3) / 4;
+  if ((rc = c->tile_lo.ensure(g.nqt)) || (rc = c->tile_hi.ensure(g.nqt)) || (rc = c->tile_lo2.ensure(g.nqt)) || (rc = c->tile_hi2.ensure(g.nqt)) ||
+      (rc = c->qcol.ensure((size_t)g.nqt * n4 * 32)) || (rc = c->slow_flag.ensure(Q)))
+    return rc;
+  CK(cudaMemsetAsync(c->slow_flag.p, 0, sizeof(int32_t) * Q, c->stream));
+  tile_range_kernel<32><<<(g.nqt + 127) / 128, 128, 0, c->stream>>>(c->qsite.p, c->nq.p, c->qorder.p, (int)Q, g.nqt, c->Lp, c->tile_lo.p, c->tile_hi.p); LAUNCH_CHECK(c);
+  qlane_pair_ranges_kernel<<<(g.nqt + 127) / 128, 128, 0, c->stream>>>(c->tile_lo.p, c->tile_hi.p, g.nqt, c->tile_lo2.p, c->tile_hi2.p); LAUNCH_CHECK(c);
+  qlane_pair_pack_kernel<<<dim3((n4 + 7) / 8, g.nqt), 256, 0, c->stream>>>(c->codes.p, c->qorder.p, c->qcol.p, (int)Q, c->L, c->Lp, g.nqt, c->slow_flag.p); LAUNCH_CHECK(c);
+  PreArgs A;
+  if ((rc = prefilter_args(c, Q, g, &A))) return rc;
+  PreArgs A2 = A;                                       // the pair view the main kernel walks
+  A2.sn.L = L2; A2.tile_lo = c->tile_lo2.p; A2.tile_hi = c->tile_hi2.p;
+  const size_t sm = G::smem_bytes();
+  auto kern = prefilter_qlane_kernel<W, SPS, NS, MINB, NC, false>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  kern<<<dim3(g.gx, g.gy, g.zs), (W + 1) * 32, sm, c->stream>>>(A2, c->LTq2.p, c->qcol.p); LAUNCH_CHECK(c);
+  c->prefilter_kernel_used = 8;
+  if ((rc = prefilter_finish(c, Q, g))) return rc;
+  A.out = c->scores.p;
+  prefilter_qlane_fix_kernel<<<dim3((unsigned)Q, (c->n_nodes + 127) / 128), 128, 0, c->stream>>>(A, c->qsite.p, c->Lp, c->slow_flag.p, c->scores.p); LAUNCH_CHECK(c);
+  return PP_OK;
+}
+
 // the same form for the 20-state models (Gamma mixtures and Price-CAT): 22 columns (prefilter_qlane.cuh, second half)
 template <int S, bool G, int W, int SPS, int NS, int MINB>
 static int launch_prefilter_qlane_generic(pp_ctx *c, int64_t Q, double pend, int blocks_per_sm) {
@@ -937,6 +981,13 @@ static int run_prefilter(pp_ctx *c, int64_t Q, int kernel_choice, double pend) {
     // log-table form: one load + one add per (query, edge, site); measured (r4f) 11.8 ms against 9.9 ms for the product
     // table on C2 - it executes half the instructions but one L1 request per (query, site) instead of 5 per site
     // (ncu r4g: l1tex 77 %, long_scoreboard 6.4 warps per issue) - so it is selectable (6), not the default
+    // r5y: the pair-of-sites table is the default for large batches (C2 3.84 -> 2.90 ms, C4 42.7 -> 30.0 ms per 10k queries); PPB_PF_PAIRS=0
+    // goes back to one word per site (form 7), which is also what an out-of-memory table allocation falls back to
+    static const bool pairs_default = [] { const char *e = std::getenv("PPB_PF_PAIRS"); return !e || std::atoi(e) != 0; }();
+    if (kernel_choice == 8 || (kernel_choice == 0 && pairs_default && Q >= 256)) {
+      rc = launch_prefilter_qlane_pairs<8, 4, 4, 1>(c, Q, pend, 1);
+      if (!(rc == PP_ENOMEM && kernel_choice == 0)) return rc;
+    }
     if (kernel_choice == 7 || (kernel_choice == 0 && kQlaneDefault && Q >= 256)) {
       static const int qv = [] { const char *e = std::getenv("PPB_PFQ_VARIANT"); return e ? std::atoi(e) : 0; }();
       if (qv == 1) return launch_prefilter_qlane<4, 16, 4, 2>(c, Q, pend, 2);
@@ -1151,7 +1202,7 @@ extern "C" int pp_set_figs(pp_ctx *c, int32_t n_figs, const int32_t *rep, const 
   if (!c || n_figs < 0) return fail(PP_EINVAL, "pp_set_figs: bad arguments");
   CK(cudaSetDevice(c->device));
   c->fig_rep.clear(); c->fig_ptr.clear(); c->fig_idx.clear();
-  c->rep_ready = false; c->rep_mt_pend = c->rep_lt_pend = c->rep_ltq_pend = -1.0;
+  c->rep_ready = false; c->rep_mt_pend = c->rep_lt_pend = c->rep_ltq_pend = c->rep_ltq2_pend = -1.0;
   if (n_figs == 0) return PP_OK;  // Fig.Dummy: the plain ranking of every non-root edge
   if (!rep || !ptr || !idx || ptr[0] != 0) return fail(PP_EINVAL, "pp_set_figs: bad arguments");
   for (int f = 0; f < n_figs; ++f) {
@@ -1183,15 +1234,15 @@ static int run_prefilter_reps(pp_ctx *c, int64_t Q, int kernel_choice, double pe
   }
   // view swap: the prefilter launchers read the supernode arrays, the table caches and the score buffer from the context
   std::swap(c->snT_a, c->rep_a.p); std::swap(c->snT_e, c->rep_e.p); std::swap(c->Np, c->rep_Np);
-  std::swap(c->scores, c->rep_scores); std::swap(c->MT, c->rep_MT); std::swap(c->MTe, c->rep_MTe); std::swap(c->LT, c->rep_LT); std::swap(c->LTq, c->rep_LTq);
-  std::swap(c->mt_pend, c->rep_mt_pend); std::swap(c->lt_pend, c->rep_lt_pend); std::swap(c->ltq_pend, c->rep_ltq_pend);
+  std::swap(c->scores, c->rep_scores); std::swap(c->MT, c->rep_MT); std::swap(c->MTe, c->rep_MTe); std::swap(c->LT, c->rep_LT); std::swap(c->LTq, c->rep_LTq); std::swap(c->LTq2, c->rep_LTq2);
+  std::swap(c->mt_pend, c->rep_mt_pend); std::swap(c->lt_pend, c->rep_lt_pend); std::swap(c->ltq_pend, c->rep_ltq_pend); std::swap(c->ltq2_pend, c->rep_ltq2_pend);
   const int nn = c->n_nodes, root = c->root_id;
   c->n_nodes = m; c->root_id = -1;
   rc = run_prefilter(c, Q, kernel_choice, pend);
   c->n_nodes = nn; c->root_id = root;
   std::swap(c->snT_a, c->rep_a.p); std::swap(c->snT_e, c->rep_e.p); std::swap(c->Np, c->rep_Np);
-  std::swap(c->scores, c->rep_scores); std::swap(c->MT, c->rep_MT); std::swap(c->MTe, c->rep_MTe); std::swap(c->LT, c->rep_LT); std::swap(c->LTq, c->rep_LTq);
-  std::swap(c->mt_pend, c->rep_mt_pend); std::swap(c->lt_pend, c->rep_lt_pend); std::swap(c->ltq_pend, c->rep_ltq_pend);
+  std::swap(c->scores, c->rep_scores); std::swap(c->MT, c->rep_MT); std::swap(c->MTe, c->rep_MTe); std::swap(c->LT, c->rep_LT); std::swap(c->LTq, c->rep_LTq); std::swap(c->LTq2, c->rep_LTq2);
+  std::swap(c->mt_pend, c->rep_mt_pend); std::swap(c->lt_pend, c->rep_lt_pend); std::swap(c->ltq_pend, c->rep_ltq_pend); std::swap(c->ltq2_pend, c->rep_ltq2_pend);
   return rc;
 }
 
@@ -1571,9 +1622,9 @@ extern "C" int pp_set_stream(pp_ctx *c, void *cuda_stream) {
 }
 
 extern "C" int pp_set_prefilter_kernel(pp_ctx *c, int32_t kernel) {
-  if (!c || kernel < 0 || kernel > 7) return fail(PP_EINVAL, "pp_set_prefilter_kernel: kernel must be 0 ... 7");
+  if (!c || kernel < 0 || kernel > 8) return fail(PP_EINVAL, "pp_set_prefilter_kernel: kernel must be 0 ... 8");
   const bool dna4 = c->S == 4 && !c->gcat && c->K == 16;
-  if ((kernel == 2 || (kernel >= 4 && kernel <= 6)) && !dna4) return fail(PP_EINVAL, "pp_set_prefilter_kernel: the table and staged forms exist for the DNA Gamma-4 model only");
+  if ((kernel == 2 || (kernel >= 4 && kernel <= 6) || kernel == 8) && !dna4) return fail(PP_EINVAL, "pp_set_prefilter_kernel: the table and staged forms exist for the DNA Gamma-4 model only");
 
   c->prefilter_choice = kernel;
   return PP_OK;

@@ -209,6 +209,98 @@ prefilter_qlane_fix_kernel(const PreArgs A, const int32_t *__restrict__ qsite, i
 
 
 // ---------------------------------------------------------------------------------------------------------------
+// Pair-of-sites table (DNA Gamma-4, r5y).  ncu r5b and the r5x layout experiment: the query-lane form is bound by the
+// BYTES the shared-memory pipe delivers to the lanes - 128 B per clock per SM, one 8-byte word per (query, edge, site)
+// unit - not by requests or bank conflicts.  So two adjacent sites share one word:
+//     LT2[et][pair][e][c1 * 6 + c2] = LT[2 pair][e][c1] + LT[2 pair + 1][e][c2]        (36 columns, column 35 = 0)
+// and the same kernel (prefilter_qlane_kernel<..., NC = 36>) walks PAIRS: half the loads and half the additions per
+// unit for three times the table (C4: 2.2 GB).  The pairwise sums reassociate the reference's sum of logs; -inf and
+// NaN still propagate through plain additions.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kQlPairCols = 36;
+
+// one thread per (pair, edge): the five log columns of both sites, then the 36 sums
+template <int K>
+__global__ void __launch_bounds__(128)
+qlane_pair_table_kernel(const SnT sn, const TqFive tp, double *__restrict__ LT2, int pair0) {
+  const int64_t Np = sn.Np;
+  const int e = blockIdx.x * 128 + threadIdx.x;
+  const int pair = pair0 + blockIdx.y;
+  if (e >= Np) return;
+  double lg[2][6];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int site = 2 * pair + h;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) lg[h][j] = 0.0;
+    if (site < sn.L) {
+      const double *col = sn.a + ((int64_t)site * K) * Np + e;
+      double v[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) v[k] = __ldg(col + (int64_t)k * Np);
+      const double ex = kLn2 * (double)__ldg(sn.e + (int64_t)site * Np + e);
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        double lo = tp.v[j][0] * v[0], hi = tp.v[j][K / 2] * v[K / 2];
+#pragma unroll
+        for (int k = 1; k < K / 2; ++k) { lo = fma(tp.v[j][k], v[k], lo); hi = fma(tp.v[j][K / 2 + k], v[K / 2 + k], hi); }
+        lg[h][j] = log(lo + hi) + ex;
+      }
+    }
+  }
+  const int n_pairs = (sn.L + 1) / 2;
+  double *dst = LT2 + (((int64_t)(e / kQlEdges) * n_pairs + pair) * kQlEdges + (e % kQlEdges)) * kQlPairCols;
+#pragma unroll
+  for (int c1 = 0; c1 < 6; ++c1)
+#pragma unroll
+    for (int c2 = 0; c2 < 6; ++c2) dst[c1 * 6 + c2] = lg[0][c1] + lg[1][c2];
+}
+
+// column bytes per PAIR, four pairs per word: byte = c1 * 6 + c2 (c = 5: uninformative, pad, ambiguity code -> fix kernel)
+__global__ void __launch_bounds__(256)
+qlane_pair_pack_kernel(const uint8_t *__restrict__ codes, const int32_t *__restrict__ order, uint32_t *__restrict__ qcol, int Q, int L,
+                       int64_t Lp, int n_groups, int32_t *__restrict__ slow_flag) {
+  const int p4 = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, grp = blockIdx.y;
+  const int n_pairs = (L + 1) / 2, n4 = (n_pairs + 3) / 4;
+  if (p4 >= n4) return;
+  const int slot = grp * 32 + lane;
+  uint32_t w = 0x01010101u * (kQlPairCols - 1);
+  if (slot < Q) {
+    const int q = order[slot];
+    const uint8_t *row = codes + (int64_t)q * Lp;
+    w = 0;
+    bool slow = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      unsigned cc[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int site = (p4 * 4 + j) * 2 + h;
+        unsigned c = 5;
+        if (site < L) {
+          const unsigned code = row[site];
+          if (!(code & 0x80u)) {
+            c = (unsigned)(kLogColOfCode >> (4 * (code & 15u))) & 15u;
+            if (c == 15u) { c = 5; slow = true; }
+          }
+        }
+        cc[h] = c;
+      }
+      w |= (cc[0] * 6 + cc[1]) << (8 * j);
+    }
+    if (slow) slow_flag[q] = 1;
+  }
+  qcol[((int64_t)grp * n4 + p4) * 32 + lane] = w;
+}
+
+// tile windows in pair units
+__global__ void qlane_pair_ranges_kernel(const int32_t *__restrict__ lo, const int32_t *__restrict__ hi, int n, int32_t *__restrict__ lo2,
+                                         int32_t *__restrict__ hi2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { lo2[i] = lo[i] >> 1; hi2[i] = (hi[i] + 1) >> 1; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // The same form for any alphabet and model class (proteins, DNA with Price-CAT or a Gamma mixture other than four
 // rates): NC = S + 2 columns - one per state, one for the "any" code (X / N: informative in the reference,
 // alignment.ml:235), and a zero column (uninformative sites, pad lanes, the other multi-state codes).

@@ -28,6 +28,7 @@ PROBLEMS = {
     "zero_cat": lambda: configs.synthetic(1500, 48, 6, seed=9, alpha=0.5, mean_bl=0.12, min_len=30),
 }
 _cache = {}
+DEFAULT_BIG = 7 if os.environ.get("PPB_PF_PAIRS", "1") == "0" else 8   # prefilter form of DNA Gamma-4 batches of >= 256 queries
 PP_KEEP = dict(keep_factor=0.001, keep_at_most=20)     # what -p sets (prefs.ml:198-203)
 
 
@@ -116,7 +117,7 @@ def test_prefilter_scores_and_ranking_match_oracle(oracle_binding, name):
             assert a == b or abs(w[q][a] - w[q][b]) <= 1e-9 * abs(w[q][a]), (q, a, b)
 
 
-@pytest.mark.parametrize("name,kernel", [(n, k) for n in ("c1_gtr", "synth", "zero_cat") for k in (1, 2, 3, 4, 5, 6, 7)])
+@pytest.mark.parametrize("name,kernel", [(n, k) for n in ("c1_gtr", "synth", "zero_cat") for k in (1, 2, 3, 4, 5, 6, 7, 8)])
 def test_prefilter_kernel_variants_match_oracle(oracle_binding, name, kernel):
     """The direct FMA form (1: evolved-query table in the constant bank, 3: in shared memory), the
     four-base table form (2) and the staged forms (TMA bulk copies + mbarrier ring; 4: FMA, 5: FP64 tensor
@@ -125,7 +126,7 @@ def test_prefilter_kernel_variants_match_oracle(oracle_binding, name, kernel):
     _, _, st, info = o.place(prob.query_chars, oracle_prefs(oracle_binding, prob), n_threads=4, debug=True)
     want = info["scores"]
     got = p.prefilter_scores(prob.query_chars, kernel=kernel)
-    assert p.prefilter_kernel_used() == {1: 1, 2: 2, 3: 1, 4: 4, 5: 5, 6: 6, 7: 7}[kernel]
+    assert p.prefilter_kernel_used() == {1: 1, 2: 2, 3: 1, 4: 4, 5: 5, 6: 6, 7: 7, 8: 8}[kernel]
     root = prob.tree.root
     keep = [i for i in range(prob.tree.n_nodes) if i != root]
     g, w = got[:, keep], want[:, keep]
@@ -162,7 +163,7 @@ def test_prefilter_many_queries_matches_few_query_kernels(oracle_binding):
     q = prob.query_chars
     big = np.concatenate([q, q, q[:17]], axis=0)
     assert big.shape[0] > 64
-    for kernel in (0, 1, 2, 3, 4, 5, 6, 7):
+    for kernel in (0, 1, 2, 3, 4, 5, 6, 7, 8):
         a = p.prefilter_scores(q, kernel=kernel)
         b = p.prefilter_scores(big, kernel=kernel)
         for lo in (0, q.shape[0]):
@@ -418,15 +419,18 @@ def test_c4_shape_matches_oracle(oracle_binding):
         assert p.rank_fallbacks() == 0
         direct = p.prefilter_scores(prob.query_chars[:8], kernel=1)
         staged = [p.prefilter_scores(prob.query_chars[:8], kernel=k) for k in (6, 4, 5)]
-        qlane = p.prefilter_scores(prob.query_chars, kernel=7)   # the form large batches use (313 edge tiles, 720 MB table)
+        qlane = p.prefilter_scores(prob.query_chars, kernel=7)   # the forms large batches use (313 edge tiles, 720 MB / 2.2 GB tables)
         assert p.prefilter_kernel_used() == 7
+        qpair = p.prefilter_scores(prob.query_chars, kernel=8)
+        assert p.prefilter_kernel_used() == 8
     root = prob.tree.root
     keep = np.array([i for i in range(prob.tree.n_nodes) if i != root])
     g, w = gi["scores"][:, keep], oi["scores"][:, keep]
     assert np.isfinite(w).all()
     assert np.all(np.abs(g - w) <= 1e-10 * np.abs(w)), np.abs((g - w) / w).max()
-    assert np.isnan(qlane[:, root]).all()
-    assert np.all(np.abs(qlane[:, keep] - w) <= 1e-10 * np.abs(w)), np.abs((qlane[:, keep] - w) / w).max()
+    for t in (qlane, qpair):
+        assert np.isnan(t[:, root]).all()
+        assert np.all(np.abs(t[:, keep] - w) <= 1e-10 * np.abs(w)), np.abs((t[:, keep] - w) / w).max()
     for d in [direct] + staged:
         d = d[:, keep]
         assert np.all(np.abs(d - w[:8]) <= 1e-10 * np.abs(w[:8])), np.abs((d - w[:8]) / w[:8]).max()
@@ -448,9 +452,9 @@ def test_c2_prefilter_forms_agree(c2_small):
     keep = np.array([i for i in range(prob.tree.n_nodes) if i != prob.tree.root])
     assert np.isfinite(ref[:, keep]).all() and np.isnan(ref[:, prob.tree.root]).all()
     assert p.prefilter_kernel_used() == 1
-    for kernel in (0, 2, 6, 7, 4, 5):
+    for kernel in (0, 2, 6, 7, 8, 4, 5):
         got = p.prefilter_scores(q, kernel=kernel)
-        assert p.prefilter_kernel_used() == (7 if kernel == 0 else kernel)   # >= 256 queries: the query-lane log table is the default
+        assert p.prefilter_kernel_used() == (DEFAULT_BIG if kernel == 0 else kernel)   # >= 256 queries: a query-lane log table is the default
         assert np.isnan(got[:, prob.tree.root]).all()
         d = np.abs(got[:, keep] - ref[:, keep])
         assert np.all(d <= 1e-11 * np.abs(ref[:, keep])), (kernel, float((d / np.abs(ref[:, keep])).max()))
@@ -732,7 +736,7 @@ def test_fig_ranking_at_the_c2_shape(c2_small, oracle_binding):
         got, n_got, st_got, gi = p.place(q, p.prefs(), debug=True)
     finally:
         p.set_figs(None)
-    assert p.prefilter_kernel_used() == 7
+    assert p.prefilter_kernel_used() == DEFAULT_BIG
     near = assert_placements_match(got, n_got, st_got, exp, n_exp, st_exp, near_tie_ll=1e-3)
     assert len(near_queries(near)) <= 5, near
     assert (np.isfinite(gi["scores"]) == np.isfinite(oi["scores"])).all(axis=1).mean() >= 0.97
